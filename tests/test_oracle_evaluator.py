@@ -1,0 +1,159 @@
+"""Oracle pinning, part 2: evaluator primitives.
+
+(a) switch_key / rescale of the C oracle against an independent big-integer restatement
+    of SURVEY.md 9.6 / 9.7 (tests/ckks_ref.py) at toy sizes, bit-exact;
+(b) homomorphic correctness after decryption against float64 numpy at the reference's
+    parameter sets (matrix_operations.cpp:1048-1052)."""
+import numpy as np
+import pytest
+
+import ckks_ref as ref
+from oracle import oracle as orc
+
+
+def _rand_poly(rng, moduli, shape_prefix, n):
+    out = np.empty(tuple(shape_prefix) + (len(moduli), n), dtype=np.uint64)
+    for i, q in enumerate(moduli):
+        out[..., i, :] = rng.integers(0, q, size=tuple(shape_prefix) + (n,), dtype=np.uint64)
+    return out
+
+
+@pytest.mark.parametrize("bits,L", [([30, 25, 28, 30], 3), ([30, 25, 28, 30], 2), ([20, 30, 25], 2), ([30, 30], 1)])
+def test_switch_key_and_rescale_vs_bigint(bits, L):
+    n = 16
+    moduli = orc.coeff_modulus_create(n, bits)
+    K = len(moduli)
+    o = orc.Oracle(n, moduli)
+    psis = [o.psi(i) for i in range(K)]
+    rng = np.random.default_rng(7)
+    ct = _rand_poly(rng, moduli[:L], (2,), n)
+    target = _rand_poly(rng, moduli[:L], (), n)
+    key = _rand_poly(rng, moduli, (K - 1, 2), n)
+    got = o.switch_key(ct, target, key)
+    want = ref.switch_key_ref(ct.tolist(), target.tolist(), key.tolist(), moduli, psis, L)
+    assert got.tolist() == want
+    if L >= 2:
+        ct3 = _rand_poly(rng, moduli[:L], (3,), n)
+        assert o.rescale(ct3).tolist() == ref.rescale_ref(ct3.tolist(), moduli, psis, L)
+        assert np.array_equal(o.mod_switch(ct3), ct3[:, : L - 1, :])
+
+
+@pytest.fixture(scope="module")
+def setup8192():
+    n = 8192
+    moduli = orc.coeff_modulus_create(n, [60, 40, 40, 60])
+    o = orc.Oracle(n, moduli)
+    enc = ref.Encoder(n, moduli, o.ntt_fwd, o.ntt_inv)
+    s = o.sample_secret(1234)
+    return n, moduli, o, enc, s
+
+
+def test_encrypt_decrypt_roundtrip(setup8192):
+    n, moduli, o, enc, s = setup8192
+    rng = np.random.default_rng(0)
+    z = rng.uniform(-1, 1, n // 2) + 1j * rng.uniform(-1, 1, n // 2)
+    scale = 2.0**40
+    pt = enc.encode(z, scale, 3)
+    assert np.max(np.abs(enc.decode(pt, scale) - z)) < 1e-9
+    ct = o.encrypt_symmetric(99, s, pt)
+    dec = enc.decode(o.decrypt(ct, s), scale)
+    assert np.max(np.abs(dec - z)) < 1e-7
+
+
+def test_homomorphic_ops(setup8192):
+    n, moduli, o, enc, s = setup8192
+    rng = np.random.default_rng(1)
+    slots = n // 2
+    scale = 2.0**40
+    x = rng.uniform(-1, 1, slots)
+    y = rng.uniform(-1, 1, slots)
+    ptx, pty = enc.encode(x, scale, 3), enc.encode(y, scale, 3)
+    cx, cy = o.encrypt_symmetric(1, s, ptx), o.encrypt_symmetric(2, s, pty)
+    rk = o.gen_relin_key(3, s)
+
+    def dec(ct, sc):
+        return enc.decode(o.decrypt(ct, s), sc).real
+
+    assert np.max(np.abs(dec(o.add(cx, cy), scale) - (x + y))) < 1e-7
+    assert np.max(np.abs(dec(o.sub(cx, cy), scale) - (x - y))) < 1e-7
+    assert np.max(np.abs(dec(o.negate(cx), scale) + x)) < 1e-7
+    assert np.max(np.abs(dec(o.add_plain(cx, pty), scale) - (x + y))) < 1e-7
+    assert np.max(np.abs(dec(o.sub_plain(cx, pty), scale) - (x - y))) < 1e-7
+    # multiply_plain + rescale
+    mp = o.rescale(o.multiply_plain(cx, pty))
+    assert np.max(np.abs(dec(mp, scale * scale / moduli[2]) - x * y)) < 1e-6
+    # multiply (size 3 decrypts), relinearize, rescale
+    m3 = o.multiply(cx, cy)
+    assert m3.shape[0] == 3
+    assert np.max(np.abs(dec(m3, scale * scale) - x * y)) < 1e-6
+    m2 = o.relinearize(m3, rk)
+    assert np.max(np.abs(dec(m2, scale * scale) - x * y)) < 1e-6
+    r = o.rescale(m2)
+    assert np.max(np.abs(dec(r, scale * scale / moduli[2]) - x * y)) < 1e-6
+    # square == multiply(a, a); size-3 add/sub semantics
+    assert np.array_equal(o.square(cx), o.multiply(cx, cx))
+    a23 = o.add(cx, m3)
+    assert np.array_equal(a23[2], m3[2])
+    s23 = o.sub(cx, m3)
+    assert np.array_equal(s23[2], o.negate(m3)[2])
+
+
+def test_rotation_and_naf(setup8192):
+    n, moduli, o, enc, s = setup8192
+    rng = np.random.default_rng(2)
+    slots = n // 2
+    scale = 2.0**40
+    x = rng.uniform(-1, 1, slots)
+    cx = o.encrypt_symmetric(5, s, enc.encode(x, scale, 3))
+    gk = o.gen_galois_keys_for_steps(100, s, [1, 2, 4, 8, -1, -2, 16])
+
+    def dec(ct):
+        return enc.decode(o.decrypt(ct, s), scale).real
+
+    r1, nks = o.rotate(cx, 1, gk)
+    assert nks == 1
+    assert np.max(np.abs(dec(r1) - np.roll(x, -1))) < 1e-6
+    r7, nks = o.rotate(cx, 7, gk)  # NAF 7 = [-1, 8]
+    assert nks == 2
+    assert np.max(np.abs(dec(r7) - np.roll(x, -7))) < 1e-6
+    # NAF order is part of the contract: rotate(7) == rotate(rotate(ct,-1), 8)
+    step_a, _ = o.rotate(cx, -1, gk)
+    step_b, _ = o.rotate(step_a, 8, gk)
+    assert np.array_equal(r7, step_b)
+    r0, nks = o.rotate(cx, 0, gk)
+    assert nks == 0 and np.array_equal(r0, cx)
+    with pytest.raises(ValueError):
+        o.rotate(cx, 32, gk)  # single-term NAF without a key
+    # lower level (after a rescale) uses the same keys
+    low = o.rescale(o.multiply_plain(cx, enc.encode_scalar(1.0, scale, 3)))
+    r, _ = o.rotate(low, 2, gk)
+    d = enc.decode(o.decrypt(r, s), scale * scale / moduli[2]).real
+    assert np.max(np.abs(d - np.roll(x, -2))) < 1e-6
+
+
+def test_matvec_bsgs_decrypts_to_matvec():
+    n = 8192
+    moduli = orc.coeff_modulus_create(n, [60, 40, 40, 60])
+    o = orc.Oracle(n, moduli)
+    enc = ref.Encoder(n, moduli, o.ntt_fwd, o.ntt_inv)
+    s = o.sample_secret(77)
+    rng = np.random.default_rng(3)
+    dim, n1, n2 = 16, 4, 4
+    slots = n // 2
+    scale = 2.0**40
+    M = rng.uniform(-1, 1, (dim, dim))
+    v = rng.uniform(-1, 1, dim)
+    vrep = np.tile(v, slots // dim)
+    ct = o.encrypt_symmetric(8, s, enc.encode(vrep, scale, 3))
+    pts = np.empty((dim, 3, n), dtype=np.uint64)
+    for g in range(n2):
+        for b in range(n1):
+            d = g * n1 + b
+            diag = np.array([M[r, (r + d) % dim] for r in range(dim)])
+            pts[d] = enc.encode(np.roll(np.tile(diag, slots // dim), g * n1), scale, 3)
+    bk = [None] + [o.gen_galois_key(200 + b, s, orc.galois_elt_from_step(n, b)) for b in range(1, n1)]
+    gkeys = [None] + [o.gen_galois_key(300 + g, s, orc.galois_elt_from_step(n, g * n1)) for g in range(1, n2)]
+    out = o.matvec_bsgs(ct[None], n1, n2, pts, bk, gkeys, threads=2)
+    got = enc.decode(o.decrypt(out[0], s), scale * scale / moduli[2]).real[:dim]
+    tol = 8 * np.sqrt(dim) * 2.0 ** -(40 - 16)  # CKKS scale-derived tolerance
+    assert np.max(np.abs(got - M @ v)) < tol
