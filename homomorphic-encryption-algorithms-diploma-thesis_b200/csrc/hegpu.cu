@@ -1,0 +1,1430 @@
+// hegpu.cu -- host side of libhegpu.so: context/tables, device handles, the C ABI of
+// include/hegpu.h and the composites that stay on the device.  No CPU arithmetic on
+// ciphertext data happens here; the host only builds constant tables and launches kernels.
+#include "../../include/hegpu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace hegpu;
+
+// ------------------------------------------------------------------------- errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CU(expr)                                                                                  \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            if (_e == cudaErrorMemoryAllocation) return fail(HEGPU_ERR_OUT_OF_MEMORY, std::string("out of device memory: ") + #expr); \
+            return fail(HEGPU_ERR_CUDA, std::string(cudaGetErrorString(_e)) + " at " + #expr);    \
+        }                                                                                         \
+    } while (0)
+#define TRY(expr)                 \
+    do {                          \
+        int _s = (expr);          \
+        if (_s != HEGPU_OK) return _s; \
+    } while (0)
+#define INVALID(msg) return fail(HEGPU_ERR_INVALID_ARGUMENT, msg)
+#define LOGIC(msg) return fail(HEGPU_ERR_LOGIC, msg)
+
+extern "C" const char *hegpu_last_error(void) { return g_err.c_str(); }
+extern "C" const char *hegpu_version(void) { return "hegpu 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------- host number theory
+typedef unsigned __int128 u128;
+static u64 h_mulmod(u64 a, u64 b, u64 q) { return (u64)(((u128)a * b) % q); }
+static u64 h_powmod(u64 a, u64 e, u64 q)
+{
+    u64 r = 1;
+    a %= q;
+    while (e) {
+        if (e & 1) r = h_mulmod(r, a, q);
+        a = h_mulmod(a, a, q);
+        e >>= 1;
+    }
+    return r;
+}
+static u64 h_invmod(u64 a, u64 q) { return h_powmod(a, q - 2, q); }
+static u64 h_shoup(u64 w, u64 q) { return (u64)(((u128)w << 64) / q); }
+static bool h_is_prime(u64 n)
+{
+    if (n < 2) return false;
+    static const u64 sp[] = { 2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37 };
+    for (u64 p : sp) {
+        if (n == p) return true;
+        if (n % p == 0) return false;
+    }
+    u64 d = n - 1;
+    int r = 0;
+    while (!(d & 1)) { d >>= 1; ++r; }
+    for (u64 a : sp) {
+        u64 x = h_powmod(a, d, n);
+        if (x == 1 || x == n - 1) continue;
+        bool comp = true;
+        for (int j = 1; j < r; ++j) {
+            x = h_mulmod(x, x, n);
+            if (x == n - 1) { comp = false; break; }
+        }
+        if (comp) return false;
+    }
+    return true;
+}
+static u32 h_brev(u32 x, u32 bits)
+{
+    u32 r = 0;
+    for (u32 i = 0; i < bits; ++i) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
+// the numerically smallest primitive 2N-th root of unity (SEAL try_minimal_primitive_root)
+static u64 h_min_root(u64 q, u32 n)
+{
+    const u64 e = (q - 1) / (2ull * n);
+    u64 root = 0;
+    for (u64 g = 2;; ++g) {
+        u64 r = h_powmod(g, e, q);
+        if (h_powmod(r, n, q) == q - 1) { root = r; break; }
+    }
+    const u64 sq = h_mulmod(root, root, q);
+    u64 cur = root, best = root;
+    for (u32 i = 0; i < n; ++i) {
+        best = std::min(best, cur);
+        cur = h_mulmod(cur, sq, q);
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------------- objects
+struct Arena {  // grow-only device scratch, bump-allocated per API call
+    char *base = nullptr;
+    size_t cap = 0, off = 0;
+};
+
+struct hegpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    u32 n = 0, logn = 0, K = 0;
+    std::vector<u64> q, psi;
+    std::vector<int> level_bits;  // total_coeff_modulus_bit_count for L = 1..K
+    // device tables
+    ulonglong2 *d_fwd = nullptr, *d_inv = nullptr, *d_inv_last = nullptr;
+    ModConst *d_mods = nullptr;
+    MdConst *d_md = nullptr;  // [K][K]: row d = dropped modulus, column i = target limb
+    NttTables tabs{};
+    // keys
+    u64 *relin_key = nullptr;
+    std::map<u32, u64 *> galois_keys;
+    std::map<u32, u32 *> perms;
+    Arena arena;
+    u64 *stage = nullptr;  // host<->device staging
+    size_t stage_words = 0;
+    u64 launches = 0;
+    int sms = 148;
+    size_t ws_budget = (size_t)24 << 30;  // scratch budget per composite chunk
+};
+
+struct hegpu_ct {
+    hegpu_ctx *ctx;
+    u64 *d;
+    u32 batch, size_cap, L_cap;
+    u32 size, L;
+    double scale;
+    CtView view() const { return CtView{ d, (size_t)size_cap * L_cap * ctx->n, (size_t)L_cap * ctx->n, (size_t)ctx->n }; }
+    CtView view_at(u32 b0) const
+    {
+        CtView v = view();
+        v.p += b0 * v.sb;
+        return v;
+    }
+};
+
+struct hegpu_pt {
+    hegpu_ctx *ctx;
+    u64 *d;
+    u32 count, L_cap, L;
+    double scale;
+    size_t stride() const { return (size_t)L_cap * ctx->n; }
+};
+
+static int set_device(hegpu_ctx *c)
+{
+    CU(cudaSetDevice(c->device));
+    return HEGPU_OK;
+}
+
+static int arena_reserve(hegpu_ctx *c, size_t bytes)
+{
+    if (bytes <= c->arena.cap) return HEGPU_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->arena.base) CU(cudaFree(c->arena.base));
+    c->arena.base = nullptr;
+    c->arena.cap = 0;
+    size_t want = bytes + (bytes >> 3);
+    CU(cudaMalloc(&c->arena.base, want));
+    c->arena.cap = want;
+    return HEGPU_OK;
+}
+struct ArenaPlan {  // first pass sizes the scratch, second pass hands out pointers
+    hegpu_ctx *c;
+    size_t off = 0;
+    u64 *take(size_t words)
+    {
+        size_t bytes = (words * sizeof(u64) + 255) & ~(size_t)255;
+        u64 *p = (u64 *)(c->arena.base + off);
+        off += bytes;
+        return p;
+    }
+};
+static inline size_t align256(size_t words) { return ((words * sizeof(u64) + 255) & ~(size_t)255); }
+
+static int stage_reserve(hegpu_ctx *c, size_t words)
+{
+    if (words <= c->stage_words) return HEGPU_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->stage) CU(cudaFree(c->stage));
+    c->stage = nullptr;
+    c->stage_words = 0;
+    CU(cudaMalloc(&c->stage, words * sizeof(u64)));
+    c->stage_words = words;
+    return HEGPU_OK;
+}
+
+static inline int ew_grid(hegpu_ctx *c, size_t total)
+{
+    size_t blocks = (total + 255) / 256;
+    size_t cap = (size_t)c->sms * 16;
+    return (int)std::max<size_t>(1, std::min(blocks, cap));
+}
+
+// ------------------------------------------------------------------------- context
+extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *moduli, uint32_t K, int device)
+{
+    if (!out || !moduli) INVALID("null argument");
+    if (n != 4096 && n != 8192 && n != 16384 && n != 32768) INVALID("poly_modulus_degree must be 4096, 8192, 16384 or 32768");
+    if (K < 1 || K > 62) INVALID("coeff_modulus size out of range");
+    int ndev = 0;
+    cudaError_t de = cudaGetDeviceCount(&ndev);
+    if (de != cudaSuccess || ndev == 0)
+        return fail(HEGPU_ERR_CUDA, "no CUDA device: libhegpu has no CPU fallback");
+    if (device < 0 || device >= ndev) INVALID("invalid device ordinal");
+    for (u32 i = 0; i < K; ++i) {
+        if (moduli[i] >> 60) INVALID("coeff_modulus primes must be at most 60 bits");
+        if (!h_is_prime(moduli[i]) || (moduli[i] - 1) % (2ull * n)) INVALID("coeff_modulus primes must be prime and = 1 mod 2N");
+        for (u32 j = 0; j < i; ++j)
+            if (moduli[i] == moduli[j]) INVALID("coeff_modulus primes must be distinct");
+    }
+    hegpu_ctx *c = new hegpu_ctx();
+    c->device = device;
+    c->n = n;
+    c->K = K;
+    while ((1u << c->logn) < n) c->logn++;
+    c->q.assign(moduli, moduli + K);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+
+    // bit counts of q_0..q_{L-1} products (SEAL total_coeff_modulus_bit_count)
+    {
+        std::vector<u64> big(1, 1);
+        for (u32 i = 0; i < K; ++i) {
+            u64 carry = 0;
+            for (auto &w : big) {
+                u128 t = (u128)w * c->q[i] + carry;
+                w = (u64)t;
+                carry = (u64)(t >> 64);
+            }
+            if (carry) big.push_back(carry);
+            int bits = (int)(big.size() - 1) * 64 + (64 - __builtin_clzll(big.back()));
+            c->level_bits.push_back(bits);
+        }
+    }
+
+    std::vector<ulonglong2> fwd((size_t)K * n), inv((size_t)K * n), inv_last(K);
+    std::vector<ModConst> mods(K);
+    std::vector<MdConst> md((size_t)K * K);
+    for (u32 i = 0; i < K; ++i) {
+        const u64 q = c->q[i];
+        const u64 psi = h_min_root(q, n), ipsi = h_invmod(psi, q);
+        c->psi.push_back(psi);
+        u64 p = 1, ip = 1;
+        for (u32 k = 0; k < n; ++k) {
+            const u32 r = h_brev(k, c->logn);
+            fwd[(size_t)i * n + r] = make_ulonglong2(p, h_shoup(p, q));
+            inv[(size_t)i * n + r] = make_ulonglong2(ip, h_shoup(ip, q));
+            p = h_mulmod(p, psi, q);
+            ip = h_mulmod(ip, ipsi, q);
+        }
+        ModConst &m = mods[i];
+        m.q = q;
+        u128 mu = (~(u128)0) / q;  // floor((2^128-1)/q) == floor(2^128/q) for odd q > 1
+        m.mu_hi = (u64)(mu >> 64);
+        m.mu_lo = (u64)mu;
+        m.ninv = h_invmod(n % q, q);
+        m.ninv_sh = h_shoup(m.ninv, q);
+        m.big = (q >> 58 ? 1u : 0u) | (q >> 46 ? 2u : 0u);
+        m.pad = 0;
+        const u64 wl = h_mulmod(inv[(size_t)i * n + 1].x, m.ninv, q);
+        inv_last[i] = make_ulonglong2(wl, h_shoup(wl, q));
+        for (u32 d = 0; d < K; ++d) {
+            MdConst &e = md[(size_t)d * K + i];
+            e.pad = 0;
+            if (d == i) { e.inv = e.inv_sh = e.halfmod = 0; continue; }
+            e.inv = h_invmod(c->q[d] % q, q);
+            e.inv_sh = h_shoup(e.inv, q);
+            e.halfmod = (c->q[d] >> 1) % q;
+        }
+    }
+    CU(cudaMalloc(&c->d_fwd, fwd.size() * sizeof(ulonglong2)));
+    CU(cudaMalloc(&c->d_inv, inv.size() * sizeof(ulonglong2)));
+    CU(cudaMalloc(&c->d_inv_last, inv_last.size() * sizeof(ulonglong2)));
+    CU(cudaMalloc(&c->d_mods, mods.size() * sizeof(ModConst)));
+    CU(cudaMalloc(&c->d_md, md.size() * sizeof(MdConst)));
+    CU(cudaMemcpy(c->d_fwd, fwd.data(), fwd.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_inv, inv.data(), inv.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_inv_last, inv_last.data(), inv_last.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_mods, mods.data(), mods.size() * sizeof(ModConst), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_md, md.data(), md.size() * sizeof(MdConst), cudaMemcpyHostToDevice));
+    c->tabs.fwd = c->d_fwd;
+    c->tabs.inv = c->d_inv;
+    c->tabs.inv_last = c->d_inv_last;
+    c->tabs.mods = c->d_mods;
+    c->tabs.n = n;
+    c->tabs.logn = c->logn;
+    *out = c;
+    return HEGPU_OK;
+}
+
+extern "C" int hegpu_ctx_destroy(hegpu_ctx *c)
+{
+    if (!c) return HEGPU_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_fwd);
+    cudaFree(c->d_inv);
+    cudaFree(c->d_inv_last);
+    cudaFree(c->d_mods);
+    cudaFree(c->d_md);
+    cudaFree(c->relin_key);
+    for (auto &kv : c->galois_keys) cudaFree(kv.second);
+    for (auto &kv : c->perms) cudaFree(kv.second);
+    cudaFree(c->arena.base);
+    cudaFree(c->stage);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return HEGPU_OK;
+}
+
+extern "C" int hegpu_sync(hegpu_ctx *c)
+{
+    if (!c) INVALID("null context");
+    TRY(set_device(c));
+    CU(cudaStreamSynchronize(c->stream));
+    return HEGPU_OK;
+}
+extern "C" void *hegpu_ctx_stream(hegpu_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" uint64_t hegpu_ctx_psi(hegpu_ctx *c, uint32_t i) { return (c && i < c->K) ? c->psi[i] : 0; }
+extern "C" uint64_t hegpu_launch_count(hegpu_ctx *c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------- keys
+static size_t key_words(hegpu_ctx *c) { return (size_t)(c->K - 1) * 2 * c->K * c->n; }
+
+extern "C" int hegpu_load_relin_key(hegpu_ctx *c, const uint64_t *host)
+{
+    if (!c || !host) INVALID("null argument");
+    if (c->K < 2) LOGIC("keyswitching is not supported by the context");
+    TRY(set_device(c));
+    if (!c->relin_key) CU(cudaMalloc(&c->relin_key, key_words(c) * sizeof(u64)));
+    CU(cudaMemcpyAsync(c->relin_key, host, key_words(c) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return HEGPU_OK;
+}
+
+// GaloisTool::generate_table_ntt
+static int get_perm(hegpu_ctx *c, u32 elt, const u32 **out)
+{
+    auto it = c->perms.find(elt);
+    if (it != c->perms.end()) { *out = it->second; return HEGPU_OK; }
+    std::vector<u32> tab(c->n);
+    for (u32 i = 0; i < c->n; ++i) {
+        u64 r = 2ull * h_brev(i, c->logn) + 1;
+        u64 raw = ((u64)elt * r) >> 1;
+        tab[i] = h_brev((u32)(raw & (c->n - 1)), c->logn);
+    }
+    u32 *d = nullptr;
+    CU(cudaMalloc(&d, c->n * sizeof(u32)));
+    CU(cudaMemcpy(d, tab.data(), c->n * sizeof(u32), cudaMemcpyHostToDevice));
+    c->perms[elt] = d;
+    *out = d;
+    return HEGPU_OK;
+}
+
+extern "C" int hegpu_load_galois_key(hegpu_ctx *c, uint32_t elt, const uint64_t *host)
+{
+    if (!c || !host) INVALID("null argument");
+    if (c->K < 2) LOGIC("keyswitching is not supported by the context");
+    if (!(elt & 1) || elt >= 2 * c->n) INVALID("Galois element is not valid");
+    TRY(set_device(c));
+    u64 *&slot = c->galois_keys[elt];
+    if (!slot) CU(cudaMalloc(&slot, key_words(c) * sizeof(u64)));
+    CU(cudaMemcpyAsync(slot, host, key_words(c) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const u32 *pm;
+    TRY(get_perm(c, elt, &pm));
+    return HEGPU_OK;
+}
+extern "C" int hegpu_has_galois_key(hegpu_ctx *c, uint32_t elt) { return c && c->galois_keys.count(elt) ? 1 : 0; }
+
+extern "C" int hegpu_galois_elt_from_step(hegpu_ctx *c, int step, uint32_t *elt)
+{
+    if (!c || !elt) INVALID("null argument");
+    const u32 n = c->n, m = 2 * n;
+    if (step == 0) { *elt = m - 1; return HEGPU_OK; }
+    const u32 pos = (u32)std::abs(step);
+    if (pos >= (n >> 1)) INVALID("step count too large");
+    const u32 s = step < 0 ? (n >> 1) - pos : pos;
+    u64 e = 1;
+    for (u32 i = 0; i < s; ++i) e = (e * 3) & (m - 1);
+    *elt = (u32)e;
+    return HEGPU_OK;
+}
+
+// ------------------------------------------------------------------------- handles
+extern "C" int hegpu_ct_create(hegpu_ctx *c, hegpu_ct **out, uint32_t batch, uint32_t size_cap, uint32_t L_cap)
+{
+    if (!c || !out) INVALID("null argument");
+    if (batch == 0 || size_cap < 2 || size_cap > 3 || L_cap == 0 || L_cap > c->K) INVALID("invalid ciphertext batch shape");
+    TRY(set_device(c));
+    hegpu_ct *t = new hegpu_ct{ c, nullptr, batch, size_cap, L_cap, 0, 0, 1.0 };
+    cudaError_t e = cudaMalloc(&t->d, (size_t)batch * size_cap * L_cap * c->n * sizeof(u64));
+    if (e != cudaSuccess) {
+        delete t;
+        return fail(e == cudaErrorMemoryAllocation ? HEGPU_ERR_OUT_OF_MEMORY : HEGPU_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = t;
+    return HEGPU_OK;
+}
+extern "C" int hegpu_ct_destroy(hegpu_ct *t)
+{
+    if (!t) return HEGPU_OK;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    cudaFree(t->d);
+    delete t;
+    return HEGPU_OK;
+}
+
+static int launch_repack(hegpu_ctx *c, CtView dst, CtView src, u32 B, u32 polys, u32 L)
+{
+    const size_t total = (size_t)B * polys * L * c->n;
+    repack_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(dst, src, B, polys, L, c->n);
+    c->launches++;
+    CU(cudaGetLastError());
+    return HEGPU_OK;
+}
+
+static int ct_io(hegpu_ct *t, u32 b0, u32 nb, u64 *host, bool upload)
+{
+    hegpu_ctx *c = t->ctx;
+    TRY(set_device(c));
+    const size_t words = (size_t)nb * t->size * t->L * c->n;
+    const bool packed = (t->size == t->size_cap && t->L == t->L_cap);
+    CtView dv = t->view_at(b0);
+    if (packed) {
+        if (upload)
+            CU(cudaMemcpyAsync(dv.p, host, words * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+        else
+            CU(cudaMemcpyAsync(host, dv.p, words * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        TRY(stage_reserve(c, words));
+        CtView sv{ c->stage, (size_t)t->size * t->L * c->n, (size_t)t->L * c->n, (size_t)c->n };
+        if (upload) {
+            CU(cudaMemcpyAsync(c->stage, host, words * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+            TRY(launch_repack(c, dv, sv, nb, t->size, t->L));
+        } else {
+            TRY(launch_repack(c, sv, dv, nb, t->size, t->L));
+            CU(cudaMemcpyAsync(host, c->stage, words * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    if (!upload) CU(cudaStreamSynchronize(c->stream));
+    return HEGPU_OK;
+}
+
+extern "C" int hegpu_ct_upload(hegpu_ct *t, const uint64_t *host, uint32_t size, uint32_t L, double scale)
+{
+    if (!t || !host) INVALID("null argument");
+    if (size < 2 || size > t->size_cap || L == 0 || L > t->L_cap) INVALID("ciphertext does not fit the batch capacity");
+    t->size = size;
+    t->L = L;
+    t->scale = scale;
+    return ct_io(t, 0, t->batch, const_cast<u64 *>((const u64 *)host), true);
+}
+extern "C" int hegpu_ct_download(hegpu_ct *t, uint64_t *host)
+{
+    if (!t || !host) INVALID("null argument");
+    if (!t->L) INVALID("ciphertext batch is uninitialised");
+    return ct_io(t, 0, t->batch, (u64 *)host, false);
+}
+extern "C" int hegpu_ct_upload_one(hegpu_ct *t, uint32_t index, const uint64_t *host)
+{
+    if (!t || !host) INVALID("null argument");
+    if (index >= t->batch || !t->L) INVALID("invalid batch index or uninitialised metadata");
+    return ct_io(t, index, 1, const_cast<u64 *>((const u64 *)host), true);
+}
+extern "C" int hegpu_ct_download_one(hegpu_ct *t, uint32_t index, uint64_t *host)
+{
+    if (!t || !host) INVALID("null argument");
+    if (index >= t->batch || !t->L) INVALID("invalid batch index or uninitialised metadata");
+    return ct_io(t, index, 1, (u64 *)host, false);
+}
+extern "C" int hegpu_ct_info(const hegpu_ct *t, uint32_t *batch, uint32_t *size, uint32_t *L, double *scale)
+{
+    if (!t) INVALID("null argument");
+    if (batch) *batch = t->batch;
+    if (size) *size = t->size;
+    if (L) *L = t->L;
+    if (scale) *scale = t->scale;
+    return HEGPU_OK;
+}
+extern "C" int hegpu_ct_set_scale(hegpu_ct *t, double scale)
+{
+    if (!t) INVALID("null argument");
+    t->scale = scale;
+    return HEGPU_OK;
+}
+extern "C" int hegpu_ct_device_view(hegpu_ct *t, void **dptr, size_t *sb, size_t *sp, size_t *sl)
+{
+    if (!t) INVALID("null argument");
+    CtView v = t->view();
+    if (dptr) *dptr = v.p;
+    if (sb) *sb = v.sb;
+    if (sp) *sp = v.sp;
+    if (sl) *sl = v.sl;
+    return HEGPU_OK;
+}
+
+template <int OP>
+static int launch_ew(hegpu_ctx *c, CtView out, CtView a, CtView b, u32 B, u32 polys, u32 L)
+{
+    EwParams P{ out, a, b, B, polys, L, c->n };
+    const size_t total = (size_t)B * polys * L * c->n;
+    ew_kernel<OP><<<ew_grid(c, total), 256, 0, c->stream>>>(P, c->d_mods);
+    c->launches++;
+    CU(cudaGetLastError());
+    return HEGPU_OK;
+}
+
+static int fits(const hegpu_ct *out, u32 batch, u32 size, u32 L)
+{
+    if (out->batch != batch) INVALID("destination batch size mismatch");
+    if (size > out->size_cap || L > out->L_cap) INVALID("destination capacity too small");
+    return HEGPU_OK;
+}
+
+extern "C" int hegpu_ct_copy(hegpu_ctx *c, hegpu_ct *dst, const hegpu_ct *src)
+{
+    if (!c || !dst || !src) INVALID("null argument");
+    if (!src->L) INVALID("ciphertext batch is uninitialised");
+    TRY(set_device(c));
+    TRY(fits(dst, src->batch, src->size, src->L));
+    if (dst != src) TRY(launch_ew<EW_COPY>(c, dst->view(), src->view(), src->view(), src->batch, src->size, src->L));
+    dst->size = src->size;
+    dst->L = src->L;
+    dst->scale = src->scale;
+    return HEGPU_OK;
+}
+extern "C" int hegpu_ct_copy_one(hegpu_ctx *c, hegpu_ct *dst, uint32_t di, const hegpu_ct *src, uint32_t si)
+{
+    if (!c || !dst || !src) INVALID("null argument");
+    if (!src->L || di >= dst->batch || si >= src->batch) INVALID("invalid batch index");
+    if (src->size > dst->size_cap || src->L > dst->L_cap) INVALID("destination capacity too small");
+    if (dst->L && (dst->L != src->L || dst->size != src->size)) INVALID("metadata mismatch");
+    TRY(set_device(c));
+    TRY(launch_ew<EW_COPY>(c, dst->view_at(di), src->view_at(si), src->view_at(si), 1, src->size, src->L));
+    dst->size = src->size;
+    dst->L = src->L;
+    dst->scale = src->scale;
+    return HEGPU_OK;
+}
+
+extern "C" int hegpu_pt_create(hegpu_ctx *c, hegpu_pt **out, uint32_t count, uint32_t L_cap)
+{
+    if (!c || !out) INVALID("null argument");
+    if (count == 0 || L_cap == 0 || L_cap > c->K) INVALID("invalid plaintext set shape");
+    TRY(set_device(c));
+    hegpu_pt *t = new hegpu_pt{ c, nullptr, count, L_cap, 0, 1.0 };
+    cudaError_t e = cudaMalloc(&t->d, (size_t)count * L_cap * c->n * sizeof(u64));
+    if (e != cudaSuccess) {
+        delete t;
+        return fail(e == cudaErrorMemoryAllocation ? HEGPU_ERR_OUT_OF_MEMORY : HEGPU_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = t;
+    return HEGPU_OK;
+}
+extern "C" int hegpu_pt_destroy(hegpu_pt *t)
+{
+    if (!t) return HEGPU_OK;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    cudaFree(t->d);
+    delete t;
+    return HEGPU_OK;
+}
+static int pt_io(hegpu_pt *t, u32 i0, u32 cnt, u64 *host, bool upload)
+{
+    hegpu_ctx *c = t->ctx;
+    TRY(set_device(c));
+    const size_t row = (size_t)t->L * c->n * sizeof(u64);
+    u64 *d = t->d + i0 * t->stride();
+    if (upload)
+        CU(cudaMemcpy2DAsync(d, t->stride() * sizeof(u64), host, row, row, cnt, cudaMemcpyHostToDevice, c->stream));
+    else {
+        CU(cudaMemcpy2DAsync(host, row, d, t->stride() * sizeof(u64), row, cnt, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return HEGPU_OK;
+}
+extern "C" int hegpu_pt_upload(hegpu_pt *t, const uint64_t *host, uint32_t L, double scale)
+{
+    if (!t || !host) INVALID("null argument");
+    if (L == 0 || L > t->L_cap) INVALID("plaintext does not fit the set capacity");
+    t->L = L;
+    t->scale = scale;
+    return pt_io(t, 0, t->count, const_cast<u64 *>((const u64 *)host), true);
+}
+extern "C" int hegpu_pt_upload_one(hegpu_pt *t, uint32_t index, const uint64_t *host)
+{
+    if (!t || !host) INVALID("null argument");
+    if (index >= t->count || !t->L) INVALID("invalid plaintext index or uninitialised metadata");
+    return pt_io(t, index, 1, const_cast<u64 *>((const u64 *)host), true);
+}
+extern "C" int hegpu_pt_download_one(hegpu_pt *t, uint32_t index, uint64_t *host)
+{
+    if (!t || !host) INVALID("null argument");
+    if (index >= t->count || !t->L) INVALID("invalid plaintext index or uninitialised metadata");
+    return pt_io(t, index, 1, (u64 *)host, false);
+}
+
+// ------------------------------------------------------------------------- NTT launchers
+template <int LOGL, int SPLIT, class Job>
+static int launch_fwd_shape(hegpu_ctx *c, const Job &job, u32 jobs)
+{
+    auto kern = ntt_fwd_kernel<LOGL, SPLIT, Job>;
+    static bool configured[16] = {};
+    if (!configured[c->device]) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL>::SMEM));
+        configured[c->device] = true;
+    }
+    kern<<<jobs << SPLIT, NttShape<LOGL>::THREADS, NttShape<LOGL>::SMEM, c->stream>>>(job, c->tabs);
+    c->launches++;
+    CU(cudaGetLastError());
+    return HEGPU_OK;
+}
+template <class Job>
+static int launch_ntt_fwd(hegpu_ctx *c, const Job &job, u32 jobs)
+{
+    if (jobs == 0) return HEGPU_OK;
+    switch (c->logn) {
+    case 12: return launch_fwd_shape<12, 0>(c, job, jobs);
+    case 13: return launch_fwd_shape<13, 0>(c, job, jobs);
+    case 14: return launch_fwd_shape<14, 0>(c, job, jobs);
+    case 15: return launch_fwd_shape<14, 1>(c, job, jobs);
+    }
+    LOGIC("unsupported ring degree");
+}
+
+template <int LOGL, int SPLIT, class Job>
+static int launch_inv_shape(hegpu_ctx *c, const Job &job, u32 jobs, u64 *scratch)
+{
+    auto kern = ntt_inv_kernel<LOGL, SPLIT, Job>;
+    static bool configured[16] = {};
+    if (!configured[c->device]) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL>::SMEM));
+        configured[c->device] = true;
+    }
+    kern<<<jobs << SPLIT, NttShape<LOGL>::THREADS, NttShape<LOGL>::SMEM, c->stream>>>(job, c->tabs, scratch);
+    c->launches++;
+    CU(cudaGetLastError());
+    if (SPLIT) {
+        const size_t total = (size_t)jobs << LOGL;
+        ntt_inv_final_kernel<LOGL, Job><<<ew_grid(c, total), 256, 0, c->stream>>>(job, c->tabs, scratch, jobs);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    return HEGPU_OK;
+}
+// scratch: [jobs][N] words, only used for N = 32768
+template <class Job>
+static int launch_ntt_inv(hegpu_ctx *c, const Job &job, u32 jobs, u64 *scratch)
+{
+    if (jobs == 0) return HEGPU_OK;
+    switch (c->logn) {
+    case 12: return launch_inv_shape<12, 0>(c, job, jobs, scratch);
+    case 13: return launch_inv_shape<13, 0>(c, job, jobs, scratch);
+    case 14: return launch_inv_shape<14, 0>(c, job, jobs, scratch);
+    case 15: return launch_inv_shape<14, 1>(c, job, jobs, scratch);
+    }
+    LOGIC("unsupported ring degree");
+}
+static size_t inv_scratch_words(hegpu_ctx *c, size_t jobs) { return c->logn == 15 ? jobs * c->n : 0; }
+
+static int ntt_device(hegpu_ctx *c, void *d, u32 count, u32 first_mod, u32 n_mods, bool inverse)
+{
+    if (!c || !d) INVALID("null argument");
+    if (n_mods == 0 || first_mod + n_mods > c->K) INVALID("modulus index out of range");
+    TRY(set_device(c));
+    PlainJob job{ (const u64 *)d, (u64 *)d, first_mod, n_mods, c->n };
+    if (!inverse) return launch_ntt_fwd(c, job, count);
+    const size_t sw = inv_scratch_words(c, count);
+    TRY(arena_reserve(c, align256(sw)));
+    return launch_ntt_inv(c, job, count, (u64 *)c->arena.base);
+}
+extern "C" int hegpu_ntt_forward_device(hegpu_ctx *c, void *d, uint32_t count, uint32_t first_mod, uint32_t n_mods)
+{
+    return ntt_device(c, d, count, first_mod, n_mods, false);
+}
+extern "C" int hegpu_ntt_inverse_device(hegpu_ctx *c, void *d, uint32_t count, uint32_t first_mod, uint32_t n_mods)
+{
+    return ntt_device(c, d, count, first_mod, n_mods, true);
+}
+static int ntt_host(hegpu_ctx *c, u64 *host, u32 count, u32 first_mod, u32 n_mods, bool inverse)
+{
+    if (!c || !host) INVALID("null argument");
+    TRY(set_device(c));
+    const size_t words = (size_t)count * c->n;
+    TRY(stage_reserve(c, words));
+    CU(cudaMemcpyAsync(c->stage, host, words * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    TRY(ntt_device(c, c->stage, count, first_mod, n_mods, inverse));
+    CU(cudaMemcpyAsync(host, c->stage, words * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return HEGPU_OK;
+}
+extern "C" int hegpu_ntt_forward_host(hegpu_ctx *c, uint64_t *h, uint32_t count, uint32_t first_mod, uint32_t n_mods)
+{
+    return ntt_host(c, (u64 *)h, count, first_mod, n_mods, false);
+}
+extern "C" int hegpu_ntt_inverse_host(hegpu_ctx *c, uint64_t *h, uint32_t count, uint32_t first_mod, uint32_t n_mods)
+{
+    return ntt_host(c, (u64 *)h, count, first_mod, n_mods, true);
+}
+
+// ------------------------------------------------------------------------- checks (SEAL wording)
+static bool are_close(double a, double b)
+{
+    double sf = std::max(std::max(std::fabs(a), std::fabs(b)), 1.0);
+    return std::fabs(a - b) < std::numeric_limits<double>::epsilon() * sf;
+}
+static bool scale_in_bounds(hegpu_ctx *c, double scale, u32 L)
+{
+    if (!(scale > 0)) return false;
+    return (int)std::log2(scale) < c->level_bits[L - 1];
+}
+static int check_ct(const hegpu_ct *a)
+{
+    if (!a) INVALID("null argument");
+    if (!a->L || a->size < 2) INVALID("encrypted is not valid for encryption parameters");
+    return HEGPU_OK;
+}
+static int batch_of(const hegpu_ct *a, const hegpu_ct *b, u32 *B, size_t *b_sb)
+{
+    if (b->batch != a->batch && b->batch != 1) INVALID("batch sizes do not match");
+    *B = a->batch;
+    *b_sb = (b->batch == 1 && a->batch != 1) ? 0 : b->view().sb;
+    return HEGPU_OK;
+}
+
+// ------------------------------------------------------------------------- element-wise ops
+extern "C" int hegpu_negate(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a)
+{
+    if (!c || !out) INVALID("null argument");
+    TRY(check_ct(a));
+    TRY(set_device(c));
+    TRY(fits(out, a->batch, a->size, a->L));
+    TRY(launch_ew<EW_NEG>(c, out->view(), a->view(), a->view(), a->batch, a->size, a->L));
+    out->size = a->size;
+    out->L = a->L;
+    out->scale = a->scale;
+    return HEGPU_OK;
+}
+
+static int add_sub(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a, const hegpu_ct *b, bool sub)
+{
+    if (!c || !out) INVALID("null argument");
+    TRY(check_ct(a));
+    TRY(check_ct(b));
+    if (a->L != b->L) INVALID("encrypted1 and encrypted2 parameter mismatch");
+    if (!are_close(a->scale, b->scale)) INVALID("scale mismatch");
+    TRY(set_device(c));
+    u32 B;
+    size_t bsb;
+    TRY(batch_of(a, b, &B, &bsb));
+    const u32 mn = std::min(a->size, b->size), mx = std::max(a->size, b->size);
+    TRY(fits(out, B, mx, a->L));
+    CtView va = a->view(), vb = b->view(), vo = out->view();
+    vb.sb = bsb;
+    if (sub)
+        TRY(launch_ew<EW_SUB>(c, vo, va, vb, B, mn, a->L));
+    else
+        TRY(launch_ew<EW_ADD>(c, vo, va, vb, B, mn, a->L));
+    if (mx > mn) {  // extra polynomial of the larger operand: copied (add / minuend) or negated (subtrahend)
+        CtView xo = vo, xa = va, xb = vb;
+        xo.p += mn * xo.sp;
+        xa.p += mn * xa.sp;
+        xb.p += mn * xb.sp;
+        if (a->size > b->size) {
+            if (out != a) TRY(launch_ew<EW_COPY>(c, xo, xa, xa, B, mx - mn, a->L));
+        } else if (sub) {
+            TRY(launch_ew<EW_NEGCOPY_B>(c, xo, xb, xb, B, mx - mn, a->L));
+        } else {
+            TRY(launch_ew<EW_COPY>(c, xo, xb, xb, B, mx - mn, a->L));
+        }
+    }
+    out->size = mx;
+    out->L = a->L;
+    out->scale = a->scale;
+    return HEGPU_OK;
+}
+extern "C" int hegpu_add(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a, const hegpu_ct *b) { return add_sub(c, out, a, b, false); }
+extern "C" int hegpu_sub(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a, const hegpu_ct *b) { return add_sub(c, out, a, b, true); }
+
+static int pt_view(const hegpu_ct *a, const hegpu_pt *pt, int pt_index, CtView *v)
+{
+    if (!pt || !pt->L) INVALID("plain is not valid for encryption parameters");
+    if (pt->L != a->L) INVALID("encrypted_ntt and plain_ntt parameter mismatch");
+    if (pt_index >= 0) {
+        if ((u32)pt_index >= pt->count) INVALID("plaintext index out of range");
+        *v = CtView{ pt->d + (size_t)pt_index * pt->stride(), 0, 0, (size_t)pt->ctx->n };
+    } else {
+        if (pt->count != a->batch) INVALID("plaintext set size must equal the batch size");
+        *v = CtView{ pt->d, pt->stride(), 0, (size_t)pt->ctx->n };
+    }
+    return HEGPU_OK;
+}
+
+static int plain_addsub(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a, const hegpu_pt *pt, int pt_index, bool sub)
+{
+    if (!c || !out) INVALID("null argument");
+    TRY(check_ct(a));
+    CtView vp;
+    TRY(pt_view(a, pt, pt_index, &vp));
+    if (!are_close(a->scale, pt->scale)) INVALID("scale mismatch");
+    TRY(set_device(c));
+    TRY(fits(out, a->batch, a->size, a->L));
+    CtView va = a->view(), vo = out->view();
+    if (sub)
+        TRY(launch_ew<EW_SUBPLAIN>(c, vo, va, vp, a->batch, 1, a->L));
+    else
+        TRY(launch_ew<EW_ADDPLAIN>(c, vo, va, vp, a->batch, 1, a->L));
+    if (out != a) {
+        CtView xo = vo, xa = va;
+        xo.p += xo.sp;
+        xa.p += xa.sp;
+        TRY(launch_ew<EW_COPY>(c, xo, xa, xa, a->batch, a->size - 1, a->L));
+    }
+    out->size = a->size;
+    out->L = a->L;
+    out->scale = a->scale;
+    return HEGPU_OK;
+}
+extern "C" int hegpu_add_plain(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a, const hegpu_pt *pt, int i)
+{
+    return plain_addsub(c, out, a, pt, i, false);
+}
+extern "C" int hegpu_sub_plain(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a, const hegpu_pt *pt, int i)
+{
+    return plain_addsub(c, out, a, pt, i, true);
+}
+
+extern "C" int hegpu_multiply_plain(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a, const hegpu_pt *pt, int pt_index)
+{
+    if (!c || !out) INVALID("null argument");
+    TRY(check_ct(a));
+    CtView vp;
+    TRY(pt_view(a, pt, pt_index, &vp));
+    const double ns = a->scale * pt->scale;
+    if (!scale_in_bounds(c, ns, a->L)) INVALID("scale out of bounds");
+    TRY(set_device(c));
+    TRY(fits(out, a->batch, a->size, a->L));
+    TRY(launch_ew<EW_MULPLAIN>(c, out->view(), a->view(), vp, a->batch, a->size, a->L));
+    out->size = a->size;
+    out->L = a->L;
+    out->scale = ns;
+    return HEGPU_OK;
+}
+
+static int multiply_impl(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a, const hegpu_ct *b, bool square)
+{
+    if (!c || !out) INVALID("null argument");
+    TRY(check_ct(a));
+    TRY(check_ct(b));
+    if (a->L != b->L) INVALID("encrypted1 and encrypted2 parameter mismatch");
+    const double ns = a->scale * b->scale;
+    if (!scale_in_bounds(c, ns, a->L)) INVALID("scale out of bounds");
+    TRY(set_device(c));
+    u32 B;
+    size_t bsb;
+    TRY(batch_of(a, b, &B, &bsb));
+    const u32 so = a->size + b->size - 1;
+    if (so > 3) INVALID("ciphertext products beyond size 3 are not supported; relinearize first");
+    TRY(fits(out, B, so, a->L));
+    CtView vb = b->view();
+    vb.sb = bsb;
+    EwParams P{ out->view(), a->view(), vb, B, so, a->L, c->n };
+    const size_t total = (size_t)B * a->L * c->n;
+    if (a->size == 2 && b->size == 2) {
+        if (square)
+            tensor_kernel<true><<<ew_grid(c, total), 256, 0, c->stream>>>(P, c->d_mods);
+        else
+            tensor_kernel<false><<<ew_grid(c, total), 256, 0, c->stream>>>(P, c->d_mods);
+    } else {
+        INVALID("ciphertext products beyond size 3 are not supported; relinearize first");
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    out->size = so;
+    out->L = a->L;
+    out->scale = ns;
+    return HEGPU_OK;
+}
+extern "C" int hegpu_multiply(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a, const hegpu_ct *b) { return multiply_impl(c, out, a, b, false); }
+extern "C" int hegpu_square(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a) { return multiply_impl(c, out, a, a, true); }
+
+// ------------------------------------------------------------------------- rescale / mod switch
+// a: view of B ciphertexts with `size` polys at level L; out at level L-1 (may alias a)
+static size_t rescale_scratch(hegpu_ctx *c, u32 B, u32 size) { return align256((size_t)B * size * c->n) + align256(inv_scratch_words(c, (size_t)B * size)); }
+static int rescale_views(hegpu_ctx *c, CtView out, CtView a, u32 B, u32 size, u32 L, ArenaPlan &ap)
+{
+    const u32 jobs = B * size;
+    u64 *t = ap.take((size_t)jobs * c->n);
+    u64 *scr = ap.take(inv_scratch_words(c, jobs));
+    HalfInttJob hj{ a.p + (size_t)(L - 1) * a.sl, t, a.sb, a.sp, size, L - 1, c->n };
+    TRY(launch_ntt_inv(c, hj, jobs, scr));
+    RescaleJob rj{ a, out, t, c->d_md + (size_t)(L - 1) * c->K, c->d_mods, size, L - 1, L - 1, c->n };
+    TRY(launch_ntt_fwd(c, rj, jobs * (L - 1)));
+    return HEGPU_OK;
+}
+
+extern "C" int hegpu_rescale_to_next(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a)
+{
+    if (!c || !out) INVALID("null argument");
+    TRY(check_ct(a));
+    if (a->L < 2) INVALID("end of modulus switching chain reached");
+    TRY(set_device(c));
+    TRY(fits(out, a->batch, a->size, a->L - 1));
+    TRY(arena_reserve(c, rescale_scratch(c, a->batch, a->size)));
+    ArenaPlan ap{ c };
+    TRY(rescale_views(c, out->view(), a->view(), a->batch, a->size, a->L, ap));
+    out->size = a->size;
+    out->scale = a->scale / (double)c->q[a->L - 1];
+    out->L = a->L - 1;
+    return HEGPU_OK;
+}
+
+extern "C" int hegpu_mod_switch_to_next(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a)
+{
+    if (!c || !out) INVALID("null argument");
+    TRY(check_ct(a));
+    if (a->L < 2) INVALID("end of modulus switching chain reached");
+    TRY(set_device(c));
+    TRY(fits(out, a->batch, a->size, a->L - 1));
+    if (out != a) TRY(launch_ew<EW_COPY>(c, out->view(), a->view(), a->view(), a->batch, a->size, a->L - 1));
+    out->size = a->size;
+    out->scale = a->scale;
+    out->L = a->L - 1;
+    return HEGPU_OK;
+}
+
+// ------------------------------------------------------------------------- key switching
+struct KsGroupDesc {
+    CtView in, out;
+    const u64 *key;
+    const u32 *perm;
+};
+static size_t ks_scratch(hegpu_ctx *c, size_t E, u32 L)
+{
+    const size_t n = c->n;
+    return align256(E * L * n) + align256(E * L * (L + 1) * n) + align256(E * 2 * (L + 1) * n) + align256(E * 2 * n) +
+           align256(inv_scratch_words(c, E * std::max<u32>(L, 2)));
+}
+// Evaluator::switch_key_inplace for ngroups x B ciphertexts.  out must not
+// alias in when perm != null.
+static int keyswitch(hegpu_ctx *c, const KsGroupDesc *groups, u32 ngroups, u32 B, u32 L, u32 target_poly, bool has_base1,
+                     ArenaPlan &ap)
+{
+    if (ngroups == 0 || B == 0) return HEGPU_OK;
+    const size_t E = (size_t)ngroups * B, n = c->n;
+    KsParams P{};
+    P.ngroups = ngroups;
+    P.B = B;
+    P.L = L;
+    P.K = c->K;
+    P.n = c->n;
+    P.target_poly = target_poly;
+    P.has_base1 = has_base1 ? 1u : 0u;
+    for (u32 g = 0; g < ngroups; ++g) {
+        P.in[g] = groups[g].in;
+        P.out[g] = groups[g].out;
+        P.key[g] = groups[g].key;
+        P.perm[g] = groups[g].perm;
+    }
+    P.coef = ap.take(E * L * n);
+    P.ext = ap.take(E * L * (L + 1) * n);
+    P.acc = ap.take(E * 2 * (L + 1) * n);
+    P.t = ap.take(E * 2 * n);
+    u64 *scr = ap.take(inv_scratch_words(c, E * std::max<u32>(L, 2)));
+
+    KsInttJob j1{ P };
+    TRY(launch_ntt_inv(c, j1, (u32)(E * L), scr));
+    KsLiftJob j2{ P, c->d_mods };
+    TRY(launch_ntt_fwd(c, j2, (u32)(E * L * L)));
+    {
+        const size_t total = E * (L + 1) * n;
+        ks_inner_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(P, c->d_mods);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    HalfInttJob j4{ P.acc + (size_t)L * n, P.t, (size_t)(L + 1) * n, 0, 1, c->K - 1, c->n };
+    TRY(launch_ntt_inv(c, j4, (u32)(E * 2), scr));
+    KsModDownJob j5{ P, c->d_md + (size_t)(c->K - 1) * c->K, c->d_mods };
+    TRY(launch_ntt_fwd(c, j5, (u32)(E * 2 * L)));
+    return HEGPU_OK;
+}
+
+extern "C" int hegpu_relinearize(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a)
+{
+    if (!c || !out) INVALID("null argument");
+    TRY(check_ct(a));
+    if (a->size == 2) return hegpu_ct_copy(c, out, a);
+    if (a->size != 3) INVALID("encrypted size must be 2 or 3");
+    if (!c->relin_key) INVALID("not enough relinearization keys");
+    TRY(set_device(c));
+    TRY(fits(out, a->batch, 2, a->L));
+    TRY(arena_reserve(c, ks_scratch(c, a->batch, a->L)));
+    ArenaPlan ap{ c };
+    KsGroupDesc g{ a->view(), out->view(), c->relin_key, nullptr };
+    TRY(keyswitch(c, &g, 1, a->batch, a->L, 2, true, ap));
+    out->size = 2;
+    out->L = a->L;
+    out->scale = a->scale;
+    return HEGPU_OK;
+}
+
+// out (view) = apply_galois(in (view)); views must not alias
+static int galois_views(hegpu_ctx *c, CtView out, CtView in, u32 B, u32 L, u32 elt, ArenaPlan &ap)
+{
+    auto it = c->galois_keys.find(elt);
+    if (it == c->galois_keys.end()) INVALID("Galois key not present");
+    const u32 *pm;
+    TRY(get_perm(c, elt, &pm));
+    KsGroupDesc g{ in, out, it->second, pm };
+    return keyswitch(c, &g, 1, B, L, 1, false, ap);
+}
+
+extern "C" int hegpu_apply_galois(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a, uint32_t elt)
+{
+    if (!c || !out) INVALID("null argument");
+    TRY(check_ct(a));
+    if (a->size > 2) INVALID("encrypted size must be 2");
+    if (!(elt & 1) || elt >= 2 * c->n) INVALID("Galois element is not valid");
+    if (!c->galois_keys.count(elt)) INVALID("Galois key not present");
+    TRY(set_device(c));
+    TRY(fits(out, a->batch, 2, a->L));
+    const size_t ctw = align256((size_t)a->batch * 2 * a->L * c->n);
+    TRY(arena_reserve(c, ks_scratch(c, a->batch, a->L) + ctw));
+    ArenaPlan ap{ c };
+    if (out == a || out->d == a->d) {
+        u64 *tmp = ap.take((size_t)a->batch * 2 * a->L * c->n);
+        CtView tv{ tmp, (size_t)2 * a->L * c->n, (size_t)a->L * c->n, (size_t)c->n };
+        TRY(galois_views(c, tv, a->view(), a->batch, a->L, elt, ap));
+        TRY(launch_ew<EW_COPY>(c, out->view(), tv, tv, a->batch, 2, a->L));
+    } else {
+        TRY(galois_views(c, out->view(), a->view(), a->batch, a->L, elt, ap));
+    }
+    out->size = 2;
+    out->L = a->L;
+    out->scale = a->scale;
+    return HEGPU_OK;
+}
+
+// util::naf
+static std::vector<int> naf(int value)
+{
+    std::vector<int> res;
+    bool sign = value < 0;
+    value = std::abs(value);
+    for (int i = 0; value; ++i) {
+        int zi = (value & 1) ? 2 - (value & 3) : 0;
+        value = (value - zi) >> 1;
+        if (zi) res.push_back((sign ? -zi : zi) * (1 << i));
+    }
+    return res;
+}
+
+// Evaluator::rotate_internal, in place on `t`
+static int rotate_internal(hegpu_ctx *c, hegpu_ct *t, int steps)
+{
+    if (steps == 0) return HEGPU_OK;
+    u32 elt;
+    TRY(hegpu_galois_elt_from_step(c, steps, &elt));
+    if (c->galois_keys.count(elt)) return hegpu_apply_galois(c, t, t, elt);
+    std::vector<int> terms = naf(steps);
+    if (terms.size() == 1) INVALID("Galois key not present");
+    for (int s : terms)
+        if ((u32)std::abs(s) != (c->n >> 1)) TRY(rotate_internal(c, t, s));
+    return HEGPU_OK;
+}
+
+extern "C" int hegpu_rotate_vector(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a, int steps)
+{
+    if (!c || !out) INVALID("null argument");
+    TRY(check_ct(a));
+    if (a->size > 2) INVALID("encrypted size must be 2");
+    if (c->galois_keys.empty() && steps != 0) INVALID("Galois key not present");
+    u32 elt;
+    TRY(hegpu_galois_elt_from_step(c, steps, &elt));
+    if (steps != 0 && c->galois_keys.count(elt) && out != a) return hegpu_apply_galois(c, out, a, elt);
+    TRY(hegpu_ct_copy(c, out, a));
+    return rotate_internal(c, out, steps);
+}
+
+// ------------------------------------------------------------------------- multi-GPU fix-up
+extern "C" int hegpu_reduce_fixup(hegpu_ctx *c, hegpu_ct *t, uint32_t terms)
+{
+    if (!c) INVALID("null argument");
+    TRY(check_ct(t));
+    if (terms == 0 || terms > 16) INVALID("at most 16 partial sums of 60-bit residues fit in 64 bits");
+    TRY(set_device(c));
+    const size_t total = (size_t)t->batch * t->size * t->L * c->n;
+    fixup_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(t->view(), t->batch, t->size, t->L, c->n, c->d_mods);
+    c->launches++;
+    CU(cudaGetLastError());
+    return HEGPU_OK;
+}
+
+// ------------------------------------------------------------------------- composites
+template <int N1>
+static void launch_bsgs_inner(hegpu_ctx *c, const BsgsParams &P, size_t total)
+{
+    bsgs_inner_kernel<N1><<<ew_grid(c, total), 256, 0, c->stream>>>(P, c->d_mods);
+}
+
+extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, uint32_t n1,
+                                 uint32_t n2, int rescale)
+{
+    if (!c || !out || !diags) INVALID("null argument");
+    TRY(check_ct(in));
+    if (in->size != 2) INVALID("encrypted size must be 2");
+    if (n1 == 0 || n2 == 0 || n1 > MAXG) INVALID("baby-step count must be in [1,16]");
+    if (diags->count < n1 * n2 || diags->L != in->L) INVALID("encrypted_ntt and plain_ntt parameter mismatch");
+    if (out == in) INVALID("matvec output must not alias its input");
+    const u32 L = in->L, B = in->batch;
+    if (rescale && L < 2) INVALID("end of modulus switching chain reached");
+    const double ns = in->scale * diags->scale;
+    if (!scale_in_bounds(c, ns, L)) INVALID("scale out of bounds");
+    TRY(set_device(c));
+    TRY(fits(out, B, 2, rescale ? L - 1 : L));
+    std::vector<u32> belt(n1, 0), gelt(n2, 0);
+    for (u32 k = 1; k < n1; ++k) {
+        TRY(hegpu_galois_elt_from_step(c, (int)k, &belt[k]));
+        if (!c->galois_keys.count(belt[k])) INVALID("Galois key not present");
+    }
+    for (u32 g = 1; g < n2; ++g) {
+        TRY(hegpu_galois_elt_from_step(c, (int)(g * n1), &gelt[g]));
+        if (!c->galois_keys.count(gelt[g])) INVALID("Galois key not present");
+    }
+    const size_t n = c->n, ctw = (size_t)2 * L * n;
+    // chunk the batch so that the scratch stays within the budget
+    auto need = [&](u32 Bc) {
+        const u32 gmax = std::min<u32>(MAXG, std::max(n1 - 1, n2 - 1));
+        return ks_scratch(c, (size_t)gmax * Bc, L) + align256((size_t)(n1 - 1) * Bc * ctw) + align256((size_t)n2 * Bc * ctw) +
+               align256((size_t)(n2 - 1) * Bc * ctw) + align256((size_t)Bc * ctw) + rescale_scratch(c, Bc, 2);
+    };
+    u32 Bc = B;
+    while (Bc > 1 && need(Bc) > c->ws_budget) Bc = (Bc + 1) / 2;
+    TRY(arena_reserve(c, need(Bc)));
+    for (u32 b0 = 0; b0 < B; b0 += Bc) {
+        const u32 Bn = std::min(Bc, B - b0);
+        ArenaPlan ap{ c };
+        u64 *baby = ap.take((size_t)(n1 - 1) * Bc * ctw);
+        u64 *inner = ap.take((size_t)n2 * Bc * ctw);
+        u64 *rot = ap.take((size_t)(n2 - 1) * Bc * ctw);
+        u64 *accb = ap.take((size_t)Bc * ctw);
+        const size_t ks_off = ap.off;
+        auto view_of = [&](u64 *p, size_t batch_off) { return CtView{ p + batch_off * ctw, ctw, (size_t)L * n, n }; };
+        const CtView vin = in->view_at(b0);
+        // 1. baby steps: all rotations of the input in one fused key-switch launch
+        for (u32 k0 = 1; k0 < n1; k0 += MAXG) {
+            KsGroupDesc gs[MAXG];
+            u32 ng = 0;
+            for (u32 k = k0; k < n1 && ng < (u32)MAXG; ++k, ++ng) {
+                const u32 *pm;
+                TRY(get_perm(c, belt[k], &pm));
+                gs[ng] = KsGroupDesc{ vin, view_of(baby, (size_t)(k - 1) * Bn), c->galois_keys[belt[k]], pm };
+            }
+            ap.off = ks_off;
+            TRY(keyswitch(c, gs, ng, Bn, L, 1, false, ap));
+        }
+        // 2. inner sums for every giant step
+        {
+            BsgsParams P{};
+            P.baby[0] = vin;
+            for (u32 k = 1; k < n1; ++k) P.baby[k] = view_of(baby, (size_t)(k - 1) * Bn);
+            P.inner = view_of(inner, 0);
+            P.diag = diags->d;
+            P.diag_si = diags->stride();
+            P.diag_sl = n;
+            P.n1 = n1;
+            P.n2 = n2;
+            P.B = Bn;
+            P.L = L;
+            P.n = c->n;
+            const size_t total = (size_t)Bn * ctw;
+            switch (n1) {
+            case 1: launch_bsgs_inner<1>(c, P, total); break;
+            case 2: launch_bsgs_inner<2>(c, P, total); break;
+            case 3: launch_bsgs_inner<3>(c, P, total); break;
+            case 4: launch_bsgs_inner<4>(c, P, total); break;
+            case 5: launch_bsgs_inner<5>(c, P, total); break;
+            case 6: launch_bsgs_inner<6>(c, P, total); break;
+            case 7: launch_bsgs_inner<7>(c, P, total); break;
+            case 8: launch_bsgs_inner<8>(c, P, total); break;
+            case 9: launch_bsgs_inner<9>(c, P, total); break;
+            case 10: launch_bsgs_inner<10>(c, P, total); break;
+            case 11: launch_bsgs_inner<11>(c, P, total); break;
+            case 12: launch_bsgs_inner<12>(c, P, total); break;
+            case 13: launch_bsgs_inner<13>(c, P, total); break;
+            case 14: launch_bsgs_inner<14>(c, P, total); break;
+            case 15: launch_bsgs_inner<15>(c, P, total); break;
+            default: launch_bsgs_inner<16>(c, P, total); break;
+            }
+            c->launches++;
+            CU(cudaGetLastError());
+        }
+        // 3. giant steps
+        for (u32 g0 = 1; g0 < n2; g0 += MAXG) {
+            KsGroupDesc gs[MAXG];
+            u32 ng = 0;
+            for (u32 g = g0; g < n2 && ng < (u32)MAXG; ++g, ++ng) {
+                const u32 *pm;
+                TRY(get_perm(c, gelt[g], &pm));
+                gs[ng] = KsGroupDesc{ view_of(inner, (size_t)g * Bn), view_of(rot, (size_t)(g - 1) * Bn), c->galois_keys[gelt[g]], pm };
+            }
+            ap.off = ks_off;
+            TRY(keyswitch(c, gs, ng, Bn, L, 1, false, ap));
+        }
+        // 4. accumulate, 5. rescale
+        {
+            CtView dst = rescale ? view_of(accb, 0) : out->view_at(b0);
+            SumParams S{ view_of(inner, 0), view_of(rot, 0), dst, n2, Bn, 2, L, c->n };
+            const size_t total = (size_t)Bn * ctw;
+            sum_terms_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(S, c->d_mods);
+            c->launches++;
+            CU(cudaGetLastError());
+            if (rescale) {
+                ap.off = ks_off;
+                TRY(rescale_views(c, out->view_at(b0), dst, Bn, 2, L, ap));
+            }
+        }
+    }
+    out->size = 2;
+    out->L = rescale ? L - 1 : L;
+    out->scale = rescale ? ns / (double)c->q[L - 1] : ns;
+    return HEGPU_OK;
+}
+
+// temporaries for the loop-order-exact composites
+struct TmpCt {
+    hegpu_ct *t = nullptr;
+    ~TmpCt() { hegpu_ct_destroy(t); }
+};
+
+extern "C" int hegpu_bmatmul(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *ths, const hegpu_ct *oth, uint32_t n, uint32_t p,
+                             int case_b)
+{
+    if (!c || !out) INVALID("null argument");
+    TRY(check_ct(ths));
+    TRY(check_ct(oth));
+    if (ths->size != 2 || oth->size != 2) INVALID("encrypted size must be 2");
+    if (ths->batch != n || oth->batch != (case_b ? n : p) || out->batch != p) INVALID("batch sizes do not match the matrix shape");
+    if (ths->L != oth->L) INVALID("encrypted1 and encrypted2 parameter mismatch");
+    if (!c->relin_key) INVALID("not enough relinearization keys");
+    if (ths->L < 2) INVALID("end of modulus switching chain reached");
+    if (out == ths || out == oth) INVALID("output must not alias an input");
+    TRY(set_device(c));
+    const u32 L = ths->L;
+    TmpCt acc, rot, prod, one;
+    TRY(hegpu_ct_create(c, &acc.t, p, 3, L));
+    if (!case_b) {
+        // case A: res_i = sum_j rot(other_i, j) * this_j; batch over i, `this_j` broadcast
+        TRY(hegpu_ct_create(c, &rot.t, p, 2, L));
+        TRY(hegpu_ct_create(c, &prod.t, p, 3, L));
+        TRY(hegpu_ct_create(c, &one.t, 1, 2, L));
+        for (u32 j = 0; j < n; ++j) {
+            TRY(hegpu_rotate_vector(c, rot.t, oth, (int)j));
+            TRY(hegpu_ct_copy_one(c, one.t, 0, ths, j));
+            one.t->scale = ths->scale;
+            if (j == 0) {
+                TRY(hegpu_multiply(c, acc.t, rot.t, one.t));
+            } else {
+                TRY(hegpu_multiply(c, prod.t, rot.t, one.t));
+                TRY(hegpu_add(c, acc.t, acc.t, prod.t));
+            }
+        }
+    } else {
+        // case B: res_i = sum_j rot(other_j, i) * this_j; batch over j, summed over the batch
+        TRY(hegpu_ct_create(c, &rot.t, n, 2, L));
+        TRY(hegpu_ct_create(c, &prod.t, n, 3, L));
+        for (u32 i = 0; i < p; ++i) {
+            TRY(hegpu_rotate_vector(c, rot.t, oth, (int)i));
+            TRY(hegpu_multiply(c, prod.t, rot.t, ths));
+            CtView first = prod.t->view_at(0), rest = prod.t->view_at(n > 1 ? 1 : 0);
+            SumParams S{ first, rest, acc.t->view_at(i), n, 1, 3, L, c->n };
+            const size_t total = (size_t)3 * L * c->n;
+            sum_terms_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(S, c->d_mods);
+            c->launches++;
+            CU(cudaGetLastError());
+            acc.t->size = 3;
+            acc.t->L = L;
+            acc.t->scale = prod.t->scale;
+        }
+    }
+    TRY(hegpu_relinearize(c, acc.t, acc.t));
+    TRY(hegpu_rescale_to_next(c, out, acc.t));
+    return HEGPU_OK;
+}
+
+// out(i,j) index in a column-major rows x cols matrix with the reference's transposed flag
+// (he_linalg.cpp:376-379: ij_to_idx = transposed ? i*cols' ... ) -- see host/he_linalg for
+// the mirrored class; here: idx = transposed ? (i * cols + j) : (i + j * rows).
+static inline u32 mat_idx(u32 i, u32 j, u32 rows, u32 cols, int transposed) { return transposed ? i * cols + j : i + j * rows; }
+
+__global__ void __launch_bounds__(256) matmul_tensor_kernel(CtView out, CtView a, CtView b, u32 rows, u32 inner, u32 cols,
+                                                            int at, int bt, u32 L, u32 n, const ModConst *__restrict__ mods)
+{
+    const size_t per_o = (size_t)L * n;
+    const size_t total = (size_t)rows * cols * per_o;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 x = (u32)(idx % n);
+        size_t r = idx / n;
+        const u32 l = (u32)(r % L);
+        const u32 o = (u32)(r / L);  // column-major output index
+        const u32 i = o % rows, j = o / rows;
+        const ModConst m = mods[l];
+        u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0, h2 = 0, l2 = 0;
+        for (u32 k = 0; k < inner; ++k) {
+            const u32 ia = at ? i * inner + k : i + k * rows;
+            const u32 ib = bt ? k * cols + j : k + j * inner;
+            const u64 *pa = a.p + ia * a.sb + l * a.sl + x, *pb = b.p + ib * b.sb + l * b.sl + x;
+            const u64 a0 = pa[0], a1 = pa[a.sp], b0 = pb[0], b1 = pb[b.sp];
+            mac128(h0, l0, a0, b0);
+            mac128(h1, l1, a0, b1);
+            mac128(h1, l1, a1, b0);
+            mac128(h2, l2, a1, b1);
+            if ((k & 31) == 31) {  // keep the lazy 128-bit sums far from overflow
+                l0 = barrett128(h0, l0, m); h0 = 0;
+                l1 = barrett128(h1, l1, m); h1 = 0;
+                l2 = barrett128(h2, l2, m); h2 = 0;
+            }
+        }
+        u64 *po = out.p + o * out.sb + l * out.sl + x;
+        po[0] = barrett128(h0, l0, m);
+        po[out.sp] = barrett128(h1, l1, m);
+        po[2 * out.sp] = barrett128(h2, l2, m);
+    }
+}
+
+extern "C" int hegpu_matmul_elemwise(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a, const hegpu_ct *b, uint32_t rows,
+                                     uint32_t inner, uint32_t cols, int at, int bt)
+{
+    if (!c || !out) INVALID("null argument");
+    TRY(check_ct(a));
+    TRY(check_ct(b));
+    if (a->size != 2 || b->size != 2) INVALID("encrypted size must be 2");
+    if (a->batch != rows * inner || b->batch != inner * cols || out->batch != rows * cols) INVALID("batch sizes do not match the matrix shape");
+    if (a->L != b->L) INVALID("encrypted1 and encrypted2 parameter mismatch");
+    if (!c->relin_key) INVALID("not enough relinearization keys");
+    if (a->L < 2) INVALID("end of modulus switching chain reached");
+    if (out == a || out == b) INVALID("output must not alias an input");
+    const double ns = a->scale * b->scale;
+    if (!scale_in_bounds(c, ns, a->L)) INVALID("scale out of bounds");
+    TRY(set_device(c));
+    TmpCt acc;
+    TRY(hegpu_ct_create(c, &acc.t, rows * cols, 3, a->L));
+    const size_t total = (size_t)rows * cols * a->L * c->n;
+    matmul_tensor_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(acc.t->view(), a->view(), b->view(), rows, inner, cols, at, bt,
+                                                                    a->L, c->n, c->d_mods);
+    c->launches++;
+    CU(cudaGetLastError());
+    acc.t->size = 3;
+    acc.t->L = a->L;
+    acc.t->scale = ns;
+    (void)mat_idx;
+    TRY(hegpu_relinearize(c, acc.t, acc.t));
+    TRY(hegpu_rescale_to_next(c, out, acc.t));
+    return HEGPU_OK;
+}
+
+extern "C" int hegpu_bfft_stage(hegpu_ctx *c, hegpu_ct *y, const hegpu_pt *pts, int steps, int with_d2)
+{
+    if (!c || !pts) INVALID("null argument");
+    TRY(check_ct(y));
+    if (pts->count < (with_d2 ? 3u : 2u)) INVALID("stage needs the D0, D1 (and D2) plaintexts");
+    TmpCt y0, y1, y2;
+    TRY(hegpu_ct_create(c, &y0.t, y->batch, 2, y->L));
+    TRY(hegpu_ct_create(c, &y1.t, y->batch, 2, y->L));
+    TRY(hegpu_multiply_plain(c, y0.t, y, pts, 0));
+    TRY(hegpu_rescale_to_next(c, y0.t, y0.t));
+    TRY(hegpu_rotate_vector(c, y1.t, y, steps));
+    TRY(hegpu_multiply_plain(c, y1.t, y1.t, pts, 1));
+    TRY(hegpu_rescale_to_next(c, y1.t, y1.t));
+    if (with_d2) {
+        TRY(hegpu_ct_create(c, &y2.t, y->batch, 2, y->L));
+        TRY(hegpu_rotate_vector(c, y2.t, y, -steps));
+        TRY(hegpu_multiply_plain(c, y2.t, y2.t, pts, 2));
+        TRY(hegpu_rescale_to_next(c, y2.t, y2.t));
+    }
+    TRY(hegpu_add(c, y, y0.t, y1.t));
+    if (with_d2) TRY(hegpu_add(c, y, y, y2.t));
+    return HEGPU_OK;
+}
+
+extern "C" int hegpu_fft_butterflies(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *even, const hegpu_ct *odd,
+                                     const hegpu_pt *w, const hegpu_pt *one)
+{
+    if (!c || !out || !w || !one) INVALID("null argument");
+    TRY(check_ct(even));
+    TRY(check_ct(odd));
+    const u32 half = even->batch;
+    if (odd->batch != half || out->batch != 2 * half || w->count != half) INVALID("batch sizes do not match");
+    if (out == even || out == odd) INVALID("output must not alias an input");
+    TmpCt t, e;
+    TRY(hegpu_ct_create(c, &t.t, half, 2, odd->L));
+    TRY(hegpu_ct_create(c, &e.t, half, 2, even->L));
+    TRY(hegpu_multiply_plain(c, t.t, odd, w, -1));
+    TRY(hegpu_rescale_to_next(c, t.t, t.t));
+    TRY(hegpu_multiply_plain(c, e.t, even, one, 0));
+    TRY(hegpu_rescale_to_next(c, e.t, e.t));
+    if (!are_close(e.t->scale, t.t->scale)) INVALID("scale mismatch");
+    const u32 L = e.t->L;
+    if (L > out->L_cap) INVALID("destination capacity too small");
+    CtView ve = e.t->view(), vt = t.t->view();
+    TRY(launch_ew<EW_ADD>(c, out->view_at(0), ve, vt, half, 2, L));
+    TRY(launch_ew<EW_SUB>(c, out->view_at(half), ve, vt, half, 2, L));
+    out->size = 2;
+    out->L = L;
+    out->scale = e.t->scale;
+    return HEGPU_OK;
+}

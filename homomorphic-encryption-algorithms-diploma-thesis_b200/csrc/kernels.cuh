@@ -1,0 +1,517 @@
+// kernels.cuh -- the CUDA kernels of the CKKS evaluator (sm_100a).
+//
+//  K1/K2  ntt_fwd_kernel / ntt_inv_kernel (+ ntt_inv_final_kernel for N = 32768)
+//  K3-K5  element-wise: add / sub / negate / multiply_plain / tensor product / square
+//  K6     Galois permutation: fused as a gather into the key-switch INTT load, the key
+//         inner product (digit i == j) and the mod-down epilogue -- never a separate pass
+//  K7     key-switch: ks INTT -> lift+NTT -> key inner product -> INTT(+half) -> mod-down NTT
+//  K8     rescale: INTT(+half) -> mod-down NTT (same two kernels as the end of K7)
+//  K10    bsgs_inner_kernel: sum_k baby_k (.) diag_{g,k} for all giant steps at once
+//  K11    fixup_kernel: reduce NCCL uint64 sums back to [0,q)
+#pragma once
+#include "ntt.cuh"
+
+namespace hegpu {
+
+constexpr int MAXG = 16;  // rotation groups fused into one key-switch launch
+
+// strided view of a ciphertext batch in HBM: word (b, p, l, x) at p + b*sb + p*sp + l*sl + x
+struct CtView {
+    u64 *p;
+    size_t sb, sp, sl;
+};
+
+// dropped-modulus constants: d^-1 mod q_i and floor(d/2) mod q_i
+struct MdConst {
+    u64 inv, inv_sh, halfmod, pad;
+};
+
+// ---------------------------------------------------------------------------------------
+// NTT job resolvers.  A resolver maps a job id (blockIdx.x >> SPLIT) to the modulus and to
+// the load / store functions of that limb polynomial.
+// ---------------------------------------------------------------------------------------
+
+// plain transform of `count` limb polynomials [count][N] (measurement API, host tooling)
+struct PlainJob {
+    const u64 *src;
+    u64 *dst;
+    u32 first_mod, n_mods, n;
+    __device__ __forceinline__ u32 mod(u32 j) const { return first_mod + j % n_mods; }
+    __device__ __forceinline__ u64 load(u32 j, u32 i, const ModConst &) const { return src[(size_t)j * n + i]; }
+    __device__ __forceinline__ void store(u32 j, u32 i, u64 v, const ModConst &) const { dst[(size_t)j * n + i] = v; }
+};
+
+// key-switch launch parameters (one launch handles ngroups rotations/relinearisations of
+// B ciphertexts each: element e = g*B + b)
+struct KsParams {
+    u32 ngroups, B, L, K, n;
+    u32 target_poly;  // 1: Galois (switch pi(c1)); 2: relinearise (switch c2)
+    u32 has_base1;    // add in[1] to component 1 (relinearise)
+    CtView in[MAXG];
+    CtView out[MAXG];
+    const u64 *key[MAXG];   // [Lmax][2][K][N]
+    const u32 *perm[MAXG];  // Galois gather table or null
+    u64 *coef;              // [E][L][N]
+    u64 *ext;               // [E][L][L+1][N]
+    u64 *acc;               // [E][2][L+1][N]
+    u64 *t;                 // [E][2][N]
+};
+
+// K7 step 1: c_j = INTT_{q_j}( pi(target)[j] )
+struct KsInttJob {
+    KsParams P;
+    __device__ __forceinline__ u32 mod(u32 j) const { return j % P.L; }
+    __device__ __forceinline__ u64 load(u32 j, u32 i, const ModConst &) const
+    {
+        const u32 e = j / P.L, l = j % P.L, g = e / P.B, b = e % P.B;
+        const CtView &v = P.in[g];
+        const u32 *pm = P.perm[g];
+        const u32 src = pm ? __ldg(pm + i) : i;
+        return v.p[b * v.sb + P.target_poly * v.sp + l * v.sl + src];
+    }
+    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &) const { P.coef[(size_t)j * P.n + i] = x; }
+};
+
+// K7 step 2: ext[e][j][i] = NTT_{m_i}( c_j mod m_i ), i != j, i in [0, L]
+struct KsLiftJob {
+    KsParams P;
+    const ModConst *mods;
+    __device__ __forceinline__ void split(u32 j, u32 &e, u32 &dj, u32 &di) const
+    {
+        const u32 LL = P.L * P.L;
+        e = j / LL;
+        const u32 r = j % LL;
+        dj = r / P.L;
+        const u32 ii = r % P.L;
+        di = ii < dj ? ii : ii + 1;
+    }
+    __device__ __forceinline__ u32 mod(u32 j) const
+    {
+        u32 e, dj, di;
+        split(j, e, dj, di);
+        return di == P.L ? P.K - 1 : di;
+    }
+    __device__ __forceinline__ u64 load(u32 j, u32 i, const ModConst &m) const
+    {
+        u32 e, dj, di;
+        split(j, e, dj, di);
+        const u64 v = P.coef[((size_t)e * P.L + dj) * P.n + i];
+        return (mods[dj].q > m.q) ? barrett64(v, m) : v;
+    }
+    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &) const
+    {
+        u32 e, dj, di;
+        split(j, e, dj, di);
+        P.ext[(((size_t)e * P.L + dj) * (P.L + 1) + di) * P.n + i] = x;
+    }
+};
+
+// INTT of a dropped limb with the rounding offset added: t = (INTT_d(src) + floor(d/2)) mod d.
+// Used by K7 step 4 (d = special prime) and by rescale (d = q_{L-1}).
+struct HalfInttJob {
+    const u64 *src;  // job j at src + (j / inner) * s_outer + (j % inner) * s_inner
+    u64 *dst;        // [jobs][N]
+    size_t s_outer, s_inner;
+    u32 inner, drop_mod, n;
+    __device__ __forceinline__ u32 mod(u32) const { return drop_mod; }
+    __device__ __forceinline__ u64 load(u32 j, u32 i, const ModConst &) const
+    {
+        return src[(j / inner) * s_outer + (j % inner) * s_inner + i];
+    }
+    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m) const
+    {
+        dst[(size_t)j * n + i] = addmod(x, m.q >> 1, m.q);
+    }
+};
+
+// K7 step 5: out[c][i] = base_c[i] + (acc[c][i] - NTT_{q_i}((t_c mod q_i) - half)) * P^-1
+struct KsModDownJob {
+    KsParams P;
+    const MdConst *md;  // [K] constants of the dropped modulus (special prime) per target limb
+    const ModConst *mods;
+    __device__ __forceinline__ void split(u32 j, u32 &e, u32 &c, u32 &l) const
+    {
+        l = j % P.L;
+        c = (j / P.L) & 1u;
+        e = j / (2 * P.L);
+    }
+    __device__ __forceinline__ u32 mod(u32 j) const { return j % P.L; }
+    __device__ __forceinline__ u64 load(u32 j, u32 i, const ModConst &m) const
+    {
+        u32 e, c, l;
+        split(j, e, c, l);
+        u64 v = P.t[((size_t)e * 2 + c) * P.n + i];
+        if (mods[P.K - 1].q > m.q) v = barrett64(v, m);
+        return submod(v, md[l].halfmod, m.q);
+    }
+    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m) const
+    {
+        u32 e, c, l;
+        split(j, e, c, l);
+        const u32 g = e / P.B, b = e % P.B;
+        const u64 a = P.acc[(((size_t)e * 2 + c) * (P.L + 1) + l) * P.n + i];
+        const u64 r = mul_shoup(submod(a, x, m.q), md[l].inv, md[l].inv_sh, m.q);
+        const CtView &vi = P.in[g];
+        u64 base = 0;
+        if (c == 0) {
+            const u32 *pm = P.perm[g];
+            base = vi.p[b * vi.sb + l * vi.sl + (pm ? __ldg(pm + i) : i)];
+        } else if (P.has_base1) {
+            base = vi.p[b * vi.sb + vi.sp + l * vi.sl + i];
+        }
+        const CtView &vo = P.out[g];
+        vo.p[b * vo.sb + c * vo.sp + l * vo.sl + i] = addmod(base, r, m.q);
+    }
+};
+
+// rescale step 2: out[b][p][i] = (a[b][p][i] - NTT_{q_i}((t mod q_i) - half)) * q_last^-1
+struct RescaleJob {
+    CtView a, out;
+    const u64 *t;       // [B*size][N]
+    const MdConst *md;  // constants of dropped modulus q_{L-1} per target limb
+    const ModConst *mods;
+    u32 size, Lm1, drop_mod, n;  // Lm1 = L-1 target limbs
+    __device__ __forceinline__ u32 mod(u32 j) const { return j % Lm1; }
+    __device__ __forceinline__ u64 load(u32 j, u32 i, const ModConst &m) const
+    {
+        u64 v = t[(size_t)(j / Lm1) * n + i];
+        if (mods[drop_mod].q > m.q) v = barrett64(v, m);
+        return submod(v, md[j % Lm1].halfmod, m.q);
+    }
+    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m) const
+    {
+        const u32 l = j % Lm1, bp = j / Lm1, p = bp % size, b = bp / size;
+        const u64 av = a.p[b * a.sb + p * a.sp + l * a.sl + i];
+        out.p[b * out.sb + p * out.sp + l * out.sl + i] = mul_shoup(submod(av, x, m.q), md[l].inv, md[l].inv_sh, m.q);
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// NTT kernels.  grid = jobs << SPLIT, block = 2^LOGL / 16, dynamic smem = 8 << LOGL.
+// ---------------------------------------------------------------------------------------
+template <int LOGL, int SPLIT, class Job>
+__global__ void __launch_bounds__(NttShape<LOGL>::THREADS, 1) ntt_fwd_kernel(const Job job, const NttTables T)
+{
+    extern __shared__ __align__(16) u64 sm[];
+    const u32 jid = blockIdx.x >> SPLIT;
+    const u32 h = blockIdx.x & ((1u << SPLIT) - 1u);
+    const u32 mi = job.mod(jid);
+    const ModConst m = T.mods[mi];
+    const ulonglong2 *tw = T.fwd + (size_t)mi * T.n;
+    const u32 boff = h << LOGL;
+    auto store = [&](u32 i, u64 v) { job.store(jid, boff + i, v, m); };
+    if constexpr (SPLIT == 0) {
+        auto load = [&](u32 i) -> u64 { return job.load(jid, i, m); };
+        if (m.big & 1u)
+            ntt_fwd_cta<LOGL, true>(load, store, tw, T.n, m, sm);
+        else
+            ntt_fwd_cta<LOGL, false>(load, store, tw, T.n, m, sm);
+    } else {
+        // stage 1 (stride N/2) redone from global memory by both halves
+        const ulonglong2 W = __ldg(tw + 1);
+        const u64 q2 = m.q << 1;
+        auto load = [&](u32 i) -> u64 {
+            const u64 X = job.load(jid, i, m);
+            const u64 Y = job.load(jid, i + (1u << LOGL), m);
+            const u64 Tm = mul_shoup_lazy(Y, W.x, W.y, m.q);
+            return h ? X + q2 - Tm : X + Tm;
+        };
+        if (m.big & 1u)
+            ntt_fwd_cta<LOGL, true>(load, store, tw, T.n + boff, m, sm);
+        else
+            ntt_fwd_cta<LOGL, false>(load, store, tw, T.n + boff, m, sm);
+    }
+}
+
+// SPLIT = 1: the CTA transforms its half and leaves lazy values in `scratch`
+// ([jobs][N]); ntt_inv_final_kernel applies the last stage and the job's store.
+template <int LOGL, int SPLIT, class Job>
+__global__ void __launch_bounds__(NttShape<LOGL>::THREADS, 1)
+    ntt_inv_kernel(const Job job, const NttTables T, u64 *__restrict__ scratch)
+{
+    extern __shared__ __align__(16) u64 sm[];
+    const u32 jid = blockIdx.x >> SPLIT;
+    const u32 h = blockIdx.x & ((1u << SPLIT) - 1u);
+    const u32 mi = job.mod(jid);
+    const ModConst m = T.mods[mi];
+    const ulonglong2 *tw = T.inv + (size_t)mi * T.n;
+    const ulonglong2 wl = T.inv_last[mi];
+    const u32 boff = h << LOGL;
+    auto load = [&](u32 i) -> u64 { return job.load(jid, boff + i, m); };
+    if constexpr (SPLIT == 0) {
+        auto store = [&](u32 i, u64 v) { job.store(jid, i, v, m); };
+        if (m.big & 2u)
+            ntt_inv_cta<LOGL, true, LOGL - 1>(load, store, tw, T.n, m, wl, sm);
+        else
+            ntt_inv_cta<LOGL, false, LOGL - 1>(load, store, tw, T.n, m, wl, sm);
+    } else {
+        u64 *dst = scratch + (size_t)jid * T.n + boff;
+        auto store = [&](u32 i, u64 v) { dst[i] = v; };
+        if (m.big & 2u)
+            ntt_inv_cta<LOGL, true, -1>(load, store, tw, T.n + boff, m, wl, sm);
+        else
+            ntt_inv_cta<LOGL, false, -1>(load, store, tw, T.n + boff, m, wl, sm);
+    }
+}
+
+// last (stride N/2) INTT stage for N = 2^(LOGL+1), element-wise over scratch
+template <int LOGL, class Job>
+__global__ void __launch_bounds__(256) ntt_inv_final_kernel(const Job job, const NttTables T, const u64 *__restrict__ scratch,
+                                                            u32 jobs)
+{
+    const u32 halfn = 1u << LOGL;
+    const size_t total = (size_t)jobs * halfn;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 jid = (u32)(idx >> LOGL), i = (u32)(idx & (halfn - 1));
+        const u32 mi = job.mod(jid);
+        const ModConst m = T.mods[mi];
+        const ulonglong2 wl = T.inv_last[mi];
+        const u64 X = scratch[(size_t)jid * T.n + i], Y = scratch[(size_t)jid * T.n + halfn + i];
+        u64 Sm, D;
+        if (m.big & 2u) {
+            Sm = csub(X + Y, m.q << 1);
+            D = X + (m.q << 1) - Y;
+        } else {
+            Sm = X + Y;
+            D = X + (m.q << (LOGL + 1)) - Y;
+        }
+        job.store(jid, i, mul_shoup(Sm, m.ninv, m.ninv_sh, m.q), m);
+        job.store(jid, i + halfn, mul_shoup(D, wl.x, wl.y, m.q), m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K7 step 3: key inner product.  acc[e][c][i] = sum_j ext[e][j][i] (.) key[j][c][ki] mod m_i;
+// digit i == j reads the (permuted) target directly.  128-bit lazy accumulation, one
+// Barrett reduction (as SEAL).  One thread per (e, i, x).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ks_inner_kernel(const KsParams P, const ModConst *__restrict__ mods)
+{
+    const u32 L = P.L, n = P.n;
+    const size_t per_e = (size_t)(L + 1) * n;
+    const size_t total = (size_t)P.ngroups * P.B * per_e;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 e = (u32)(idx / per_e);
+        const u32 r = (u32)(idx % per_e);
+        const u32 i = r / n, x = r % n;
+        const u32 g = e / P.B, b = e % P.B;
+        const u32 ki = (i == L) ? P.K - 1 : i;
+        const ModConst m = mods[ki];
+        const u64 *key = P.key[g];
+        u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+        for (u32 j = 0; j < L; ++j) {
+            u64 d;
+            if (j == i) {
+                const CtView &v = P.in[g];
+                const u32 *pm = P.perm[g];
+                d = v.p[b * v.sb + P.target_poly * v.sp + j * v.sl + (pm ? __ldg(pm + x) : x)];
+            } else {
+                d = P.ext[(((size_t)e * L + j) * (L + 1) + i) * n + x];
+            }
+            const u64 k0 = __ldg(key + (((size_t)j * 2 + 0) * P.K + ki) * n + x);
+            const u64 k1 = __ldg(key + (((size_t)j * 2 + 1) * P.K + ki) * n + x);
+            mac128(h0, l0, d, k0);
+            mac128(h1, l1, d, k1);
+        }
+        P.acc[(((size_t)e * 2 + 0) * (L + 1) + i) * n + x] = barrett128(h0, l0, m);
+        P.acc[(((size_t)e * 2 + 1) * (L + 1) + i) * n + x] = barrett128(h1, l1, m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// element-wise kernels over (b, p, l, x).  b's batch stride may be 0 (broadcast).
+// ---------------------------------------------------------------------------------------
+enum EwOp { EW_ADD, EW_SUB, EW_NEG, EW_COPY, EW_MULPLAIN, EW_ADDPLAIN, EW_SUBPLAIN, EW_NEGCOPY_B };
+
+struct EwParams {
+    CtView out, a, b;  // b: second ciphertext, or plaintext (sp = 0)
+    u32 B, polys, L, n;
+};
+
+template <int OP>
+__global__ void __launch_bounds__(256) ew_kernel(const EwParams P, const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)P.polys * P.L * P.n;
+    const size_t total = (size_t)P.B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        u32 r = (u32)(idx % per_b);
+        const u32 x = r % P.n;
+        r /= P.n;
+        const u32 l = r % P.L, p = r / P.L;
+        const size_t oa = b * P.a.sb + p * P.a.sp + l * P.a.sl + x;
+        const size_t ob = b * P.b.sb + p * P.b.sp + l * P.b.sl + x;
+        const size_t oo = b * P.out.sb + p * P.out.sp + l * P.out.sl + x;
+        const u64 q = mods[l].q;
+        u64 v;
+        if (OP == EW_ADD) v = addmod(P.a.p[oa], P.b.p[ob], q);
+        else if (OP == EW_SUB) v = submod(P.a.p[oa], P.b.p[ob], q);
+        else if (OP == EW_NEG) v = negmod(P.a.p[oa], q);
+        else if (OP == EW_COPY) v = P.a.p[oa];
+        else if (OP == EW_NEGCOPY_B) v = negmod(P.b.p[ob], q);
+        else if (OP == EW_MULPLAIN) v = mulmod(P.a.p[oa], P.b.p[ob], mods[l]);
+        else if (OP == EW_ADDPLAIN) v = addmod(P.a.p[oa], P.b.p[ob], q);
+        else v = submod(P.a.p[oa], P.b.p[ob], q);
+        P.out.p[oo] = v;
+    }
+}
+
+// K5: tensor product 2x2 -> 3 (d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1); SQUARE: b = a.
+// out may alias a or b: every thread reads its inputs before it writes.
+template <bool SQUARE>
+__global__ void __launch_bounds__(256) tensor_kernel(const EwParams P, const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)P.L * P.n;
+    const size_t total = (size_t)P.B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        const u32 r = (u32)(idx % per_b);
+        const u32 l = r / P.n, x = r % P.n;
+        const ModConst m = mods[l];
+        const size_t oa = b * P.a.sb + l * P.a.sl + x;
+        const u64 a0 = P.a.p[oa], a1 = P.a.p[oa + P.a.sp];
+        u64 b0, b1;
+        if (SQUARE) {
+            b0 = a0;
+            b1 = a1;
+        } else {
+            const size_t ob = b * P.b.sb + l * P.b.sl + x;
+            b0 = P.b.p[ob];
+            b1 = P.b.p[ob + P.b.sp];
+        }
+        const u64 d0 = mulmod(a0, b0, m), d2 = mulmod(a1, b1, m);
+        u64 h = 0, lo = 0;
+        mac128(h, lo, a0, b1);
+        mac128(h, lo, a1, b0);
+        const u64 d1 = barrett128(h, lo, m);
+        const size_t oo = b * P.out.sb + l * P.out.sl + x;
+        P.out.p[oo] = d0;
+        P.out.p[oo + P.out.sp] = d1;
+        P.out.p[oo + 2 * P.out.sp] = d2;
+    }
+}
+
+// general ciphertext product (sizes sa x sb -> sa+sb-1), used when an operand has size 3.
+// out must not alias.
+__global__ void __launch_bounds__(256) convolve_kernel(const EwParams P, u32 sa, u32 sb, const ModConst *__restrict__ mods)
+{
+    const u32 so = sa + sb - 1;
+    const size_t per_b = (size_t)so * P.L * P.n;
+    const size_t total = (size_t)P.B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        u32 r = (u32)(idx % per_b);
+        const u32 x = r % P.n;
+        r /= P.n;
+        const u32 l = r % P.L, k = r / P.L;
+        const ModConst m = mods[l];
+        u64 h = 0, lo = 0;
+        for (u32 ia = 0; ia < sa; ++ia) {
+            if (k < ia || k - ia >= sb) continue;
+            mac128(h, lo, P.a.p[b * P.a.sb + ia * P.a.sp + l * P.a.sl + x], P.b.p[b * P.b.sb + (k - ia) * P.b.sp + l * P.b.sl + x]);
+        }
+        P.out.p[b * P.out.sb + k * P.out.sp + l * P.out.sl + x] = barrett128(h, lo, m);
+    }
+}
+
+// K6 standalone (only used when a rotation's output aliases its input): out = pi(in)
+__global__ void __launch_bounds__(256) fixup_kernel(const CtView v, u32 B, u32 polys, u32 L, u32 n, const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)polys * L * n;
+    const size_t total = (size_t)B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        u32 r = (u32)(idx % per_b);
+        const u32 x = r % n;
+        r /= n;
+        const u32 l = r % L, p = r / L;
+        u64 *ptr = v.p + b * v.sb + p * v.sp + l * v.sl + x;
+        *ptr = barrett64(*ptr, mods[l]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K10: BSGS inner sums for every giant step in one pass over the baby rotations.
+//   inner[g][b][p][l][x] = sum_{k<n1} baby_k[b][p][l][x] * diag[g*n1+k][l][x]  mod q_l
+// A thread keeps the n1 baby values of its (b,p,l,x) in registers and sweeps g, so the
+// rotated ciphertexts are read from HBM once; the diagonals are shared by the whole batch
+// and stay in L2.
+// ---------------------------------------------------------------------------------------
+struct BsgsParams {
+    CtView baby[MAXG];  // baby[0] = the input batch
+    CtView inner;       // batch index = g*B + b
+    const u64 *diag;    // [n1*n2][Lcap][N]
+    size_t diag_si, diag_sl;
+    u32 n1, n2, B, L, n;
+};
+
+template <int N1>
+__global__ void __launch_bounds__(256) bsgs_inner_kernel(const BsgsParams P, const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)2 * P.L * P.n;
+    const size_t total = (size_t)P.B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        // x fastest, then batch, then (p,l): neighbouring CTAs share the same diagonal tiles
+        const u32 x = (u32)(idx % P.n);
+        size_t r = idx / P.n;
+        const u32 b = (u32)(r % P.B);
+        r /= P.B;
+        const u32 l = (u32)(r % P.L), p = (u32)(r / P.L);
+        const ModConst m = mods[l];
+        u64 v[N1];
+#pragma unroll
+        for (int k = 0; k < N1; ++k) {
+            const CtView &c = P.baby[k];
+            v[k] = c.p[b * c.sb + p * c.sp + l * c.sl + x];
+        }
+        for (u32 g = 0; g < P.n2; ++g) {
+            u64 h = 0, lo = 0;
+            const u64 *d = P.diag + (size_t)g * N1 * P.diag_si + l * P.diag_sl + x;
+#pragma unroll
+            for (int k = 0; k < N1; ++k) mac128(h, lo, v[k], __ldg(d + k * P.diag_si));
+            P.inner.p[((size_t)g * P.B + b) * P.inner.sb + p * P.inner.sp + l * P.inner.sl + x] = barrett128(h, lo, m);
+        }
+    }
+}
+
+// sum of `terms` ciphertext batches laid out at batch offsets g*B: out = sum_g src_g
+struct SumParams {
+    CtView first;  // term 0
+    CtView rest;   // terms 1.., batch index (g-1)*B + b
+    CtView out;
+    u32 terms, B, polys, L, n;
+};
+__global__ void __launch_bounds__(256) sum_terms_kernel(const SumParams P, const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)P.polys * P.L * P.n;
+    const size_t total = (size_t)P.B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        u32 r = (u32)(idx % per_b);
+        const u32 x = r % P.n;
+        r /= P.n;
+        const u32 l = r % P.L, p = r / P.L;
+        const u64 q = mods[l].q;
+        u64 s = P.first.p[b * P.first.sb + p * P.first.sp + l * P.first.sl + x];
+        for (u32 g = 1; g < P.terms; ++g)
+            s = addmod(s, P.rest.p[((size_t)(g - 1) * P.B + b) * P.rest.sb + p * P.rest.sp + l * P.rest.sl + x], q);
+        P.out.p[b * P.out.sb + p * P.out.sp + l * P.out.sl + x] = s;
+    }
+}
+
+// strided repack between SEAL's packed host layout (staged in HBM) and the batch layout
+__global__ void __launch_bounds__(256) repack_kernel(const CtView dst, const CtView src, u32 B, u32 polys, u32 L, u32 n)
+{
+    const size_t per_b = (size_t)polys * L * n;
+    const size_t total = (size_t)B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        u32 r = (u32)(idx % per_b);
+        const u32 x = r % n;
+        r /= n;
+        const u32 l = r % L, p = r / L;
+        dst.p[b * dst.sb + p * dst.sp + l * dst.sl + x] = src.p[b * src.sb + p * src.sp + l * src.sl + x];
+    }
+}
+
+}  // namespace hegpu

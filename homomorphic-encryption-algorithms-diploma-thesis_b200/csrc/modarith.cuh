@@ -1,0 +1,74 @@
+// modarith.cuh -- 64-bit modular arithmetic for sm_100a, built on 32-bit IMAD chains.
+// Canonical residues in [0,q), q < 2^61.  Constants (Shoup quotients, Barrett ratios) are
+// precomputed on the host (context.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace hegpu {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// per-modulus constants, one per prime of the key-level chain
+struct ModConst {
+    u64 q;
+    u64 mu_hi;    // floor(2^128 / q) >> 64  == floor(2^64 / q)
+    u64 mu_lo;    // floor(2^128 / q) low word
+    u64 ninv;     // N^{-1} mod q
+    u64 ninv_sh;  // Shoup quotient of ninv
+    u32 big;      // q >= 2^48: lazy ranges need per-stage corrections
+    u32 pad;
+};
+
+__device__ __forceinline__ u64 csub(u64 v, u64 c) { return v >= c ? v - c : v; }
+
+// x * w mod q, lazily in [0, 2q); wsh = floor(w * 2^64 / q); any x < 2^64
+__device__ __forceinline__ u64 mul_shoup_lazy(u64 x, u64 w, u64 wsh, u64 q)
+{
+    u64 h = __umul64hi(x, wsh);
+    return x * w - h * q;
+}
+__device__ __forceinline__ u64 mul_shoup(u64 x, u64 w, u64 wsh, u64 q) { return csub(mul_shoup_lazy(x, w, wsh, q), q); }
+
+// x mod q for any x < 2^64 (SEAL barrett_reduce_64)
+__device__ __forceinline__ u64 barrett64(u64 x, const ModConst &m)
+{
+    u64 h = __umul64hi(x, m.mu_hi);
+    return csub(x - h * m.q, m.q);
+}
+
+// (hi:lo) mod q for hi:lo < 2^124 (SEAL barrett_reduce_128)
+__device__ __forceinline__ u64 barrett128(u64 hi, u64 lo, const ModConst &m)
+{
+    u64 carry = __umul64hi(lo, m.mu_lo);
+    u64 t2lo = lo * m.mu_hi, t2hi = __umul64hi(lo, m.mu_hi);
+    u64 tmp1 = t2lo + carry;
+    u64 tmp3 = t2hi + (tmp1 < t2lo);
+    t2lo = hi * m.mu_lo;
+    t2hi = __umul64hi(hi, m.mu_lo);
+    u64 s = tmp1 + t2lo;
+    carry = t2hi + (s < tmp1);
+    u64 qhat = hi * m.mu_hi + tmp3 + carry;
+    u64 r = lo - qhat * m.q;
+    return csub(csub(r, m.q), m.q);
+}
+
+__device__ __forceinline__ u64 mulmod(u64 a, u64 b, const ModConst &m)
+{
+    return barrett128(__umul64hi(a, b), a * b, m);
+}
+
+// 128-bit accumulate acc += a*b
+__device__ __forceinline__ void mac128(u64 &hi, u64 &lo, u64 a, u64 b)
+{
+    u64 pl = a * b, ph = __umul64hi(a, b);
+    lo += pl;
+    hi += ph + (lo < pl);
+}
+
+__device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { return csub(a + b, q); }
+__device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
+__device__ __forceinline__ u64 negmod(u64 a, u64 q) { return a ? q - a : 0; }
+
+}  // namespace hegpu

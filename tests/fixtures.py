@@ -1,0 +1,61 @@
+"""Shared fixtures: oracle context + keys + ciphertext builders (test infrastructure)."""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+
+import ckks_ref as ref
+from oracle import oracle as orc
+
+
+def rand_residues(rng, moduli, prefix, n):
+    out = np.empty(tuple(prefix) + (len(moduli), n), dtype=np.uint64)
+    for i, q in enumerate(moduli):
+        out[..., i, :] = rng.integers(0, q, size=tuple(prefix) + (n,), dtype=np.uint64)
+    return out
+
+
+class Setup:
+    """One parameter set with an oracle, an encoder, a secret key and lazily generated keys."""
+
+    def __init__(self, n, bits, seed=1):
+        self.n = n
+        self.bits = list(bits)
+        self.moduli = orc.coeff_modulus_create(n, self.bits)
+        self.K = len(self.moduli)
+        self.Lmax = self.K - 1
+        self.o = orc.Oracle(n, self.moduli)
+        self.enc = ref.Encoder(n, self.moduli, self.o.ntt_fwd, self.o.ntt_inv)
+        self.seed = seed
+        self.s = self.o.sample_secret(seed)
+        self._rk = None
+        self._gk = {}
+
+    @property
+    def rk(self):
+        if self._rk is None:
+            self._rk = self.o.gen_relin_key(self.seed + 1, self.s)
+        return self._rk
+
+    def gk(self, steps):
+        """{elt: key} for the given rotation steps."""
+        out = {}
+        for st in steps:
+            elt = orc.galois_elt_from_step(self.n, st)
+            if elt not in self._gk:
+                self._gk[elt] = self.o.gen_galois_key(self.seed + 1000 + elt, self.s, elt)
+            out[elt] = self._gk[elt]
+        return out
+
+    def encrypt(self, values, scale, L=None, seed=0):
+        L = self.Lmax if L is None else L
+        return self.o.encrypt_symmetric(self.seed + 5000 + seed, self.s, self.enc.encode(values, scale, L))
+
+    def decrypt(self, ct, scale):
+        return self.enc.decode(self.o.decrypt(ct, self.s), scale)
+
+
+@functools.lru_cache(maxsize=None)
+def setup(n, bits, seed=1):
+    return Setup(n, bits, seed)

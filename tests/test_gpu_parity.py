@@ -1,0 +1,359 @@
+"""GPU parity tests proper: every evaluator primitive of libhegpu.so (called through the
+C ABI) must be BIT-EXACT against the CPU oracle on the same inputs (integer arithmetic;
+tolerance = 0).  Decrypted composites are additionally checked against float64 numpy
+within the CKKS tolerance 8*sqrt(n)*2^-(log2(scale)-16) stated in DESIGN.md."""
+import numpy as np
+import pytest
+
+import hegpu_loader
+from fixtures import rand_residues, setup
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hg():
+    return hegpu_loader.load()
+
+
+def make_ctx(hg, S):
+    return hg.Context(S.n, S.moduli)
+
+
+# ------------------------------------------------------------------ NTT
+@pytest.mark.parametrize("n", [4096, 8192, 16384, 32768])
+def test_ntt_bit_exact(hg, n):
+    bits = [60, 50, 40, 30, 59, 47]  # covers both lazy-range code paths (fwd: 2^58, inv: 2^46)
+    S = setup(n, tuple(bits))
+    ctx = make_ctx(hg, S)
+    rng = np.random.default_rng(n)
+    for i, q in enumerate(S.moduli):
+        assert ctx.psi(i) == S.o.psi(i)
+    a = rand_residues(rng, S.moduli, (3,), n)  # [3][K][N]
+    a[0, :, :] = 0
+    for i, q in enumerate(S.moduli):
+        a[1, i, :] = q - 1
+    f = a.copy()
+    ctx.ntt_forward_host(f, 0, S.K)
+    want = np.stack([np.stack([S.o.ntt_fwd(i, a[r, i]) for i in range(S.K)]) for r in range(3)])
+    assert np.array_equal(f, want)
+    g = f.copy()
+    ctx.ntt_inverse_host(g, 0, S.K)
+    assert np.array_equal(g, a)
+    # monomial X -> psi^(2 brev(k)+1) (SURVEY 9.2 sanity test)
+    x = np.zeros((1, n), dtype=np.uint64)
+    x[0, 1] = 1
+    ctx.ntt_forward_host(x, 0, 1)
+    assert int(x[0, 0]) == S.o.psi(0)
+
+
+# ------------------------------------------------------------------ element-wise
+@pytest.mark.parametrize("n,bits", [(8192, (60, 40, 40, 60)), (4096, (36, 36, 37))])
+def test_elementwise_bit_exact(hg, n, bits):
+    S = setup(n, bits)
+    ctx = make_ctx(hg, S)
+    L = S.Lmax
+    rng = np.random.default_rng(11)
+    B = 3
+    a = rand_residues(rng, S.moduli[:L], (B, 2), n)
+    b = rand_residues(rng, S.moduli[:L], (B, 2), n)
+    c3 = rand_residues(rng, S.moduli[:L], (B, 3), n)
+    pt = rand_residues(rng, S.moduli[:L], (B,), n)
+    sc = 2.0**20
+    A, Bc, C3 = ctx.upload_ct(a, sc), ctx.upload_ct(b, sc), ctx.upload_ct(c3, sc)
+    P = ctx.upload_pt(pt, sc)
+    out = ctx.ct(B)
+    o = S.o
+
+    def each(fn, *args):
+        return np.stack([fn(*[x[i] for x in args]) for i in range(B)])
+
+    ctx.add(out, A, Bc)
+    assert np.array_equal(out.download(), each(o.add, a, b))
+    ctx.sub(out, A, Bc)
+    assert np.array_equal(out.download(), each(o.sub, a, b))
+    ctx.negate(out, A)
+    assert np.array_equal(out.download(), each(o.negate, a))
+    # mixed sizes 2 vs 3
+    ctx.add(out, A, C3)
+    assert np.array_equal(out.download(), each(o.add, a, c3))
+    ctx.sub(out, A, C3)
+    assert np.array_equal(out.download(), each(o.sub, a, c3))
+    ctx.sub(out, C3, A)
+    assert np.array_equal(out.download(), each(o.sub, c3, a))
+    ctx.add(out, C3, A)
+    assert np.array_equal(out.download(), each(o.add, c3, a))
+    # plaintext ops: per-element plaintexts (index -1) and one broadcast plaintext
+    ctx.multiply_plain(out, A, P, -1)
+    assert np.array_equal(out.download(), each(o.multiply_plain, a, pt))
+    assert out.scale == sc * sc
+    ctx.multiply_plain(out, C3, P, 1)
+    assert np.array_equal(out.download(), np.stack([o.multiply_plain(c3[i], pt[1]) for i in range(B)]))
+    ctx.add_plain(out, A, P, -1)
+    assert np.array_equal(out.download(), each(o.add_plain, a, pt))
+    ctx.sub_plain(out, A, P, 2)
+    assert np.array_equal(out.download(), np.stack([o.sub_plain(a[i], pt[2]) for i in range(B)]))
+    # tensor product and square
+    ctx.multiply(out, A, Bc)
+    assert np.array_equal(out.download(), each(o.multiply, a, b))
+    ctx.square(out, A)
+    assert np.array_equal(out.download(), each(o.square, a))
+    # broadcast of a batch-1 second operand
+    one = ctx.upload_ct(b[:1], sc)
+    ctx.multiply(out, A, one)
+    assert np.array_equal(out.download(), np.stack([o.multiply(a[i], b[0]) for i in range(B)]))
+    # in place
+    ctx.add(A, A, Bc)
+    assert np.array_equal(A.download(), each(o.add, a, b))
+
+
+def test_error_behaviour_matches_seal(hg):
+    S = setup(8192, (60, 40, 40, 60))
+    ctx = make_ctx(hg, S)
+    rng = np.random.default_rng(3)
+    a = rand_residues(rng, S.moduli[:3], (1, 2), S.n)
+    A = ctx.upload_ct(a, 2.0**40)
+    Bc = ctx.upload_ct(a, 2.0**41)
+    out = ctx.ct(1)
+    with pytest.raises(hg.InvalidArgument, match="scale mismatch"):
+        ctx.add(out, A, Bc)
+    low = ctx.upload_ct(a[:, :, :2], 2.0**40)
+    with pytest.raises(hg.InvalidArgument, match="parameter mismatch"):
+        ctx.add(out, A, low)
+    big = ctx.upload_ct(a, 2.0**100)
+    with pytest.raises(hg.InvalidArgument, match="scale out of bounds"):
+        ctx.multiply(out, big, big)
+    l1 = ctx.upload_ct(a[:, :, :1], 2.0**40)
+    with pytest.raises(hg.InvalidArgument, match="end of modulus switching chain reached"):
+        ctx.rescale_to_next(out, l1)
+    with pytest.raises(hg.InvalidArgument, match="Galois key not present"):
+        ctx.rotate_vector(out, A, 1)
+    with pytest.raises(hg.InvalidArgument, match="step count too large"):
+        ctx.rotate_vector(out, A, S.n // 2)
+    ctx.multiply(out, A, A)
+    with pytest.raises(hg.InvalidArgument, match="not enough relinearization keys"):
+        ctx.relinearize(out, out)
+
+
+# ------------------------------------------------------------------ rescale / key switching
+@pytest.mark.parametrize("n,bits", [(8192, (60, 40, 40, 60)), (16384, (60, 31, 30, 30, 30, 60)), (4096, (36, 36, 37)),
+                                    (32768, (60, 40, 40, 60))])
+def test_rescale_relin_galois_bit_exact(hg, n, bits):
+    S = setup(n, bits)
+    ctx = make_ctx(hg, S)
+    rng = np.random.default_rng(5)
+    o = S.o
+    steps = [1, -1, 2, 8]
+    gk = S.gk(steps)
+    ctx.load_relin_key(S.rk)
+    ctx.load_galois_keys(gk)
+    B = 2
+    for L in range(S.Lmax, 0, -1):
+        mods = S.moduli[:L]
+        c3 = rand_residues(rng, mods, (B, 3), n)
+        c2 = np.ascontiguousarray(c3[:, :2])
+        C3, C2 = ctx.upload_ct(c3, 2.0**30), ctx.upload_ct(c2, 2.0**30)
+        out = ctx.ct(B)
+        if L >= 2:
+            ctx.rescale_to_next(out, C3)
+            assert np.array_equal(out.download(), np.stack([o.rescale(c3[i]) for i in range(B)]))
+            assert out.scale == 2.0**30 / mods[-1] and out.L == L - 1
+            ctx.mod_switch_to_next(out, C3)
+            assert np.array_equal(out.download(), np.stack([o.mod_switch(c3[i]) for i in range(B)]))
+        ctx.relinearize(out, C3)
+        assert np.array_equal(out.download(), np.stack([o.relinearize(c3[i], S.rk) for i in range(B)]))
+        for st in steps:
+            elt = orc.galois_elt_from_step(n, st)
+            assert ctx.galois_elt_from_step(st) == elt
+            ctx.rotate_vector(out, C2, st)
+            assert np.array_equal(out.download(), np.stack([o.apply_galois(c2[i], elt, gk[elt]) for i in range(B)]))
+        # in place + NAF chain: 7 = [-1, 8]
+        want = np.stack([o.rotate(c2[i], 7, gk)[0] for i in range(B)])
+        ctx.rotate_vector(C2, C2, 7)
+        assert np.array_equal(C2.download(), want)
+        # relinearize in place
+        ctx.relinearize(C3, C3)
+        assert np.array_equal(C3.download(), np.stack([o.relinearize(c3[i], S.rk) for i in range(B)]))
+
+
+def test_rotation_zero_and_negative_naf(hg):
+    S = setup(8192, (60, 40, 40, 60))
+    ctx = make_ctx(hg, S)
+    rng = np.random.default_rng(9)
+    gk = S.gk([1, 2, 4, -1, -2, -4])
+    ctx.load_galois_keys(gk)
+    c2 = rand_residues(rng, S.moduli[:3], (1, 2), S.n)
+    C2 = ctx.upload_ct(c2, 2.0**40)
+    out = ctx.ct(1)
+    ctx.rotate_vector(out, C2, 0)
+    assert np.array_equal(out.download(), c2)
+    for st in (3, -3, 5, -7):
+        ctx.rotate_vector(out, C2, st)
+        assert np.array_equal(out.download()[0], S.o.rotate(c2[0], st, gk)[0])
+
+
+# ------------------------------------------------------------------ composites
+def _diag_plaintexts(S, M, n1, n2, scale, L):
+    dim = M.shape[0]
+    slots = S.n // 2
+    pts = np.empty((dim, L, S.n), dtype=np.uint64)
+    for g in range(n2):
+        for b in range(n1):
+            d = g * n1 + b
+            diag = np.array([M[r, (r + d) % dim] for r in range(dim)])
+            pts[d] = S.enc.encode(np.roll(np.tile(diag, slots // dim), g * n1), scale, L)
+    return pts
+
+
+@pytest.mark.parametrize("n,dim,n1,n2", [(8192, 16, 4, 4), (16384, 32, 8, 4)])
+def test_matvec_bsgs_bit_exact_and_decrypts(hg, n, dim, n1, n2):
+    S = setup(n, (60, 40, 40, 60))
+    ctx = make_ctx(hg, S)
+    rng = np.random.default_rng(21)
+    scale, L, B = 2.0**40, 3, 3
+    M = rng.uniform(-1, 1, (dim, dim))
+    V = rng.uniform(-1, 1, (B, dim))
+    cts = np.stack([S.encrypt(np.tile(V[i], S.n // 2 // dim), scale, L, seed=i) for i in range(B)])
+    pts = _diag_plaintexts(S, M, n1, n2, scale, L)
+    bsteps = list(range(1, n1))
+    gsteps = [g * n1 for g in range(1, n2)]
+    gk = S.gk(bsteps + gsteps)
+    ctx.load_galois_keys(gk)
+    bk = [None] + [gk[orc.galois_elt_from_step(n, s)] for s in bsteps]
+    gkeys = [None] + [gk[orc.galois_elt_from_step(n, s)] for s in gsteps]
+    want = S.o.matvec_bsgs(cts, n1, n2, pts, bk, gkeys, threads=4)
+    X = ctx.upload_ct(cts, scale)
+    D = ctx.upload_pt(pts, scale)
+    out = ctx.ct(B, 2)
+    ctx.matvec_bsgs(out, X, D, n1, n2)
+    got = out.download()
+    assert np.array_equal(got, want)
+    tol = 8 * np.sqrt(dim) * 2.0 ** -(40 - 16)
+    for i in range(B):
+        dec = S.decrypt(got[i], out.scale).real[:dim]
+        assert np.max(np.abs(dec - M @ V[i])) < tol
+
+
+@pytest.mark.parametrize("case_b", [False, True])
+def test_bmatmul_reference_loop_order(hg, case_b):
+    """BatchedMatrix::matmul (he_linalg.cpp:943-1006) restated on the oracle in the reference's own
+    loop order with SEAL's default power-of-two Galois keys (NAF rotations)."""
+    n, dim = 8192, 4
+    S = setup(n, (60, 40, 40, 60))
+    ctx = make_ctx(hg, S)
+    rng = np.random.default_rng(31)
+    scale, L = 2.0**40, 3
+    gk = S.gk([1, 2, -1, -2])
+    ctx.load_galois_keys(gk)
+    ctx.load_relin_key(S.rk)
+    A = rng.uniform(-1, 1, (dim, dim))
+    Bm = rng.uniform(-1, 1, (dim, dim))
+    slots = n // 2
+    rep = lambda v: np.tile(v, slots // dim)
+    if not case_b:
+        this_vals = [np.array([A[r, (r + d) % dim] for r in range(dim)]) for d in range(dim)]  # diagonals of A
+        other_vals = [Bm[:, j] for j in range(dim)]  # columns of B
+    else:
+        this_vals = [A[:, j] for j in range(dim)]  # columns of A
+        other_vals = [Bm[j, :] for j in range(dim)]  # rows of B (transposed col batching)
+    this_c = np.stack([S.encrypt(rep(v), scale, L, seed=10 + i) for i, v in enumerate(this_vals)])
+    other_c = np.stack([S.encrypt(rep(v), scale, L, seed=20 + i) for i, v in enumerate(other_vals)])
+    o = S.o
+    want = []
+    for i in range(dim):
+        acc = None
+        for j in range(dim):
+            src, st = (other_c[i], j) if not case_b else (other_c[j], i)
+            r, _ = o.rotate(src, st, gk)
+            t = o.multiply(r, this_c[j])
+            acc = t if acc is None else o.add(acc, t)
+        want.append(o.rescale(o.relinearize(acc, S.rk)))
+    want = np.stack(want)
+    T, O = ctx.upload_ct(this_c, scale), ctx.upload_ct(other_c, scale)
+    out = ctx.ct(dim, 2)
+    ctx.bmatmul(out, T, O, dim, dim, case_b)
+    got = out.download()
+    assert np.array_equal(got, want)
+    tol = 8 * np.sqrt(dim) * 2.0 ** -(40 - 16)
+    if not case_b:
+        for j in range(dim):  # column j of A @ B
+            assert np.max(np.abs(S.decrypt(got[j], out.scale).real[:dim] - (A @ Bm)[:, j])) < tol
+
+
+def test_matmul_elemwise_bit_exact(hg):
+    """Matrix::matmul (he_linalg.cpp:202-236): one ciphertext per entry, column-major."""
+    n = 4096
+    S = setup(n, (36, 36, 37))
+    ctx = make_ctx(hg, S)
+    ctx.load_relin_key(S.rk)
+    rng = np.random.default_rng(41)
+    rows, inner, cols, L = 2, 3, 2, 2
+    a = rand_residues(rng, S.moduli[:L], (rows * inner, 2), n)
+    b = rand_residues(rng, S.moduli[:L], (inner * cols, 2), n)
+    o = S.o
+    want = []
+    for j in range(cols):
+        for i in range(rows):
+            acc = None
+            for k in range(inner):
+                t = o.multiply(a[i + k * rows], b[k + j * inner])
+                acc = t if acc is None else o.add(acc, t)
+            want.append(o.rescale(o.relinearize(acc, S.rk)))
+    want = np.stack(want)  # column-major index i + j*rows
+    A, Bc = ctx.upload_ct(a, 2.0**15), ctx.upload_ct(b, 2.0**15)
+    out = ctx.ct(rows * cols, 2)
+    ctx.matmul_elemwise(out, A, Bc, rows, inner, cols)
+    assert np.array_equal(out.download(), want)
+
+
+def test_bfft_stage_and_fft_butterflies_bit_exact(hg):
+    n = 8192
+    S = setup(n, (60, 40, 40, 60))
+    ctx = make_ctx(hg, S)
+    gk = S.gk([4, -4])
+    ctx.load_galois_keys(gk)
+    rng = np.random.default_rng(51)
+    L, sc = 3, 2.0**40
+    o = S.o
+    y = rand_residues(rng, S.moduli[:L], (2, 2), n)
+    d = rand_residues(rng, S.moduli[:L], (3,), n)
+    for with_d2 in (True, False):
+        Y = ctx.upload_ct(y, sc)
+        ctx.bfft_stage(Y, ctx.upload_pt(d, sc), 4, with_d2)
+        want = []
+        for i in range(2):
+            y0 = o.rescale(o.multiply_plain(y[i], d[0]))
+            y1 = o.rescale(o.multiply_plain(o.rotate(y[i], 4, gk)[0], d[1]))
+            r = o.add(y0, y1)
+            if with_d2:
+                r = o.add(r, o.rescale(o.multiply_plain(o.rotate(y[i], -4, gk)[0], d[2])))
+            want.append(r)
+        assert np.array_equal(Y.download(), np.stack(want))
+    half = 3
+    ev = rand_residues(rng, S.moduli[:L], (half, 2), n)
+    od = rand_residues(rng, S.moduli[:L], (half, 2), n)
+    w = rand_residues(rng, S.moduli[:L], (half,), n)
+    one = rand_residues(rng, S.moduli[:L], (1,), n)
+    out = ctx.ct(2 * half, 2)
+    ctx.fft_butterflies(out, ctx.upload_ct(ev, sc), ctx.upload_ct(od, sc), ctx.upload_pt(w, sc), ctx.upload_pt(one, sc))
+    got = out.download()
+    for k in range(half):
+        t = o.rescale(o.multiply_plain(od[k], w[k]))
+        e = o.rescale(o.multiply_plain(ev[k], one[0]))
+        assert np.array_equal(got[k], o.add(e, t))
+        assert np.array_equal(got[k + half], o.sub(e, t))
+
+
+def test_reduce_fixup(hg):
+    S = setup(8192, (60, 40, 40, 60))
+    ctx = make_ctx(hg, S)
+    rng = np.random.default_rng(61)
+    parts = rand_residues(rng, S.moduli[:3], (8, 1, 2), S.n)
+    summed = parts.sum(axis=0, dtype=np.uint64)  # what an NCCL uint64 sum produces
+    T = ctx.upload_ct(summed, 1.0)
+    ctx.reduce_fixup(T, 8)
+    want = parts[0]
+    for k in range(1, 8):
+        want = np.stack([S.o.add(want[0], parts[k][0])])
+    assert np.array_equal(T.download(), want)
