@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: CKKS matvecs/s, N = 2^14, 128x128 plaintext matrix x
+encrypted vector, BSGS 16x8, batch of 64 ciphertexts per step (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One process per GPU (torchrun for N > 1).  A step is one pass of hegpu_matvec_bsgs over a
+batch of 64 encrypted vectors on every rank (batch sharding, no data-path collective ->
+weak scaling).  Prints ONE JSON line (rank 0).
+
+  value     matvecs/s with inputs resident in HBM (CUDA events on the context's stream)
+  e2e       same through the C ABI with pinned HOST buffers: upload of the 64 input
+            ciphertexts + matvec + download of the 64 results inside the timed region
+  roofline  the dominant kernel family (per-launch CUDA events in a second pass of the same
+            steps; algorithmic bytes per DESIGN.md) against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (a port of SEAL 4.1's algorithms; SEAL itself is not
+            installable here) running the same BSGS matvec on all host cores, N=1 only
+
+--impl reference times that CPU port alone on the same config (the reference's evaluator
+is Microsoft SEAL, an absent external dependency, so `kind` is "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(N=16384, bits=(60, 40, 40, 60), dim=128, n1=16, n2=8, batch=64, scale=2.0**40, L=3)
+METRIC = "CKKS matvecs/s (N=2^14, 128x128)"
+
+
+# ------------------------------------------------------------------ helpers
+def tolerance(n_terms, N, scale):
+    """CKKS key-switch noise bound stated in DESIGN.md ("Tolerance")."""
+    return n_terms * 3.2 * N**1.5 / (8.0 * scale)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.rows, self.stop_flag = device, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(r[col].lower() == "active" for r in self.rows if len(r) > col):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth_problem(client, seed):
+    """128x128 matrix -> 128 pre-rotated plaintext diagonals; 64 encrypted vectors."""
+    c = CFG
+    rng = np.random.default_rng(seed)
+    dim, n1, n2, slots = c["dim"], c["n1"], c["n2"], c["N"] // 2
+    M = rng.uniform(-1, 1, (dim, dim))
+    V = rng.uniform(-1, 1, (c["batch"], dim))
+    rows = np.empty((dim, slots))
+    r = np.arange(dim)
+    for g in range(n2):
+        for b in range(n1):
+            d = g * n1 + b
+            rows[d] = np.roll(np.tile(M[r, (r + d) % dim], slots // dim), g * n1)
+    pts = client.encode_many(rows, c["scale"], c["L"])
+    plains = client.encode_many(np.tile(V, (1, slots // dim)), c["scale"], c["L"])
+    cts = client.encrypt_many(plains)
+    return M, V, pts, cts
+
+
+def rotation_steps():
+    return list(range(1, CFG["n1"])) + [g * CFG["n1"] for g in range(1, CFG["n2"])]
+
+
+# ------------------------------------------------------------------ reference arm (CPU)
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+
+    c = CFG
+    threads = orc.max_threads()
+    moduli = orc.coeff_modulus_create(c["N"], c["bits"])
+    o = orc.Oracle(c["N"], moduli)
+    rng = np.random.default_rng(1)
+    s = o.sample_secret(7)
+    gk = o.gen_galois_keys_for_steps(11, s, rotation_steps())
+    bk = [None] + [gk[orc.galois_elt_from_step(c["N"], k)] for k in range(1, c["n1"])]
+    gkeys = [None] + [gk[orc.galois_elt_from_step(c["N"], g * c["n1"])] for g in range(1, c["n2"])]
+    mods = moduli[: c["L"]]
+    pts = np.empty((c["dim"], c["L"], c["N"]), dtype=np.uint64)
+    for i, q in enumerate(mods):
+        pts[:, i, :] = rng.integers(0, q, size=(c["dim"], c["N"]), dtype=np.uint64)
+    per_step = threads  # one ciphertext per host thread per step (bounded sample of the 64-batch)
+    cts = np.empty((per_step, 2, c["L"], c["N"]), dtype=np.uint64)
+    for i, q in enumerate(mods):
+        cts[:, :, i, :] = rng.integers(0, q, size=(per_step, 2, c["N"]), dtype=np.uint64)
+    for _ in range(args.warmup):
+        o.matvec_bsgs(cts, c["n1"], c["n2"], pts, bk, gkeys, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.matvec_bsgs(cts, c["n1"], c["n2"], pts, bk, gkeys, threads=threads)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = f"{per_step} ciphertexts per step (1 per host thread) of the 64-ciphertext batch, same BSGS 16x8 matvec"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "matvecs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "cfg2: CKKS N=16384 {60,40,40,60}, 128x128 plaintext diagonals x encrypted vector, BSGS 16x8",
+                   "batch_per_step": per_step, "note": "CPU port of SEAL 4.1's algorithms (oracle/); real SEAL is not installable here"},
+        "cpu_baseline": {"value": value, "unit": "matvecs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "matvecs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+
+    import hegpu_loader
+
+    hg = hegpu_loader.load()
+    from hegpu_b200.client import Client, coeff_modulus_create  # package registered by hegpu_loader
+
+    c = CFG
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    moduli = coeff_modulus_create(c["N"], c["bits"])
+    ctx = hg.Context(c["N"], moduli, device=local)
+    client = Client(ctx, seed=1234)  # same keys on every rank (replicated), different vectors per rank
+    gk = client.galois_keys_for_steps(rotation_steps())
+    ctx.load_galois_keys(gk)
+    M, V, pts, cts = synth_problem(client, seed=0xC0FFEE + 2 + 1000 * rank)
+    B = c["batch"]
+
+    D = ctx.upload_pt(pts, c["scale"])
+    X = ctx.upload_ct(cts, c["scale"], size_cap=2, L_cap=c["L"])
+    OUT = ctx.ct(B, 2, c["L"] - 1)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local)
+
+    def step():
+        ctx.matvec_bsgs(OUT, X, D, c["n1"], c["n2"])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        ctx.sync()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    # correctness of the measured path (decrypt on rank 0, first ciphertext)
+    step()
+    got = OUT.download()
+    out_scale = OUT.scale
+    dec = client.decode(client.decrypt(got[0]), out_scale).real[: c["dim"]]
+    tol = tolerance(c["dim"], c["N"], c["scale"])
+    max_err = float(np.max(np.abs(dec - M @ V[0])))
+    if not max_err < tol:
+        raise SystemExit(f"decrypted matvec is wrong: max |err| {max_err:.3e} >= tolerance {tol:.3e}")
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launches
+    ms = timed(step, args.steps)
+    launches = ctx.launches - l0
+    clocks = sampler.summary()
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e: pinned host buffers, H2D + matvec + D2H every step
+    h_in = torch.from_numpy(cts).pin_memory()
+    h_out = torch.empty((B, 2, c["L"] - 1, c["N"]), dtype=torch.int64).pin_memory()
+
+    def e2e_step():
+        X.upload(h_in.data_ptr(), c["scale"], size=2, L=c["L"])
+        ctx.matvec_bsgs(OUT, X, D, c["n1"], c["n2"])
+        hg._ck(hg.lib().hegpu_ct_download(OUT._h, h_out.data_ptr()))
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    assert np.array_equal(h_out.numpy().view(np.uint64), got), "e2e path result differs from the resident path"
+
+    # ---- per-kernel pass (same steps, events around every launch) -> roofline of the dominant family
+    ctx.profile_reset()
+    ctx.profile(True)
+    for _ in range(args.steps):
+        step()
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    peak, peak_src = measured_peak_gbs()
+    d = prof[dom]
+    achieved = d["algo_bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] else 0.0
+    kernels = {k: {"ms_per_step": v["ms"] / args.steps, "share": v["ms"] / tot_ms, "launches_per_step": v["launches"] // args.steps,
+                   "algo_GBps": (v["algo_bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] else 0.0}
+               for k, v in prof.items() if v["launches"]}
+    ntt_ms = sum(v["ms"] for k, v in prof.items() if "ntt" in k)
+    ntt_bytes = sum(v["algo_bytes"] for k, v in prof.items() if "ntt" in k)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "traffic": None,
+                "avg_launch_ms": d["ms"] / max(d["launches"], 1), "share_of_step": d["ms"] / tot_ms,
+                "all_ntt_kernels": {"achieved": ntt_bytes / (ntt_ms * 1e-3) / 1e9 if ntt_ms else 0.0, "share_of_step": ntt_ms / tot_ms},
+                "kernels": kernels}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "matvecs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": {"workload": "cfg2: CKKS N=16384 {60,40,40,60}, 128x128 plaintext diagonals x encrypted vector, BSGS 16x8",
+                   "batch_per_gpu_per_step": B, "parallelism": f"batch-sharded x{world}, keys and diagonals replicated",
+                   "l2": "no flush: each step streams ~3.5 GB of key-switch scratch per GPU, far beyond the 126 MB L2",
+                   "tolerance": tol, "max_abs_err_vs_numpy": max_err},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "matvecs/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(cts.nbytes),
+                "d2h_bytes_per_step": int(h_out.numel() * 8)},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+
+    # ---- CPU baseline on rank 0, N = 1 only: the oracle on a bounded sample of the same batch
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+
+        threads = orc.max_threads()
+        o = orc.Oracle(c["N"], moduli)
+        bk = [None] + [gk[ctx.galois_elt_from_step(k)] for k in range(1, c["n1"])]
+        gkeys = [None] + [gk[ctx.galois_elt_from_step(g * c["n1"])] for g in range(1, c["n2"])]
+        sample_n = min(B, max(threads, 1) * 2)
+        sub = np.ascontiguousarray(cts[:sample_n])
+        t0 = time.perf_counter()
+        ref_out = o.matvec_bsgs(sub, c["n1"], c["n2"], pts, bk, gkeys, threads=threads)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": sample_n / dt, "unit": "matvecs/s", "cores": threads, "kind": "port",
+                                "sample": f"first {sample_n} of the {B} ciphertexts of one step, same keys/diagonals, {dt:.1f} s wall",
+                                "bit_exact_vs_gpu": bool(np.array_equal(ref_out, got[:sample_n]))}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="hegpu", choices=["hegpu", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

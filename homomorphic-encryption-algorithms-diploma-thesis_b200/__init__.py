@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
         L.hegpu_ctx_psi.argtypes = [C.c_void_p, C.c_uint32]
         L.hegpu_launch_count.restype = C.c_uint64
         L.hegpu_launch_count.argtypes = [C.c_void_p]
+        L.hegpu_profile_kind_name.restype = C.c_char_p
+        L.hegpu_profile_kind_name.argtypes = [C.c_int]
         vp, u32, i32, dbl = C.c_void_p, C.c_uint32, C.c_int, C.c_double
         sigs = {
             "hegpu_ctx_create": [C.POINTER(vp), u32, u64p, u32, i32],
@@ -113,6 +115,9 @@ def lib() -> C.CDLL:
             "hegpu_bfft_stage": [vp, vp, vp, i32, i32],
             "hegpu_fft_butterflies": [vp, vp, vp, vp, vp, vp],
             "hegpu_reduce_fixup": [vp, vp, u32],
+            "hegpu_profile_enable": [vp, i32],
+            "hegpu_profile_reset": [vp],
+            "hegpu_profile_read": [vp, i32, C.POINTER(dbl), u64p, u64p, u64p],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -208,6 +213,7 @@ class Context:
         """host [B][size][L][N] (or [size][L][N] for a batch of one)."""
         if host.ndim == 3:
             host = host[None]
+        host = np.ascontiguousarray(host)
         t = self.ct(host.shape[0], max(size_cap, host.shape[1]), L_cap)
         t.upload(host, scale)
         return t
@@ -215,6 +221,7 @@ class Context:
     def upload_pt(self, host: np.ndarray, scale: float, L_cap: int | None = None) -> "PtSet":
         if host.ndim == 2:
             host = host[None]
+        host = np.ascontiguousarray(host)
         t = self.pt(host.shape[0], L_cap)
         t.upload(host, scale)
         return t
@@ -287,6 +294,26 @@ class Context:
 
     def fft_butterflies(self, out, even, odd, w_pts, one_pt):
         _ck(lib().hegpu_fft_butterflies(self._h, out._h, even._h, odd._h, w_pts._h, one_pt._h))
+
+    # ---- per-kernel timing (bench roofline)
+    def profile(self, on: bool):
+        _ck(lib().hegpu_profile_enable(self._h, int(on)))
+
+    def profile_reset(self):
+        _ck(lib().hegpu_profile_reset(self._h))
+
+    def profile_read(self) -> dict:
+        out = {}
+        k = 0
+        while True:
+            name = lib().hegpu_profile_kind_name(k)
+            if name is None:
+                break
+            ms, la, un, by = C.c_double(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+            _ck(lib().hegpu_profile_read(self._h, k, C.byref(ms), C.byref(la), C.byref(un), C.byref(by)))
+            out[name.decode()] = {"ms": ms.value, "launches": la.value, "units": un.value, "algo_bytes": by.value}
+            k += 1
+        return out
 
     def reduce_fixup(self, ct, terms: int):
         _ck(lib().hegpu_reduce_fixup(self._h, ct._h, terms))

@@ -112,7 +112,25 @@ struct Arena {  // grow-only device scratch, bump-allocated per API call
     size_t cap = 0, off = 0;
 };
 
+enum ProfKind {
+    PK_NTT_FWD_PLAIN, PK_NTT_INV_PLAIN, PK_KS_INTT, PK_KS_LIFT_NTT, PK_KS_INNER, PK_HALF_INTT, PK_KS_MODDOWN_NTT,
+    PK_RESCALE_NTT, PK_BSGS_INNER, PK_TENSOR, PK_ELEMENTWISE, PK_COUNT
+};
+static const char *const kProfNames[PK_COUNT] = { "ntt_fwd_plain", "ntt_inv_plain", "ks_intt", "ks_lift_ntt", "ks_inner",
+                                                  "half_intt", "ks_moddown_ntt", "rescale_ntt", "bsgs_inner", "tensor",
+                                                  "elementwise" };
+struct ProfRec {
+    int kind;
+    cudaEvent_t a, b;
+    u64 units, bytes;
+};
+
 struct hegpu_ctx {
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    double prof_ms[PK_COUNT] = {};
+    u64 prof_launches[PK_COUNT] = {}, prof_units[PK_COUNT] = {}, prof_bytes[PK_COUNT] = {};
     int device = 0;
     cudaStream_t stream = nullptr;
     u32 n = 0, logn = 0, K = 0;
@@ -156,6 +174,35 @@ struct hegpu_pt {
     u32 count, L_cap, L;
     double scale;
     size_t stride() const { return (size_t)L_cap * ctx->n; }
+};
+
+// brackets one launch with events while profiling is enabled
+struct Prof {
+    hegpu_ctx *c;
+    ProfRec r{};
+    bool on;
+    Prof(hegpu_ctx *c_, int kind, u64 units, u64 bytes) : c(c_), on(c_->profiling)
+    {
+        if (!on) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        r.kind = kind;
+        r.units = units;
+        r.bytes = bytes;
+        r.a = get();
+        r.b = get();
+        cudaEventRecord(r.a, c->stream);
+    }
+    ~Prof()
+    {
+        if (!on) return;
+        cudaEventRecord(r.b, c->stream);
+        c->prof.push_back(r);
+    }
 };
 
 static int set_device(hegpu_ctx *c)
@@ -339,6 +386,57 @@ extern "C" void *hegpu_ctx_stream(hegpu_ctx *c) { return c ? (void *)c->stream :
 extern "C" uint64_t hegpu_ctx_psi(hegpu_ctx *c, uint32_t i) { return (c && i < c->K) ? c->psi[i] : 0; }
 extern "C" uint64_t hegpu_launch_count(hegpu_ctx *c) { return c ? c->launches : 0; }
 
+// ------------------------------------------------------------------------- profiling
+static int prof_collect(hegpu_ctx *c)
+{
+    if (c->prof.empty()) return HEGPU_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto &r : c->prof) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, r.a, r.b));
+        c->prof_ms[r.kind] += ms;
+        c->prof_launches[r.kind]++;
+        c->prof_units[r.kind] += r.units;
+        c->prof_bytes[r.kind] += r.bytes;
+        c->ev_pool.push_back(r.a);
+        c->ev_pool.push_back(r.b);
+    }
+    c->prof.clear();
+    return HEGPU_OK;
+}
+extern "C" int hegpu_profile_enable(hegpu_ctx *c, int on)
+{
+    if (!c) INVALID("null context");
+    TRY(set_device(c));
+    TRY(prof_collect(c));
+    c->profiling = on != 0;
+    return HEGPU_OK;
+}
+extern "C" int hegpu_profile_reset(hegpu_ctx *c)
+{
+    if (!c) INVALID("null context");
+    TRY(set_device(c));
+    TRY(prof_collect(c));
+    for (int k = 0; k < PK_COUNT; ++k) {
+        c->prof_ms[k] = 0;
+        c->prof_launches[k] = c->prof_units[k] = c->prof_bytes[k] = 0;
+    }
+    return HEGPU_OK;
+}
+extern "C" const char *hegpu_profile_kind_name(int kind) { return (kind >= 0 && kind < PK_COUNT) ? kProfNames[kind] : nullptr; }
+extern "C" int hegpu_profile_read(hegpu_ctx *c, int kind, double *ms, uint64_t *launches, uint64_t *units, uint64_t *bytes)
+{
+    if (!c) INVALID("null context");
+    if (kind < 0 || kind >= PK_COUNT) INVALID("profile kind out of range");
+    TRY(set_device(c));
+    TRY(prof_collect(c));
+    if (ms) *ms = c->prof_ms[kind];
+    if (launches) *launches = c->prof_launches[kind];
+    if (units) *units = c->prof_units[kind];
+    if (bytes) *bytes = c->prof_bytes[kind];
+    return HEGPU_OK;
+}
+
 // ------------------------------------------------------------------------- keys
 static size_t key_words(hegpu_ctx *c) { return (size_t)(c->K - 1) * 2 * c->K * c->n; }
 
@@ -430,6 +528,7 @@ extern "C" int hegpu_ct_destroy(hegpu_ct *t)
 static int launch_repack(hegpu_ctx *c, CtView dst, CtView src, u32 B, u32 polys, u32 L)
 {
     const size_t total = (size_t)B * polys * L * c->n;
+    Prof pf(c, PK_ELEMENTWISE, total, total * 16);
     repack_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(dst, src, B, polys, L, c->n);
     c->launches++;
     CU(cudaGetLastError());
@@ -521,6 +620,7 @@ static int launch_ew(hegpu_ctx *c, CtView out, CtView a, CtView b, u32 B, u32 po
 {
     EwParams P{ out, a, b, B, polys, L, c->n };
     const size_t total = (size_t)B * polys * L * c->n;
+    Prof pf(c, PK_ELEMENTWISE, total, total * ((OP == EW_NEG || OP == EW_COPY || OP == EW_NEGCOPY_B) ? 16 : 24));
     ew_kernel<OP><<<ew_grid(c, total), 256, 0, c->stream>>>(P, c->d_mods);
     c->launches++;
     CU(cudaGetLastError());
@@ -620,8 +720,9 @@ extern "C" int hegpu_pt_download_one(hegpu_pt *t, uint32_t index, uint64_t *host
 
 // ------------------------------------------------------------------------- NTT launchers
 template <int LOGL, int SPLIT, class Job>
-static int launch_fwd_shape(hegpu_ctx *c, const Job &job, u32 jobs)
+static int launch_fwd_shape(hegpu_ctx *c, const Job &job, u32 jobs, int kind, u64 words_per_job)
 {
+    Prof pf(c, kind, jobs, (u64)jobs * words_per_job * 8 * c->n);
     auto kern = ntt_fwd_kernel<LOGL, SPLIT, Job>;
     static bool configured[16] = {};
     if (!configured[c->device]) {
@@ -633,22 +734,24 @@ static int launch_fwd_shape(hegpu_ctx *c, const Job &job, u32 jobs)
     CU(cudaGetLastError());
     return HEGPU_OK;
 }
+// words_per_job: algorithmic HBM words per coefficient of one job (2 = read + write)
 template <class Job>
-static int launch_ntt_fwd(hegpu_ctx *c, const Job &job, u32 jobs)
+static int launch_ntt_fwd(hegpu_ctx *c, const Job &job, u32 jobs, int kind, u64 words_per_job)
 {
     if (jobs == 0) return HEGPU_OK;
     switch (c->logn) {
-    case 12: return launch_fwd_shape<12, 0>(c, job, jobs);
-    case 13: return launch_fwd_shape<13, 0>(c, job, jobs);
-    case 14: return launch_fwd_shape<14, 0>(c, job, jobs);
-    case 15: return launch_fwd_shape<14, 1>(c, job, jobs);
+    case 12: return launch_fwd_shape<12, 0>(c, job, jobs, kind, words_per_job);
+    case 13: return launch_fwd_shape<13, 0>(c, job, jobs, kind, words_per_job);
+    case 14: return launch_fwd_shape<14, 0>(c, job, jobs, kind, words_per_job);
+    case 15: return launch_fwd_shape<14, 1>(c, job, jobs, kind, words_per_job);
     }
     LOGIC("unsupported ring degree");
 }
 
 template <int LOGL, int SPLIT, class Job>
-static int launch_inv_shape(hegpu_ctx *c, const Job &job, u32 jobs, u64 *scratch)
+static int launch_inv_shape(hegpu_ctx *c, const Job &job, u32 jobs, u64 *scratch, int kind)
 {
+    Prof pf(c, kind, jobs, (u64)jobs * 16 * c->n);
     auto kern = ntt_inv_kernel<LOGL, SPLIT, Job>;
     static bool configured[16] = {};
     if (!configured[c->device]) {
@@ -668,14 +771,14 @@ static int launch_inv_shape(hegpu_ctx *c, const Job &job, u32 jobs, u64 *scratch
 }
 // scratch: [jobs][N] words, only used for N = 32768
 template <class Job>
-static int launch_ntt_inv(hegpu_ctx *c, const Job &job, u32 jobs, u64 *scratch)
+static int launch_ntt_inv(hegpu_ctx *c, const Job &job, u32 jobs, u64 *scratch, int kind)
 {
     if (jobs == 0) return HEGPU_OK;
     switch (c->logn) {
-    case 12: return launch_inv_shape<12, 0>(c, job, jobs, scratch);
-    case 13: return launch_inv_shape<13, 0>(c, job, jobs, scratch);
-    case 14: return launch_inv_shape<14, 0>(c, job, jobs, scratch);
-    case 15: return launch_inv_shape<14, 1>(c, job, jobs, scratch);
+    case 12: return launch_inv_shape<12, 0>(c, job, jobs, scratch, kind);
+    case 13: return launch_inv_shape<13, 0>(c, job, jobs, scratch, kind);
+    case 14: return launch_inv_shape<14, 0>(c, job, jobs, scratch, kind);
+    case 15: return launch_inv_shape<14, 1>(c, job, jobs, scratch, kind);
     }
     LOGIC("unsupported ring degree");
 }
@@ -687,10 +790,10 @@ static int ntt_device(hegpu_ctx *c, void *d, u32 count, u32 first_mod, u32 n_mod
     if (n_mods == 0 || first_mod + n_mods > c->K) INVALID("modulus index out of range");
     TRY(set_device(c));
     PlainJob job{ (const u64 *)d, (u64 *)d, first_mod, n_mods, c->n };
-    if (!inverse) return launch_ntt_fwd(c, job, count);
+    if (!inverse) return launch_ntt_fwd(c, job, count, PK_NTT_FWD_PLAIN, 2);
     const size_t sw = inv_scratch_words(c, count);
     TRY(arena_reserve(c, align256(sw)));
-    return launch_ntt_inv(c, job, count, (u64 *)c->arena.base);
+    return launch_ntt_inv(c, job, count, (u64 *)c->arena.base, PK_NTT_INV_PLAIN);
 }
 extern "C" int hegpu_ntt_forward_device(hegpu_ctx *c, void *d, uint32_t count, uint32_t first_mod, uint32_t n_mods)
 {
@@ -884,6 +987,7 @@ static int multiply_impl(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a, const h
     vb.sb = bsb;
     EwParams P{ out->view(), a->view(), vb, B, so, a->L, c->n };
     const size_t total = (size_t)B * a->L * c->n;
+    Prof pf(c, PK_TENSOR, total, total * (square ? 40 : 56));
     if (a->size == 2 && b->size == 2) {
         if (square)
             tensor_kernel<true><<<ew_grid(c, total), 256, 0, c->stream>>>(P, c->d_mods);
@@ -911,9 +1015,9 @@ static int rescale_views(hegpu_ctx *c, CtView out, CtView a, u32 B, u32 size, u3
     u64 *t = ap.take((size_t)jobs * c->n);
     u64 *scr = ap.take(inv_scratch_words(c, jobs));
     HalfInttJob hj{ a.p + (size_t)(L - 1) * a.sl, t, a.sb, a.sp, size, L - 1, c->n };
-    TRY(launch_ntt_inv(c, hj, jobs, scr));
+    TRY(launch_ntt_inv(c, hj, jobs, scr, PK_HALF_INTT));
     RescaleJob rj{ a, out, t, c->d_md + (size_t)(L - 1) * c->K, c->d_mods, size, L - 1, L - 1, c->n };
-    TRY(launch_ntt_fwd(c, rj, jobs * (L - 1)));
+    TRY(launch_ntt_fwd(c, rj, jobs * (L - 1), PK_RESCALE_NTT, 3));
     return HEGPU_OK;
 }
 
@@ -987,19 +1091,21 @@ static int keyswitch(hegpu_ctx *c, const KsGroupDesc *groups, u32 ngroups, u32 B
     u64 *scr = ap.take(inv_scratch_words(c, E * std::max<u32>(L, 2)));
 
     KsInttJob j1{ P };
-    TRY(launch_ntt_inv(c, j1, (u32)(E * L), scr));
+    TRY(launch_ntt_inv(c, j1, (u32)(E * L), scr, PK_KS_INTT));
     KsLiftJob j2{ P, c->d_mods };
-    TRY(launch_ntt_fwd(c, j2, (u32)(E * L * L)));
+    TRY(launch_ntt_fwd(c, j2, (u32)(E * L * L), PK_KS_LIFT_NTT, 2));
     {
         const size_t total = E * (L + 1) * n;
+        // per (e,i,x): L digits + 2L key words read, 2 written
+        Prof pf(c, PK_KS_INNER, total, total * 8 * (3 * L + 2));
         ks_inner_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(P, c->d_mods);
         c->launches++;
         CU(cudaGetLastError());
     }
     HalfInttJob j4{ P.acc + (size_t)L * n, P.t, (size_t)(L + 1) * n, 0, 1, c->K - 1, c->n };
-    TRY(launch_ntt_inv(c, j4, (u32)(E * 2), scr));
+    TRY(launch_ntt_inv(c, j4, (u32)(E * 2), scr, PK_HALF_INTT));
     KsModDownJob j5{ P, c->d_md + (size_t)(c->K - 1) * c->K, c->d_mods };
-    TRY(launch_ntt_fwd(c, j5, (u32)(E * 2 * L)));
+    TRY(launch_ntt_fwd(c, j5, (u32)(E * 2 * L), PK_KS_MODDOWN_NTT, has_base1 ? 4 : 3));
     return HEGPU_OK;
 }
 
@@ -1092,9 +1198,9 @@ extern "C" int hegpu_rotate_vector(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *
     if (!c || !out) INVALID("null argument");
     TRY(check_ct(a));
     if (a->size > 2) INVALID("encrypted size must be 2");
-    if (c->galois_keys.empty() && steps != 0) INVALID("Galois key not present");
     u32 elt;
     TRY(hegpu_galois_elt_from_step(c, steps, &elt));
+    if (c->galois_keys.empty() && steps != 0) INVALID("Galois key not present");
     if (steps != 0 && c->galois_keys.count(elt) && out != a) return hegpu_apply_galois(c, out, a, elt);
     TRY(hegpu_ct_copy(c, out, a));
     return rotate_internal(c, out, steps);
@@ -1108,6 +1214,7 @@ extern "C" int hegpu_reduce_fixup(hegpu_ctx *c, hegpu_ct *t, uint32_t terms)
     if (terms == 0 || terms > 16) INVALID("at most 16 partial sums of 60-bit residues fit in 64 bits");
     TRY(set_device(c));
     const size_t total = (size_t)t->batch * t->size * t->L * c->n;
+    Prof pf(c, PK_ELEMENTWISE, total, total * 16);
     fixup_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(t->view(), t->batch, t->size, t->L, c->n, c->d_mods);
     c->launches++;
     CU(cudaGetLastError());
@@ -1192,6 +1299,8 @@ extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in
             P.L = L;
             P.n = c->n;
             const size_t total = (size_t)Bn * ctw;
+            // rotated ciphertexts read once, inner sums written once, diagonals read once per step
+            Prof pf(c, PK_BSGS_INNER, total, total * 8 * (n1 + n2) + (u64)n1 * n2 * L * n * 8);
             switch (n1) {
             case 1: launch_bsgs_inner<1>(c, P, total); break;
             case 2: launch_bsgs_inner<2>(c, P, total); break;
@@ -1230,6 +1339,7 @@ extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in
             CtView dst = rescale ? view_of(accb, 0) : out->view_at(b0);
             SumParams S{ view_of(inner, 0), view_of(rot, 0), dst, n2, Bn, 2, L, c->n };
             const size_t total = (size_t)Bn * ctw;
+            Prof pf(c, PK_ELEMENTWISE, total, total * 8 * (n2 + 1));
             sum_terms_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(S, c->d_mods);
             c->launches++;
             CU(cudaGetLastError());
@@ -1293,6 +1403,7 @@ extern "C" int hegpu_bmatmul(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *ths, c
             CtView first = prod.t->view_at(0), rest = prod.t->view_at(n > 1 ? 1 : 0);
             SumParams S{ first, rest, acc.t->view_at(i), n, 1, 3, L, c->n };
             const size_t total = (size_t)3 * L * c->n;
+            Prof pf(c, PK_ELEMENTWISE, total, total * 8 * (n + 1));
             sum_terms_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(S, c->d_mods);
             c->launches++;
             CU(cudaGetLastError());
@@ -1364,6 +1475,7 @@ extern "C" int hegpu_matmul_elemwise(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct
     TmpCt acc;
     TRY(hegpu_ct_create(c, &acc.t, rows * cols, 3, a->L));
     const size_t total = (size_t)rows * cols * a->L * c->n;
+    Prof pf(c, PK_TENSOR, total, total * 8 * (4 * inner + 3));
     matmul_tensor_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(acc.t->view(), a->view(), b->view(), rows, inner, cols, at, bt,
                                                                     a->L, c->n, c->d_mods);
     c->launches++;

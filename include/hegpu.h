@@ -169,6 +169,16 @@ int hegpu_bfft_stage(hegpu_ctx *ctx, hegpu_ct *y, const hegpu_pt *stage_pts, int
 int hegpu_fft_butterflies(hegpu_ctx *ctx, hegpu_ct *out, const hegpu_ct *even, const hegpu_ct *odd,
                           const hegpu_pt *w_pts, const hegpu_pt *one_pt);
 
+/* ---- per-kernel timing for bench.py's roofline (CUDA events on the context's stream around
+ * every launch while enabled).  kind indexes the kernel families; hegpu_profile_kind_name
+ * returns the family name or NULL past the end.  units = limb polynomials (NTT kernels) or
+ * coefficients (element-wise kernels); algo_bytes = algorithmic HBM bytes. */
+int hegpu_profile_enable(hegpu_ctx *ctx, int on);
+int hegpu_profile_reset(hegpu_ctx *ctx);
+const char *hegpu_profile_kind_name(int kind);
+int hegpu_profile_read(hegpu_ctx *ctx, int kind, double *ms_total, uint64_t *launches, uint64_t *units,
+                       uint64_t *algo_bytes);
+
 /* ---- multi-GPU: after an NCCL uint64 sum of `terms` partial ciphertexts the
  * residues are < terms*q; reduce them back to [0,q). */
 int hegpu_reduce_fixup(hegpu_ctx *ctx, hegpu_ct *ct, uint32_t terms);

@@ -16,6 +16,14 @@ def rand_residues(rng, moduli, prefix, n):
     return out
 
 
+def ckks_tol(n_terms, N, scale):
+    """Decryption tolerance for a sum of n_terms key-switched products (DESIGN.md "Tolerance"):
+    SEAL's RNS digits are non-centred ([0,q_j)), so the key-switch noise sum_j c_j*e_j/P is a
+    random walk of amplitude ~sigma*sqrt(N)/2 whose energy concentrates in the slots whose roots
+    lie next to 1; the worst slot sees ~0.1*sigma*N^1.5/scale per key-switch (sigma = 3.2)."""
+    return n_terms * 3.2 * N**1.5 / (8.0 * scale)
+
+
 class Setup:
     """One parameter set with an oracle, an encoder, a secret key and lazily generated keys."""
 

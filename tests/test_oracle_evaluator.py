@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 import ckks_ref as ref
+from fixtures import ckks_tol
 from oracle import oracle as orc
 
 
@@ -155,5 +156,5 @@ def test_matvec_bsgs_decrypts_to_matvec():
     gkeys = [None] + [o.gen_galois_key(300 + g, s, orc.galois_elt_from_step(n, g * n1)) for g in range(1, n2)]
     out = o.matvec_bsgs(ct[None], n1, n2, pts, bk, gkeys, threads=2)
     got = enc.decode(o.decrypt(out[0], s), scale * scale / moduli[2]).real[:dim]
-    tol = 8 * np.sqrt(dim) * 2.0 ** -(40 - 16)  # CKKS scale-derived tolerance
+    tol = ckks_tol(dim, n, scale)
     assert np.max(np.abs(got - M @ v)) < tol
