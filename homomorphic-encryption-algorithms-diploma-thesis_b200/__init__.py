@@ -280,8 +280,9 @@ class Context:
         _ck(lib().hegpu_apply_galois(self._h, out._h, a._h, elt))
 
     # ---- composites
-    def matvec_bsgs(self, out, a, diags, n1: int, n2: int, rescale: bool = True):
-        _ck(lib().hegpu_matvec_bsgs(self._h, out._h, a._h, diags._h, n1, n2, int(rescale)))
+    def matvec_bsgs(self, out, a, diags, n1: int, n2: int, rescale: bool = True, hoist: bool = False):
+        """hoist=True selects HEGPU_MATVEC_HOIST (hoisted baby steps + one mod-down for the giant steps)."""
+        _ck(lib().hegpu_matvec_bsgs(self._h, out._h, a._h, diags._h, n1, n2, (1 if rescale else 0) | (2 if hoist else 0)))
 
     def bmatmul(self, out, this_cts, other_cts, n: int, p: int, case_b: bool):
         _ck(lib().hegpu_bmatmul(self._h, out._h, this_cts._h, other_cts._h, n, p, int(case_b)))

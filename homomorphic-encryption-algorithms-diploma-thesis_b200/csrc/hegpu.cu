@@ -138,6 +138,8 @@ struct hegpu_ctx {
     std::vector<int> level_bits;  // total_coeff_modulus_bit_count for L = 1..K
     // device tables
     ulonglong2 *d_fwd = nullptr, *d_inv = nullptr, *d_inv_last = nullptr;
+    double *d_fwd_d = nullptr, *d_inv_d = nullptr;
+    ModF64 *d_modsd = nullptr;
     ModConst *d_mods = nullptr;
     MdConst *d_md = nullptr;  // [K][K]: row d = dropped modulus, column i = target limb
     NttTables tabs{};
@@ -303,6 +305,8 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     std::vector<ulonglong2> fwd((size_t)K * n), inv((size_t)K * n), inv_last(K);
     std::vector<ModConst> mods(K);
     std::vector<MdConst> md((size_t)K * K);
+    std::vector<double> fwd_d((size_t)K * n), inv_d((size_t)K * n);
+    std::vector<ModF64> modsd(K);
     for (u32 i = 0; i < K; ++i) {
         const u64 q = c->q[i];
         const u64 psi = h_min_root(q, n), ipsi = h_invmod(psi, q);
@@ -312,6 +316,8 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
             const u32 r = h_brev(k, c->logn);
             fwd[(size_t)i * n + r] = make_ulonglong2(p, h_shoup(p, q));
             inv[(size_t)i * n + r] = make_ulonglong2(ip, h_shoup(ip, q));
+            fwd_d[(size_t)i * n + r] = (double)p;  // exact below 2^53; only used when q < 2^43
+            inv_d[(size_t)i * n + r] = (double)ip;
             p = h_mulmod(p, psi, q);
             ip = h_mulmod(ip, ipsi, q);
         }
@@ -322,10 +328,12 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
         m.mu_lo = (u64)mu;
         m.ninv = h_invmod(n % q, q);
         m.ninv_sh = h_shoup(m.ninv, q);
-        m.big = (q >> 58 ? 1u : 0u) | (q >> 46 ? 2u : 0u);
+        // bit 0: forward needs corrections; bit 1: inverse needs corrections; bit 2: FP64 butterflies
+        m.big = (q >> 58 ? 1u : 0u) | (q >> 46 ? 2u : 0u) | ((q >> 43) == 0 && !getenv("HEGPU_NO_FP64") ? 4u : 0u);
         m.pad = 0;
         const u64 wl = h_mulmod(inv[(size_t)i * n + 1].x, m.ninv, q);
         inv_last[i] = make_ulonglong2(wl, h_shoup(wl, q));
+        modsd[i] = ModF64{ (double)q, 1.0 / (double)q, (double)m.ninv, (double)wl };
         for (u32 d = 0; d < K; ++d) {
             MdConst &e = md[(size_t)d * K + i];
             e.pad = 0;
@@ -340,6 +348,12 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     CU(cudaMalloc(&c->d_inv_last, inv_last.size() * sizeof(ulonglong2)));
     CU(cudaMalloc(&c->d_mods, mods.size() * sizeof(ModConst)));
     CU(cudaMalloc(&c->d_md, md.size() * sizeof(MdConst)));
+    CU(cudaMalloc(&c->d_fwd_d, fwd_d.size() * sizeof(double)));
+    CU(cudaMalloc(&c->d_inv_d, inv_d.size() * sizeof(double)));
+    CU(cudaMalloc(&c->d_modsd, modsd.size() * sizeof(ModF64)));
+    CU(cudaMemcpy(c->d_fwd_d, fwd_d.data(), fwd_d.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_inv_d, inv_d.data(), inv_d.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_modsd, modsd.data(), modsd.size() * sizeof(ModF64), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_fwd, fwd.data(), fwd.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_inv, inv.data(), inv.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_inv_last, inv_last.data(), inv_last.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice));
@@ -349,6 +363,9 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     c->tabs.inv = c->d_inv;
     c->tabs.inv_last = c->d_inv_last;
     c->tabs.mods = c->d_mods;
+    c->tabs.fwd_d = c->d_fwd_d;
+    c->tabs.inv_d = c->d_inv_d;
+    c->tabs.modsd = c->d_modsd;
     c->tabs.n = n;
     c->tabs.logn = c->logn;
     *out = c;
@@ -365,6 +382,9 @@ extern "C" int hegpu_ctx_destroy(hegpu_ctx *c)
     cudaFree(c->d_inv_last);
     cudaFree(c->d_mods);
     cudaFree(c->d_md);
+    cudaFree(c->d_fwd_d);
+    cudaFree(c->d_inv_d);
+    cudaFree(c->d_modsd);
     cudaFree(c->relin_key);
     for (auto &kv : c->galois_keys) cudaFree(kv.second);
     for (auto &kv : c->perms) cudaFree(kv.second);
@@ -1063,14 +1083,20 @@ static size_t ks_scratch(hegpu_ctx *c, size_t E, u32 L)
     return align256(E * L * n) + align256(E * L * (L + 1) * n) + align256(E * 2 * (L + 1) * n) + align256(E * 2 * n) +
            align256(inv_scratch_words(c, E * std::max<u32>(L, 2)));
 }
-// Evaluator::switch_key_inplace for ngroups x B ciphertexts.  out must not
-// alias in when perm != null.
-static int keyswitch(hegpu_ctx *c, const KsGroupDesc *groups, u32 ngroups, u32 B, u32 L, u32 target_poly, bool has_base1,
-                     ArenaPlan &ap)
+// Evaluator::switch_key_inplace for ngroups x B ciphertexts, in three phases so
+// that composites can hoist the decomposition or defer the mod-down.
+struct KsPlan {
+    KsParams P;
+    size_t E;   // ngroups * B
+    u64 *scr;   // INTT scratch (N = 32768 only)
+};
+static int ks_setup(hegpu_ctx *c, KsPlan &pl, const KsGroupDesc *groups, u32 ngroups, u32 B, u32 L, u32 target_poly,
+                    bool has_base1, bool hoisted, ArenaPlan &ap)
 {
-    if (ngroups == 0 || B == 0) return HEGPU_OK;
     const size_t E = (size_t)ngroups * B, n = c->n;
-    KsParams P{};
+    const size_t EA = hoisted ? B : E;  // elements that are decomposed
+    KsParams &P = pl.P;
+    P = KsParams{};
     P.ngroups = ngroups;
     P.B = B;
     P.L = L;
@@ -1078,34 +1104,75 @@ static int keyswitch(hegpu_ctx *c, const KsGroupDesc *groups, u32 ngroups, u32 B
     P.n = c->n;
     P.target_poly = target_poly;
     P.has_base1 = has_base1 ? 1u : 0u;
+    P.hoisted = hoisted ? 1u : 0u;
     for (u32 g = 0; g < ngroups; ++g) {
         P.in[g] = groups[g].in;
         P.out[g] = groups[g].out;
         P.key[g] = groups[g].key;
         P.perm[g] = groups[g].perm;
     }
-    P.coef = ap.take(E * L * n);
-    P.ext = ap.take(E * L * (L + 1) * n);
+    P.coef = ap.take(EA * L * n);
+    P.ext = ap.take(EA * L * (L + 1) * n);
     P.acc = ap.take(E * 2 * (L + 1) * n);
     P.t = ap.take(E * 2 * n);
-    u64 *scr = ap.take(inv_scratch_words(c, E * std::max<u32>(L, 2)));
-
-    KsInttJob j1{ P };
-    TRY(launch_ntt_inv(c, j1, (u32)(E * L), scr, PK_KS_INTT));
-    KsLiftJob j2{ P, c->d_mods };
-    TRY(launch_ntt_fwd(c, j2, (u32)(E * L * L), PK_KS_LIFT_NTT, 2));
-    {
-        const size_t total = E * (L + 1) * n;
-        // per (e,i,x): L digits + 2L key words read, 2 written
-        Prof pf(c, PK_KS_INNER, total, total * 8 * (3 * L + 2));
-        ks_inner_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(P, c->d_mods);
-        c->launches++;
-        CU(cudaGetLastError());
+    pl.E = E;
+    pl.scr = ap.take(inv_scratch_words(c, E * std::max<u32>(L, 2)));
+    return HEGPU_OK;
+}
+// steps 1-2: c_j = INTT(pi(target)_j); ext[j][i] = NTT_{m_i}(c_j mod m_i)
+static int ks_decompose(hegpu_ctx *c, KsPlan &pl)
+{
+    const u32 L = pl.P.L;
+    const size_t EA = pl.P.hoisted ? pl.P.B : pl.E;
+    KsParams PA = pl.P;
+    if (pl.P.hoisted) PA.ngroups = 1;
+    KsInttJob j1{ PA };
+    TRY(launch_ntt_inv(c, j1, (u32)(EA * L), pl.scr, PK_KS_INTT));
+    KsLiftJob j2{ PA, c->d_mods };
+    TRY(launch_ntt_fwd(c, j2, (u32)(EA * L * L), PK_KS_LIFT_NTT, 2));
+    return HEGPU_OK;
+}
+// step 3: key inner product into acc[E][2][L+1][N]
+static int ks_inner(hegpu_ctx *c, KsPlan &pl)
+{
+    const KsParams &P = pl.P;
+    const u32 L = P.L, B = P.B, ngroups = P.ngroups;
+    const size_t total = pl.E * (L + 1) * c->n;
+    // per (e,i,x): L digits read + 2 written; the 2L key words are read once per batch chunk
+    Prof pf(c, PK_KS_INNER, total, total * 8 * (L + 2) + (u64)ngroups * (L + 1) * c->n * 16 * L);
+    dim3 grid((c->n + 255) / 256, ngroups * (L + 1), (B + KS_INNER_BCHUNK - 1) / KS_INNER_BCHUNK);
+    switch (L) {
+    case 1: ks_inner_kernel<1><<<grid, 256, 0, c->stream>>>(P, c->d_mods); break;
+    case 2: ks_inner_kernel<2><<<grid, 256, 0, c->stream>>>(P, c->d_mods); break;
+    case 3: ks_inner_kernel<3><<<grid, 256, 0, c->stream>>>(P, c->d_mods); break;
+    case 4: ks_inner_kernel<4><<<grid, 256, 0, c->stream>>>(P, c->d_mods); break;
+    default: ks_inner_kernel<0><<<grid, 256, 0, c->stream>>>(P, c->d_mods); break;
     }
-    HalfInttJob j4{ P.acc + (size_t)L * n, P.t, (size_t)(L + 1) * n, 0, 1, c->K - 1, c->n };
-    TRY(launch_ntt_inv(c, j4, (u32)(E * 2), scr, PK_HALF_INTT));
+    c->launches++;
+    CU(cudaGetLastError());
+    return HEGPU_OK;
+}
+// steps 4-5: mod-down by P with rounding, add the base ciphertext, write out
+static int ks_moddown(hegpu_ctx *c, KsPlan &pl)
+{
+    const KsParams &P = pl.P;
+    const u32 L = P.L;
+    HalfInttJob j4{ P.acc + (size_t)L * c->n, P.t, (size_t)(L + 1) * c->n, 0, 1, c->K - 1, c->n };
+    TRY(launch_ntt_inv(c, j4, (u32)(pl.E * 2), pl.scr, PK_HALF_INTT));
     KsModDownJob j5{ P, c->d_md + (size_t)(c->K - 1) * c->K, c->d_mods };
-    TRY(launch_ntt_fwd(c, j5, (u32)(E * 2 * L), PK_KS_MODDOWN_NTT, has_base1 ? 4 : 3));
+    TRY(launch_ntt_fwd(c, j5, (u32)(pl.E * 2 * L), PK_KS_MODDOWN_NTT, P.has_base1 ? 4 : 3));
+    return HEGPU_OK;
+}
+// out must not alias in when perm != null.
+static int keyswitch(hegpu_ctx *c, const KsGroupDesc *groups, u32 ngroups, u32 B, u32 L, u32 target_poly, bool has_base1,
+                     ArenaPlan &ap, bool hoisted = false)
+{
+    if (ngroups == 0 || B == 0) return HEGPU_OK;
+    KsPlan pl;
+    TRY(ks_setup(c, pl, groups, ngroups, B, L, target_poly, has_base1, hoisted, ap));
+    TRY(ks_decompose(c, pl));
+    TRY(ks_inner(c, pl));
+    TRY(ks_moddown(c, pl));
     return HEGPU_OK;
 }
 
@@ -1223,14 +1290,16 @@ extern "C" int hegpu_reduce_fixup(hegpu_ctx *c, hegpu_ct *t, uint32_t terms)
 
 // ------------------------------------------------------------------------- composites
 template <int N1>
-static void launch_bsgs_inner(hegpu_ctx *c, const BsgsParams &P, size_t total)
+static void launch_bsgs_inner(hegpu_ctx *c, const BsgsParams &P, size_t)
 {
-    bsgs_inner_kernel<N1><<<ew_grid(c, total), 256, 0, c->stream>>>(P, c->d_mods);
+    dim3 grid(P.n / 32, P.L, (P.n2 + BSGS_GT - 1) / BSGS_GT), block(32, BSGS_GT);
+    bsgs_inner_kernel<N1><<<grid, block, 0, c->stream>>>(P, c->d_mods);
 }
 
 extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, uint32_t n1,
-                                 uint32_t n2, int rescale)
+                                 uint32_t n2, int flags)
 {
+    const bool rescale = (flags & HEGPU_MATVEC_RESCALE) != 0, fast = (flags & HEGPU_MATVEC_HOIST) != 0;
     if (!c || !out || !diags) INVALID("null argument");
     TRY(check_ct(in));
     if (in->size != 2) INVALID("encrypted size must be 2");
@@ -1257,7 +1326,8 @@ extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in
     auto need = [&](u32 Bc) {
         const u32 gmax = std::min<u32>(MAXG, std::max(n1 - 1, n2 - 1));
         return ks_scratch(c, (size_t)gmax * Bc, L) + align256((size_t)(n1 - 1) * Bc * ctw) + align256((size_t)n2 * Bc * ctw) +
-               align256((size_t)(n2 - 1) * Bc * ctw) + align256((size_t)Bc * ctw) + rescale_scratch(c, Bc, 2);
+               align256((size_t)(n2 - 1) * Bc * ctw) + align256((size_t)Bc * ctw) + rescale_scratch(c, Bc, 2) +
+               align256((size_t)Bc * 2 * (L + 1) * n) + align256((size_t)Bc * 2 * n);
     };
     u32 Bc = B;
     while (Bc > 1 && need(Bc) > c->ws_budget) Bc = (Bc + 1) / 2;
@@ -1282,7 +1352,7 @@ extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in
                 gs[ng] = KsGroupDesc{ vin, view_of(baby, (size_t)(k - 1) * Bn), c->galois_keys[belt[k]], pm };
             }
             ap.off = ks_off;
-            TRY(keyswitch(c, gs, ng, Bn, L, 1, false, ap));
+            TRY(keyswitch(c, gs, ng, Bn, L, 1, false, ap, fast));
         }
         // 2. inner sums for every giant step
         {
@@ -1322,31 +1392,89 @@ extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in
             c->launches++;
             CU(cudaGetLastError());
         }
-        // 3. giant steps
-        for (u32 g0 = 1; g0 < n2; g0 += MAXG) {
-            KsGroupDesc gs[MAXG];
-            u32 ng = 0;
-            for (u32 g = g0; g < n2 && ng < (u32)MAXG; ++g, ++ng) {
-                const u32 *pm;
-                TRY(get_perm(c, gelt[g], &pm));
-                gs[ng] = KsGroupDesc{ view_of(inner, (size_t)g * Bn), view_of(rot, (size_t)(g - 1) * Bn), c->galois_keys[gelt[g]], pm };
+        CtView dst = rescale ? view_of(accb, 0) : out->view_at(b0);
+        if (!fast || n2 == 1) {
+            // 3. giant steps, 4. accumulate
+            for (u32 g0 = 1; g0 < n2; g0 += MAXG) {
+                KsGroupDesc gs[MAXG];
+                u32 ng = 0;
+                for (u32 g = g0; g < n2 && ng < (u32)MAXG; ++g, ++ng) {
+                    const u32 *pm;
+                    TRY(get_perm(c, gelt[g], &pm));
+                    gs[ng] = KsGroupDesc{ view_of(inner, (size_t)g * Bn), view_of(rot, (size_t)(g - 1) * Bn), c->galois_keys[gelt[g]], pm };
+                }
+                ap.off = ks_off;
+                TRY(keyswitch(c, gs, ng, Bn, L, 1, false, ap));
             }
-            ap.off = ks_off;
-            TRY(keyswitch(c, gs, ng, Bn, L, 1, false, ap));
-        }
-        // 4. accumulate, 5. rescale
-        {
-            CtView dst = rescale ? view_of(accb, 0) : out->view_at(b0);
             SumParams S{ view_of(inner, 0), view_of(rot, 0), dst, n2, Bn, 2, L, c->n };
             const size_t total = (size_t)Bn * ctw;
             Prof pf(c, PK_ELEMENTWISE, total, total * 8 * (n2 + 1));
             sum_terms_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(S, c->d_mods);
             c->launches++;
             CU(cudaGetLastError());
-            if (rescale) {
-                ap.off = ks_off;
-                TRY(rescale_views(c, out->view_at(b0), dst, Bn, 2, L, ap));
+        } else {
+            // 3'. giant steps with ONE mod-down: the key inner products of all giant steps are summed
+            // in the extended basis (mod q_0..q_{L-1}, P) and divided by P once.
+            if (n2 - 1 > (u32)MAXG) INVALID("hoisted matvec supports at most 17 giant steps");
+            ap.off = ks_off;
+            u64 *accsum = ap.take((size_t)Bn * 2 * (L + 1) * n);
+            u64 *tsum = ap.take((size_t)Bn * 2 * n);
+            KsGroupDesc gs[MAXG];
+            BaseSumParams BS{};
+            const u32 ng = n2 - 1;
+            for (u32 g = 1; g < n2; ++g) {
+                const u32 *pm;
+                TRY(get_perm(c, gelt[g], &pm));
+                gs[g - 1] = KsGroupDesc{ view_of(inner, (size_t)g * Bn), view_of(rot, (size_t)(g - 1) * Bn), c->galois_keys[gelt[g]], pm };
+                BS.perm[g - 1] = pm;
             }
+            KsPlan pl;
+            TRY(ks_setup(c, pl, gs, ng, Bn, L, 1, false, false, ap));
+            TRY(ks_decompose(c, pl));
+            TRY(ks_inner(c, pl));
+            {
+                const size_t total = (size_t)Bn * 2 * (L + 1) * n;
+                Prof pf(c, PK_ELEMENTWISE, total, total * 8 * (ng + 1));
+                acc_group_sum_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(pl.P.acc, accsum, ng, Bn, L, c->K, c->n, c->d_mods);
+                c->launches++;
+                CU(cudaGetLastError());
+            }
+            {   // base = inner_0 + sum_g pi_g(inner_g.c0)   (written into rot[0..Bn), free by now)
+                BS.first = view_of(inner, 0);
+                BS.rest = view_of(inner, (size_t)Bn);
+                BS.out = view_of(rot, 0);
+                BS.groups = ng;
+                BS.B = Bn;
+                BS.L = L;
+                BS.n = c->n;
+                const size_t total = (size_t)Bn * ctw;
+                Prof pf(c, PK_ELEMENTWISE, total, total * 8 * 2 + (size_t)Bn * L * n * 8 * ng);
+                base_gather_sum_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(BS, c->d_mods);
+                c->launches++;
+                CU(cudaGetLastError());
+            }
+            KsGroupDesc one{ view_of(rot, 0), dst, nullptr, nullptr };
+            KsPlan pm1;
+            pm1.P = KsParams{};
+            pm1.P.ngroups = 1;
+            pm1.P.B = Bn;
+            pm1.P.L = L;
+            pm1.P.K = c->K;
+            pm1.P.n = c->n;
+            pm1.P.target_poly = 1;
+            pm1.P.has_base1 = 1;
+            pm1.P.in[0] = one.in;
+            pm1.P.out[0] = one.out;
+            pm1.P.acc = accsum;
+            pm1.P.t = tsum;
+            pm1.E = Bn;
+            pm1.scr = pl.scr;
+            TRY(ks_moddown(c, pm1));
+        }
+        // 5. rescale
+        if (rescale) {
+            ap.off = ks_off;
+            TRY(rescale_views(c, out->view_at(b0), dst, Bn, 2, L, ap));
         }
     }
     out->size = 2;

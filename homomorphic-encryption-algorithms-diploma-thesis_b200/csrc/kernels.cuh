@@ -47,6 +47,8 @@ struct KsParams {
     u32 ngroups, B, L, K, n;
     u32 target_poly;  // 1: Galois (switch pi(c1)); 2: relinearise (switch c2)
     u32 has_base1;    // add in[1] to component 1 (relinearise)
+    u32 hoisted;      // all groups rotate the same input: INTT + lift run once per ciphertext (no
+                      // gather) and the Galois permutation is applied to the lifted digits instead
     CtView in[MAXG];
     CtView out[MAXG];
     const u64 *key[MAXG];   // [Lmax][2][K][N]
@@ -65,7 +67,7 @@ struct KsInttJob {
     {
         const u32 e = j / P.L, l = j % P.L, g = e / P.B, b = e % P.B;
         const CtView &v = P.in[g];
-        const u32 *pm = P.perm[g];
+        const u32 *pm = P.hoisted ? nullptr : P.perm[g];
         const u32 src = pm ? __ldg(pm + i) : i;
         return v.p[b * v.sb + P.target_poly * v.sp + l * v.sl + src];
     }
@@ -200,12 +202,15 @@ __global__ void __launch_bounds__(NttShape<LOGL>::THREADS, 1) ntt_fwd_kernel(con
     const ulonglong2 *tw = T.fwd + (size_t)mi * T.n;
     const u32 boff = h << LOGL;
     auto store = [&](u32 i, u64 v) { job.store(jid, boff + i, v, m); };
+    const ulonglong2 nowl = make_ulonglong2(0, 0);
     if constexpr (SPLIT == 0) {
         auto load = [&](u32 i) -> u64 { return job.load(jid, i, m); };
-        if (m.big & 1u)
-            ntt_fwd_cta<LOGL, true>(load, store, tw, T.n, m, sm);
+        if (m.big & 4u)
+            ntt_fwd_cta<LOGL>(load, store, T.fwd_d + (size_t)mi * T.n, T.n, ArF64(T.modsd[mi]), sm);
+        else if (m.big & 1u)
+            ntt_fwd_cta<LOGL>(load, store, tw, T.n, ArI64<true>(m, nowl), sm);
         else
-            ntt_fwd_cta<LOGL, false>(load, store, tw, T.n, m, sm);
+            ntt_fwd_cta<LOGL>(load, store, tw, T.n, ArI64<false>(m, nowl), sm);
     } else {
         // stage 1 (stride N/2) redone from global memory by both halves
         const ulonglong2 W = __ldg(tw + 1);
@@ -217,9 +222,9 @@ __global__ void __launch_bounds__(NttShape<LOGL>::THREADS, 1) ntt_fwd_kernel(con
             return h ? X + q2 - Tm : X + Tm;
         };
         if (m.big & 1u)
-            ntt_fwd_cta<LOGL, true>(load, store, tw, T.n + boff, m, sm);
+            ntt_fwd_cta<LOGL>(load, store, tw, T.n + boff, ArI64<true>(m, nowl), sm);
         else
-            ntt_fwd_cta<LOGL, false>(load, store, tw, T.n + boff, m, sm);
+            ntt_fwd_cta<LOGL>(load, store, tw, T.n + boff, ArI64<false>(m, nowl), sm);
     }
 }
 
@@ -240,17 +245,19 @@ __global__ void __launch_bounds__(NttShape<LOGL>::THREADS, 1)
     auto load = [&](u32 i) -> u64 { return job.load(jid, boff + i, m); };
     if constexpr (SPLIT == 0) {
         auto store = [&](u32 i, u64 v) { job.store(jid, i, v, m); };
-        if (m.big & 2u)
-            ntt_inv_cta<LOGL, true, LOGL - 1>(load, store, tw, T.n, m, wl, sm);
+        if (m.big & 4u)
+            ntt_inv_cta<LOGL, LOGL - 1>(load, store, T.inv_d + (size_t)mi * T.n, T.n, ArF64(T.modsd[mi]), sm);
+        else if (m.big & 2u)
+            ntt_inv_cta<LOGL, LOGL - 1>(load, store, tw, T.n, ArI64<true>(m, wl), sm);
         else
-            ntt_inv_cta<LOGL, false, LOGL - 1>(load, store, tw, T.n, m, wl, sm);
+            ntt_inv_cta<LOGL, LOGL - 1>(load, store, tw, T.n, ArI64<false>(m, wl), sm);
     } else {
         u64 *dst = scratch + (size_t)jid * T.n + boff;
         auto store = [&](u32 i, u64 v) { dst[i] = v; };
         if (m.big & 2u)
-            ntt_inv_cta<LOGL, true, -1>(load, store, tw, T.n + boff, m, wl, sm);
+            ntt_inv_cta<LOGL, -1>(load, store, tw, T.n + boff, ArI64<true>(m, wl), sm);
         else
-            ntt_inv_cta<LOGL, false, -1>(load, store, tw, T.n + boff, m, wl, sm);
+            ntt_inv_cta<LOGL, -1>(load, store, tw, T.n + boff, ArI64<false>(m, wl), sm);
     }
 }
 
@@ -283,38 +290,63 @@ __global__ void __launch_bounds__(256) ntt_inv_final_kernel(const Job job, const
 // ---------------------------------------------------------------------------------------
 // K7 step 3: key inner product.  acc[e][c][i] = sum_j ext[e][j][i] (.) key[j][c][ki] mod m_i;
 // digit i == j reads the (permuted) target directly.  128-bit lazy accumulation, one
-// Barrett reduction (as SEAL).  One thread per (e, i, x).
+// Barrett reduction (as SEAL).  A thread owns one (group, ext limb, coefficient), keeps the
+// 2L key words of that coefficient in registers and sweeps a chunk of the batch, so the keys
+// are read once per chunk instead of once per ciphertext.  grid = (x blocks, ngroups*(L+1),
+// batch chunks).  LT = L when L <= 4 (keys in registers), 0 = generic.
 // ---------------------------------------------------------------------------------------
+constexpr int KS_INNER_BCHUNK = 16;
+
+template <int LT>
 __global__ void __launch_bounds__(256) ks_inner_kernel(const KsParams P, const ModConst *__restrict__ mods)
 {
-    const u32 L = P.L, n = P.n;
-    const size_t per_e = (size_t)(L + 1) * n;
-    const size_t total = (size_t)P.ngroups * P.B * per_e;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const u32 e = (u32)(idx / per_e);
-        const u32 r = (u32)(idx % per_e);
-        const u32 i = r / n, x = r % n;
-        const u32 g = e / P.B, b = e % P.B;
-        const u32 ki = (i == L) ? P.K - 1 : i;
-        const ModConst m = mods[ki];
-        const u64 *key = P.key[g];
-        u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
-        for (u32 j = 0; j < L; ++j) {
-            u64 d;
-            if (j == i) {
-                const CtView &v = P.in[g];
-                const u32 *pm = P.perm[g];
-                d = v.p[b * v.sb + P.target_poly * v.sp + j * v.sl + (pm ? __ldg(pm + x) : x)];
-            } else {
-                d = P.ext[(((size_t)e * L + j) * (L + 1) + i) * n + x];
-            }
-            const u64 k0 = __ldg(key + (((size_t)j * 2 + 0) * P.K + ki) * n + x);
-            const u64 k1 = __ldg(key + (((size_t)j * 2 + 1) * P.K + ki) * n + x);
-            mac128(h0, l0, d, k0);
-            mac128(h1, l1, d, k1);
+    const u32 L = LT ? LT : P.L, n = P.n;
+    const u32 x = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 g = blockIdx.y / (L + 1), i = blockIdx.y % (L + 1);
+    const u32 b0 = blockIdx.z * KS_INNER_BCHUNK;
+    const u32 b1 = min(P.B, b0 + KS_INNER_BCHUNK);
+    if (x >= n) return;
+    const u32 ki = (i == L) ? P.K - 1 : i;
+    const ModConst m = mods[ki];
+    const u64 *key = P.key[g] + (size_t)ki * n + x;
+    const size_t kstride = (size_t)P.K * n;  // between (j,c) slices
+    u64 k0[LT ? LT : 1], k1[LT ? LT : 1];
+    if (LT) {
+#pragma unroll
+        for (int j = 0; j < (LT ? LT : 1); ++j) {
+            k0[j] = __ldg(key + (size_t)(2 * j) * kstride);
+            k1[j] = __ldg(key + (size_t)(2 * j + 1) * kstride);
         }
-        P.acc[(((size_t)e * 2 + 0) * (L + 1) + i) * n + x] = barrett128(h0, l0, m);
-        P.acc[(((size_t)e * 2 + 1) * (L + 1) + i) * n + x] = barrett128(h1, l1, m);
+    }
+    const CtView &v = P.in[g];
+    const u32 *pm = P.perm[g];
+    const u32 xs = ((i < L || P.hoisted) && pm) ? __ldg(pm + x) : x;  // gathered column
+    const u32 xe = P.hoisted ? xs : x;                                  // column of the lifted digits
+    for (u32 b = b0; b < b1; ++b) {
+        const size_t e = (size_t)g * P.B + b;
+        const size_t ee = P.hoisted ? b : e;
+        u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+        if (LT) {
+            u64 d[LT ? LT : 1];
+#pragma unroll
+            for (int j = 0; j < (LT ? LT : 1); ++j)
+                d[j] = ((u32)j == i) ? v.p[b * v.sb + P.target_poly * v.sp + j * v.sl + xs]
+                                     : P.ext[((ee * L + j) * (L + 1) + i) * n + xe];
+#pragma unroll
+            for (int j = 0; j < (LT ? LT : 1); ++j) {
+                mac128(h0, l0, d[j], k0[j]);
+                mac128(h1, l1, d[j], k1[j]);
+            }
+        } else {
+            for (u32 j = 0; j < L; ++j) {
+                const u64 d = (j == i) ? v.p[b * v.sb + P.target_poly * v.sp + j * v.sl + xs]
+                                       : P.ext[((ee * L + j) * (L + 1) + i) * n + xe];
+                mac128(h0, l0, d, __ldg(key + (size_t)(2 * j) * kstride));
+                mac128(h1, l1, d, __ldg(key + (size_t)(2 * j + 1) * kstride));
+            }
+        }
+        P.acc[((e * 2 + 0) * (L + 1) + i) * n + x] = barrett128(h0, l0, m);
+        P.acc[((e * 2 + 1) * (L + 1) + i) * n + x] = barrett128(h1, l1, m);
     }
 }
 
@@ -433,9 +465,6 @@ __global__ void __launch_bounds__(256) fixup_kernel(const CtView v, u32 B, u32 p
 // ---------------------------------------------------------------------------------------
 // K10: BSGS inner sums for every giant step in one pass over the baby rotations.
 //   inner[g][b][p][l][x] = sum_{k<n1} baby_k[b][p][l][x] * diag[g*n1+k][l][x]  mod q_l
-// A thread keeps the n1 baby values of its (b,p,l,x) in registers and sweeps g, so the
-// rotated ciphertexts are read from HBM once; the diagonals are shared by the whole batch
-// and stay in L2.
 // ---------------------------------------------------------------------------------------
 struct BsgsParams {
     CtView baby[MAXG];  // baby[0] = the input batch
@@ -445,32 +474,81 @@ struct BsgsParams {
     u32 n1, n2, B, L, n;
 };
 
-template <int N1>
-__global__ void __launch_bounds__(256) bsgs_inner_kernel(const BsgsParams P, const ModConst *__restrict__ mods)
+// block = (32 coefficients) x (BSGS_GT giant steps); grid = (n/32, L, ceil(n2/BSGS_GT)).
+// A thread keeps the N1 diagonal words of its (g, l, x) in registers for the whole batch and
+// sweeps the 2B polynomials.  The rotated-ciphertext words of BSGS_C consecutive polynomials are
+// staged in shared memory by cp.async (double buffered) and shared by the BSGS_GT warps, so
+// they are read from HBM exactly once; the diagonals are read exactly once as well.
+constexpr int BSGS_GT = 8;
+constexpr int BSGS_C = 4;
+
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 {
-    const size_t per_b = (size_t)2 * P.L * P.n;
-    const size_t total = (size_t)P.B * per_b;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        // x fastest, then batch, then (p,l): neighbouring CTAs share the same diagonal tiles
-        const u32 x = (u32)(idx % P.n);
-        size_t r = idx / P.n;
-        const u32 b = (u32)(r % P.B);
-        r /= P.B;
-        const u32 l = (u32)(r % P.L), p = (u32)(r / P.L);
-        const ModConst m = mods[l];
-        u64 v[N1];
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int N1>
+__global__ void __launch_bounds__(32 * BSGS_GT) bsgs_inner_kernel(const BsgsParams P, const ModConst *__restrict__ mods)
+{
+    __shared__ u64 buf[2][BSGS_C][N1][32];
+    __shared__ const u64 *bptr[N1];
+    __shared__ size_t bsb[N1], bsp[N1];
+    const u32 tid = threadIdx.y * 32 + threadIdx.x;
+    const u32 x0 = blockIdx.x * 32, l = blockIdx.y;
+    const u32 g = blockIdx.z * BSGS_GT + threadIdx.y;
+    const bool active = g < P.n2;
+    if (tid < N1) {
+        const CtView &c = P.baby[tid];
+        bptr[tid] = c.p + l * c.sl + x0;
+        bsb[tid] = c.sb;
+        bsp[tid] = c.sp;
+    }
+    __syncthreads();
+    const ModConst m = mods[l];
+    u64 d[N1];
+    if (active) {
+        const u64 *dp = P.diag + (size_t)g * N1 * P.diag_si + l * P.diag_sl + x0 + threadIdx.x;
 #pragma unroll
-        for (int k = 0; k < N1; ++k) {
-            const CtView &c = P.baby[k];
-            v[k] = c.p[b * c.sb + p * c.sp + l * c.sl + x];
+        for (int k = 0; k < N1; ++k) d[k] = __ldg(dp + k * P.diag_si);
+    }
+    const u32 iters = 2 * P.B;
+    const u32 nchunks = (iters + BSGS_C - 1) / BSGS_C;
+    auto issue = [&](u32 chunk, u32 s) {
+        for (u32 v = tid; v < BSGS_C * N1 * 32; v += 32 * BSGS_GT) {
+            const u32 xx = v & 31, k = (v >> 5) % N1, ci = v / (32 * N1);
+            const u32 it = chunk * BSGS_C + ci;
+            if (it < iters) cp_async8(&buf[s][ci][k][xx], bptr[k] + (it >> 1) * bsb[k] + (it & 1) * bsp[k] + xx);
         }
-        for (u32 g = 0; g < P.n2; ++g) {
-            u64 h = 0, lo = 0;
-            const u64 *d = P.diag + (size_t)g * N1 * P.diag_si + l * P.diag_sl + x;
+        cp_async_commit();
+    };
+    issue(0, 0);
+    for (u32 ch = 0; ch < nchunks; ++ch) {
+        const u32 s = ch & 1;
+        if (ch + 1 < nchunks) {
+            issue(ch + 1, s ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (active) {
 #pragma unroll
-            for (int k = 0; k < N1; ++k) mac128(h, lo, v[k], __ldg(d + k * P.diag_si));
-            P.inner.p[((size_t)g * P.B + b) * P.inner.sb + p * P.inner.sp + l * P.inner.sl + x] = barrett128(h, lo, m);
+            for (int ci = 0; ci < BSGS_C; ++ci) {
+                const u32 it = ch * BSGS_C + ci;
+                if (it < iters) {
+                    u64 h = 0, lo = 0;
+#pragma unroll
+                    for (int k = 0; k < N1; ++k) mac128(h, lo, buf[s][ci][k][threadIdx.x], d[k]);
+                    P.inner.p[((size_t)g * P.B + (it >> 1)) * P.inner.sb + (it & 1) * P.inner.sp + l * P.inner.sl + x0 + threadIdx.x] =
+                        barrett128(h, lo, m);
+                }
+            }
         }
+        __syncthreads();  // the buffer is refilled by the next-but-one issue
     }
 }
 
@@ -495,6 +573,48 @@ __global__ void __launch_bounds__(256) sum_terms_kernel(const SumParams P, const
         u64 s = P.first.p[b * P.first.sb + p * P.first.sp + l * P.first.sl + x];
         for (u32 g = 1; g < P.terms; ++g)
             s = addmod(s, P.rest.p[((size_t)(g - 1) * P.B + b) * P.rest.sb + p * P.rest.sp + l * P.rest.sl + x], q);
+        P.out.p[b * P.out.sb + p * P.out.sp + l * P.out.sl + x] = s;
+    }
+}
+
+// lazy mod-down over giant steps: accsum[b][c][i] = sum_g acc[g*B+b][c][i] mod m_i  (rows = 2*(L+1))
+__global__ void __launch_bounds__(256) acc_group_sum_kernel(const u64 *__restrict__ acc, u64 *__restrict__ out, u32 groups, u32 B,
+                                                            u32 L, u32 K, u32 n, const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)2 * (L + 1) * n;
+    const size_t total = (size_t)B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        const size_t r = idx % per_b;
+        const u32 i = (u32)((r / n) % (L + 1));
+        const u64 q = mods[i == L ? K - 1 : i].q;
+        u64 s = 0;
+        for (u32 g = 0; g < groups; ++g) s = addmod(s, acc[((size_t)g * B + b) * per_b + r], q);
+        out[idx] = s;
+    }
+}
+
+// base[b][0] = first[b][0] + sum_g pi_g(rest[g*B+b][0]);  base[b][1] = first[b][1]
+struct BaseSumParams {
+    CtView first, rest, out;
+    const u32 *perm[MAXG];
+    u32 groups, B, L, n;
+};
+__global__ void __launch_bounds__(256) base_gather_sum_kernel(const BaseSumParams P, const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)2 * P.L * P.n;
+    const size_t total = (size_t)P.B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        u32 r = (u32)(idx % per_b);
+        const u32 x = r % P.n;
+        r /= P.n;
+        const u32 l = r % P.L, p = r / P.L;
+        const u64 q = mods[l].q;
+        u64 s = P.first.p[b * P.first.sb + p * P.first.sp + l * P.first.sl + x];
+        if (p == 0)
+            for (u32 g = 0; g < P.groups; ++g)
+                s = addmod(s, P.rest.p[((size_t)g * P.B + b) * P.rest.sb + l * P.rest.sl + __ldg(P.perm[g] + x)], q);
         P.out.p[b * P.out.sb + p * P.out.sp + l * P.out.sl + x] = s;
     }
 }

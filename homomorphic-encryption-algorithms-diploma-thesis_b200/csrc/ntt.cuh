@@ -14,8 +14,14 @@
 //    loader that can gather / lift / subtract) and the last pass stores through a
 //    caller-supplied epilogue, so key-switch and rescale fuse their element-wise steps
 //    into the transforms;
-//  * Shoup multiplication keeps butterflies at 10 IMAD each; lazy ranges are tracked at
-//    compile time so primes below 2^58 (fwd) / 2^46 (inv) need no per-stage corrections;
+//  * three arithmetic policies, chosen per modulus (uniform per CTA):
+//      ArI64<true>   60-bit primes: Shoup multiplication (6 IMAD.WIDE + 4 IMAD per butterfly), lazy
+//                    ranges with one correction per radix-16 pass (fwd) / per stage (inv);
+//      ArI64<false>  primes below 2^58 (fwd) / 2^46 (inv): same, no corrections at all;
+//      ArF64         primes below 2^43: the butterfly runs on the FP64 pipe (64 FMA/clk/SM on
+//                    B200) -- exact integer arithmetic in doubles: h = y*w, l = fma(y,w,-h),
+//                    t = rint(h/q), r = fma(-t,q,h) + l == y*w - t*q exactly; 8 FP64 ops per
+//                    butterfly instead of ~41 integer-multiply issue cycles;
 //  * N = 32768 runs as two CTAs that each redo the first (stride N/2) stage from global
 //    memory and then own one half (forward), or finish with one element-wise stage kernel
 //    (inverse) -- see ntt_fwd_kernel / ntt_inv_kernel SPLIT.
@@ -24,11 +30,19 @@
 
 namespace hegpu {
 
+// double-precision constants of a modulus q < 2^43 (FP64 butterfly path)
+struct ModF64 {
+    double q, qinv, ninv, wlast;  // wlast = inv[1]*N^-1 mod q
+};
+
 struct NttTables {
     const ulonglong2 *fwd;  // [K][N]  {psi^brev(i), shoup}   index m+i as in SURVEY 9.2
     const ulonglong2 *inv;  // [K][N]  {psi^-brev(i), shoup}
     const ModConst *mods;   // [K]
     const ulonglong2 *inv_last;  // [K] {inv[1]*N^-1, shoup}: bottom twiddle of the last INTT stage
+    const double *fwd_d;    // [K][N] the same twiddles as doubles (valid where mods[i].big & 4)
+    const double *inv_d;
+    const ModF64 *modsd;    // [K]
     u32 n;                  // ring degree N
     u32 logn;
 };
@@ -68,12 +82,132 @@ struct PassMap {
     }
 };
 
+// ------------------------------------------------------------------ arithmetic policies
+#define HEGPU_TWO52 4503599627370496.0
+#define HEGPU_MAGIC 6755399441055744.0 /* 1.5 * 2^52: rint() by addition for |x| < 2^51 */
+
+template <bool BIG>
+struct ArI64 {
+    typedef u64 V;
+    typedef ulonglong2 TW;
+    const ModConst &m;
+    const ulonglong2 wlast;
+    __device__ __forceinline__ ArI64(const ModConst &m_, ulonglong2 wl) : m(m_), wlast(wl) {}
+    __device__ __forceinline__ V from_load(u64 v) const { return v; }
+    // forward: values < 8q at pass start (BIG), +2q per stage, < 16q < 2^64
+    __device__ __forceinline__ V fwd_fix(V v) const { return BIG ? csub(v, m.q << 3) : v; }
+    __device__ __forceinline__ void fwd_bfly(V &X, V &Y, const TW W) const
+    {
+        const u64 T = mul_shoup_lazy(Y, W.x, W.y, m.q);
+        Y = X + (m.q << 1) - T;
+        X = X + T;
+    }
+    __device__ __forceinline__ u64 fwd_final(V v) const
+    {
+        if (BIG) {
+            v = csub(v, m.q << 3);
+            v = csub(v, m.q << 2);
+            v = csub(v, m.q << 1);
+            return csub(v, m.q);
+        }
+        return barrett64(v, m);
+    }
+    // inverse: BIG keeps [0,2q) with a correction per stage; !BIG lets the sums double
+    // (bound 2q * 2^gbit entering global stage gbit)
+    __device__ __forceinline__ V inv_fix(V v) const { return v; }
+    template <int GBIT>
+    __device__ __forceinline__ void inv_bfly(V &X, V &Y, const TW W) const
+    {
+        const u64 q2 = m.q << 1;
+        u64 Sm, D;
+        if (BIG) {
+            Sm = csub(X + Y, q2);
+            D = X + q2 - Y;
+        } else {
+            Sm = X + Y;
+            D = X + (m.q << (GBIT + 1)) - Y;
+        }
+        X = Sm;
+        Y = mul_shoup_lazy(D, W.x, W.y, m.q);
+    }
+    template <int GBIT>
+    __device__ __forceinline__ void inv_bfly_last(V &X, V &Y) const
+    {
+        const u64 q2 = m.q << 1;
+        u64 Sm, D;
+        if (BIG) {
+            Sm = csub(X + Y, q2);
+            D = X + q2 - Y;
+        } else {
+            Sm = X + Y;
+            D = X + (m.q << (GBIT + 1)) - Y;
+        }
+        X = mul_shoup(Sm, m.ninv, m.ninv_sh, m.q);
+        Y = mul_shoup(D, wlast.x, wlast.y, m.q);
+    }
+    __device__ __forceinline__ u64 inv_final(V v) const { return v; }
+};
+
+struct ArF64 {
+    typedef double V;
+    typedef double TW;
+    const ModF64 f;
+    __device__ __forceinline__ explicit ArF64(const ModF64 &f_) : f(f_) {}
+    // exact y*w - t*q with t = rint(y*w/q): |result| <= ~0.7q for |y| < 2^48, 0 <= w < q < 2^43
+    __device__ __forceinline__ double mulmod(double y, double w) const
+    {
+        const double h = __dmul_rn(y, w);
+        const double l = __fma_rn(y, w, -h);
+        const double t = __dadd_rn(__fma_rn(h, f.qinv, HEGPU_MAGIC), -HEGPU_MAGIC);
+        return __dadd_rn(__fma_rn(-t, f.q, h), l);
+    }
+    __device__ __forceinline__ double reduce(double v) const
+    {
+        const double t = __dadd_rn(__fma_rn(v, f.qinv, HEGPU_MAGIC), -HEGPU_MAGIC);
+        return __fma_rn(-t, f.q, v);
+    }
+    __device__ __forceinline__ u64 to_canonical(double r) const  // |r| < q
+    {
+        r = r < 0.0 ? __dadd_rn(r, f.q) : r;
+        return (u64)__double_as_longlong(__dadd_rn(r, HEGPU_TWO52)) & 0xFFFFFFFFFFFFFull;
+    }
+    __device__ __forceinline__ V from_load(u64 v) const  // v < 2^52
+    {
+        return __dadd_rn(__longlong_as_double((long long)(v | 0x4330000000000000ull)), -HEGPU_TWO52);
+    }
+    // forward: |T| <= 0.7q per stage, 16 stages from < 3q stay far below 2^48
+    __device__ __forceinline__ V fwd_fix(V v) const { return v; }
+    __device__ __forceinline__ void fwd_bfly(V &X, V &Y, const TW W) const
+    {
+        const double T = mulmod(Y, W);
+        Y = __dadd_rn(X, -T);
+        X = __dadd_rn(X, T);
+    }
+    __device__ __forceinline__ u64 fwd_final(V v) const { return to_canonical(reduce(v)); }
+    // inverse: the sum path doubles per stage; one reduction at the start of every full pass
+    __device__ __forceinline__ V inv_fix(V v) const { return reduce(v); }
+    template <int GBIT>
+    __device__ __forceinline__ void inv_bfly(V &X, V &Y, const TW W) const
+    {
+        const double D = __dadd_rn(X, -Y);
+        X = __dadd_rn(X, Y);
+        Y = mulmod(D, W);
+    }
+    template <int GBIT>
+    __device__ __forceinline__ void inv_bfly_last(V &X, V &Y) const
+    {
+        const double D = __dadd_rn(X, -Y);
+        X = mulmod(__dadd_rn(X, Y), f.ninv);
+        Y = mulmod(D, f.wlast);
+    }
+    __device__ __forceinline__ u64 inv_final(V v) const { return to_canonical(v); }
+};
+
 // ------------------------------------------------------------------ forward butterflies
 // S stages on register bits S-1..0 (descending).  gbase = N + (global index of x[0]).
-template <int S, int PLO, int PHI>
-__device__ __forceinline__ void fwd_stages(u64 (&x)[16], u32 gbase, const ulonglong2 *__restrict__ tw, u64 q)
+template <int S, int PLO, int PHI, class A>
+__device__ __forceinline__ void fwd_stages(typename A::V (&x)[16], u32 gbase, const typename A::TW *__restrict__ tw, const A &ar)
 {
-    const u64 q2 = q << 1;
 #pragma unroll
     for (int ss = 0; ss < S; ++ss) {
         const int s = S - 1 - ss;
@@ -82,14 +216,11 @@ __device__ __forceinline__ void fwd_stages(u64 (&x)[16], u32 gbase, const ulongl
             const u32 g = (S == 4) ? gbase : gbase + ((u32)kh << PHI);
 #pragma unroll
             for (int hi = 0; hi < (1 << ss); ++hi) {
-                const ulonglong2 W = __ldg(tw + (g >> (PLO + s + 1)) + hi);
+                const typename A::TW W = __ldg(tw + (g >> (PLO + s + 1)) + hi);
 #pragma unroll
                 for (int lo = 0; lo < (1 << s); ++lo) {
                     const int k = (kh << S) | (hi << (s + 1)) | lo;
-                    const int k2 = k | (1 << s);
-                    u64 T = mul_shoup_lazy(x[k2], W.x, W.y, q);
-                    x[k2] = x[k] + q2 - T;
-                    x[k] = x[k] + T;
+                    ar.fwd_bfly(x[k], x[k | (1 << s)], W);
                 }
             }
         }
@@ -97,8 +228,9 @@ __device__ __forceinline__ void fwd_stages(u64 (&x)[16], u32 gbase, const ulongl
 }
 
 // full radix-16 passes of the forward transform, field position descending
-template <int LOGL, bool BIG, int PASS, class Load>
-__device__ __forceinline__ void fwd_full_passes(Load &load, const ulonglong2 *__restrict__ tw, u32 goff, u64 q, u64 *sm)
+template <int LOGL, int PASS, class A, class Load>
+__device__ __forceinline__ void fwd_full_passes(Load &load, const typename A::TW *__restrict__ tw, u32 goff, const A &ar,
+                                                typename A::V *sm)
 {
     typedef NttShape<LOGL> Sh;
     if constexpr (PASS < Sh::NFULL) {
@@ -106,25 +238,25 @@ __device__ __forceinline__ void fwd_full_passes(Load &load, const ulonglong2 *__
         typedef PassMap<LOGL, 4, P, LOGL> M;
 #pragma unroll 1
         for (int it = 0; it < Sh::ITER; ++it) {
-            u64 x[16];
+            typename A::V x[16];
             const u32 b = M::base(threadIdx.x + it * Sh::THREADS);
             if constexpr (PASS == 0) {
+                u64 raw[16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) x[k] = load(b + M::off(k));
+                for (int k = 0; k < 16; ++k) raw[k] = load(b + M::off(k));
+#pragma unroll
+                for (int k = 0; k < 16; ++k) x[k] = ar.from_load(raw[k]);
             } else {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    u64 v = sm[swz(b + M::off(k))];
-                    x[k] = BIG ? csub(v, q << 3) : v;
-                }
+                for (int k = 0; k < 16; ++k) x[k] = ar.fwd_fix(sm[swz(b + M::off(k))]);
             }
-            fwd_stages<4, P, LOGL>(x, goff + b, tw, q);
+            fwd_stages<4, P, LOGL>(x, goff + b, tw, ar);
             // in-place: a thread only overwrites the slots it read itself
 #pragma unroll
             for (int k = 0; k < 16; ++k) sm[swz(b + M::off(k))] = x[k];
         }
         __syncthreads();
-        fwd_full_passes<LOGL, BIG, PASS + 1>(load, tw, goff, q, sm);
+        fwd_full_passes<LOGL, PASS + 1>(load, tw, goff, ar, sm);
     }
 }
 
@@ -132,82 +264,59 @@ __device__ __forceinline__ void fwd_full_passes(Load &load, const ulonglong2 *__
 //  load(i)  -> coefficient i of this CTA's block, any value < 3q
 //  store(i, v) receives the canonical result for position i of the block
 //  goff = N_total + block offset (global index of local coefficient 0)
-// Lazy ranges (BIG, q < 2^60): values are < 8q at the start of a pass and grow by 2q per
-// stage (< 16q < 2^64); !BIG (q < 2^58): no corrections, < 33q at the end.
-template <int LOGL, bool BIG, class Load, class Store>
-__device__ __forceinline__ void ntt_fwd_cta(Load load, Store store, const ulonglong2 *__restrict__ tw, u32 goff,
-                                            const ModConst &m, u64 *sm)
+template <int LOGL, class A, class Load, class Store>
+__device__ __forceinline__ void ntt_fwd_cta(Load load, Store store, const typename A::TW *__restrict__ tw, u32 goff, const A &ar,
+                                            u64 *smraw)
 {
     typedef NttShape<LOGL> Sh;
-    const u64 q = m.q;
-    fwd_full_passes<LOGL, BIG, 0>(load, tw, goff, q, sm);
+    typename A::V *sm = reinterpret_cast<typename A::V *>(smraw);
+    fwd_full_passes<LOGL, 0>(load, tw, goff, ar, sm);
     // last pass: REM stages on the low bits; the other register bits are the top index bits
     constexpr int S = Sh::REM;
     constexpr int PHI = (S == 4) ? LOGL : LOGL - (4 - S);
     typedef PassMap<LOGL, S, 0, PHI> M;
 #pragma unroll 1
     for (int it = 0; it < Sh::ITER; ++it) {
-        u64 x[16];
+        typename A::V x[16];
         const u32 b = M::base(threadIdx.x + it * Sh::THREADS);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            u64 v = sm[swz(b + M::off(k))];
-            x[k] = BIG ? csub(v, q << 3) : v;
-        }
-        fwd_stages<S, 0, PHI>(x, goff + b, tw, q);
+        for (int k = 0; k < 16; ++k) x[k] = ar.fwd_fix(sm[swz(b + M::off(k))]);
+        fwd_stages<S, 0, PHI>(x, goff + b, tw, ar);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            u64 v = x[k];
-            if (BIG) {
-                v = csub(v, q << 3);
-                v = csub(v, q << 2);
-                v = csub(v, q << 1);
-                v = csub(v, q);
-            } else {
-                v = barrett64(v, m);
-            }
-            store(b + M::off(k), v);
-        }
+        for (int k = 0; k < 16; ++k) store(b + M::off(k), ar.fwd_final(x[k]));
     }
 }
 
 // ------------------------------------------------------------------ inverse butterflies
-// S stages on register bits 0..S-1 (ascending).  BIT0 = global bit position of register
-// bit 0 (PLO); for !BIG the bound of every value entering global stage c is 2q * 2^c.
-template <int S, int PLO, int PHI, bool BIG, int LAST_BIT>
-__device__ __forceinline__ void inv_stages(u64 (&x)[16], u32 gbase, const ulonglong2 *__restrict__ tw, const ModConst &m,
-                                           const ulonglong2 wlast)
+// S stages on register bits 0..S-1 (ascending); global stage number = PLO + s.
+template <int S, int PLO, int PHI, int LAST_BIT, class A>
+__device__ __forceinline__ void inv_stages(typename A::V (&x)[16], u32 gbase, const typename A::TW *__restrict__ tw, const A &ar)
 {
-    const u64 q = m.q, q2 = q << 1;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        const int gbit = PLO + s;  // global stage number
 #pragma unroll
         for (int kh = 0; kh < (1 << (4 - S)); ++kh) {
             const u32 g = (S == 4) ? gbase : gbase + ((u32)kh << PHI);
 #pragma unroll
             for (int hi = 0; hi < (1 << (S - 1 - s)); ++hi) {
-                ulonglong2 W = __ldg(tw + (g >> (PLO + s + 1)) + hi);
-                if (gbit == LAST_BIT) W = wlast;
+                if (PLO + s == LAST_BIT) {
 #pragma unroll
-                for (int lo = 0; lo < (1 << s); ++lo) {
-                    const int k = (kh << S) | (hi << (s + 1)) | lo;
-                    const int k2 = k | (1 << s);
-                    const u64 X = x[k], Y = x[k2];
-                    u64 Sm, D;
-                    if (BIG) {
-                        Sm = csub(X + Y, q2);
-                        D = X + q2 - Y;
-                    } else {
-                        Sm = X + Y;
-                        D = X + (q << (gbit + 1)) - Y;
+                    for (int lo = 0; lo < (1 << s); ++lo) {
+                        const int k = (kh << S) | (hi << (s + 1)) | lo;
+                        if (s == 0) ar.template inv_bfly_last<PLO>(x[k], x[k | 1]);
+                        if (s == 1) ar.template inv_bfly_last<PLO + 1>(x[k], x[k | 2]);
+                        if (s == 2) ar.template inv_bfly_last<PLO + 2>(x[k], x[k | 4]);
+                        if (s == 3) ar.template inv_bfly_last<PLO + 3>(x[k], x[k | 8]);
                     }
-                    if (gbit == LAST_BIT) {
-                        x[k] = mul_shoup(Sm, m.ninv, m.ninv_sh, q);
-                        x[k2] = mul_shoup(D, W.x, W.y, q);
-                    } else {
-                        x[k] = Sm;
-                        x[k2] = mul_shoup_lazy(D, W.x, W.y, q);
+                } else {
+                    const typename A::TW W = __ldg(tw + (g >> (PLO + s + 1)) + hi);
+#pragma unroll
+                    for (int lo = 0; lo < (1 << s); ++lo) {
+                        const int k = (kh << S) | (hi << (s + 1)) | lo;
+                        if (s == 0) ar.template inv_bfly<PLO>(x[k], x[k | 1], W);
+                        if (s == 1) ar.template inv_bfly<PLO + 1>(x[k], x[k | 2], W);
+                        if (s == 2) ar.template inv_bfly<PLO + 2>(x[k], x[k | 4], W);
+                        if (s == 3) ar.template inv_bfly<PLO + 3>(x[k], x[k | 8], W);
                     }
                 }
             }
@@ -216,9 +325,9 @@ __device__ __forceinline__ void inv_stages(u64 (&x)[16], u32 gbase, const ulongl
 }
 
 // full radix-16 passes of the inverse transform, field position ascending
-template <int LOGL, bool BIG, int LAST_BIT, int PASS, class Store>
-__device__ __forceinline__ void inv_full_passes(Store &store, const ulonglong2 *__restrict__ tw, u32 goff, const ModConst &m,
-                                                const ulonglong2 wlast, u64 *sm)
+template <int LOGL, int LAST_BIT, int PASS, class A, class Store>
+__device__ __forceinline__ void inv_full_passes(Store &store, const typename A::TW *__restrict__ tw, u32 goff, const A &ar,
+                                                typename A::V *sm)
 {
     typedef NttShape<LOGL> Sh;
     if constexpr (PASS < Sh::NFULL) {
@@ -226,14 +335,19 @@ __device__ __forceinline__ void inv_full_passes(Store &store, const ulonglong2 *
         typedef PassMap<LOGL, 4, P, LOGL> M;
 #pragma unroll 1
         for (int it = 0; it < Sh::ITER; ++it) {
-            u64 x[16];
+            typename A::V x[16];
             const u32 b = M::base(threadIdx.x + it * Sh::THREADS);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) x[k] = sm[swz(b + M::off(k))];
-            inv_stages<4, P, LOGL, BIG, LAST_BIT>(x, goff + b, tw, m, wlast);
+            for (int k = 0; k < 16; ++k) x[k] = ar.inv_fix(sm[swz(b + M::off(k))]);
+            inv_stages<4, P, LOGL, LAST_BIT>(x, goff + b, tw, ar);
             if constexpr (PASS == Sh::NFULL - 1) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) store(b + M::off(k), x[k]);
+                for (int k = 0; k < 16; ++k) {
+                    if constexpr (LAST_BIT >= 0)
+                        store(b + M::off(k), ar.inv_final(x[k]));
+                    else
+                        store(b + M::off(k), x[k]);
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < 16; ++k) sm[swz(b + M::off(k))] = x[k];
@@ -241,35 +355,39 @@ __device__ __forceinline__ void inv_full_passes(Store &store, const ulonglong2 *
         }
         if constexpr (PASS != Sh::NFULL - 1) {
             __syncthreads();
-            inv_full_passes<LOGL, BIG, LAST_BIT, PASS + 1>(store, tw, goff, m, wlast, sm);
+            inv_full_passes<LOGL, LAST_BIT, PASS + 1>(store, tw, goff, ar, sm);
         }
     }
 }
 
 // One limb polynomial (block), inverse.  LAST_BIT = index of the final stage of the whole
 // transform (logN-1) if this CTA performs it (store receives canonical values), else -1
-// (SPLIT: values leave in [0,2q) (BIG) or [0, 2q*2^LOGL) (!BIG); ntt_inv_final_kernel finishes).
-// load(i) must return canonical residues.
-template <int LOGL, bool BIG, int LAST_BIT, class Load, class Store>
-__device__ __forceinline__ void ntt_inv_cta(Load load, Store store, const ulonglong2 *__restrict__ tw, u32 goff,
-                                            const ModConst &m, const ulonglong2 wlast, u64 *sm)
+// (SPLIT, integer policies only: values leave in [0,2q) (BIG) or [0, 2q*2^LOGL) (!BIG);
+// ntt_inv_final_kernel finishes).  load(i) must return canonical residues.
+template <int LOGL, int LAST_BIT, class A, class Load, class Store>
+__device__ __forceinline__ void ntt_inv_cta(Load load, Store store, const typename A::TW *__restrict__ tw, u32 goff, const A &ar,
+                                            u64 *smraw)
 {
     typedef NttShape<LOGL> Sh;
+    typename A::V *sm = reinterpret_cast<typename A::V *>(smraw);
     constexpr int S = Sh::REM;
     constexpr int PHI = (S == 4) ? LOGL : LOGL - (4 - S);
     typedef PassMap<LOGL, S, 0, PHI> M;
 #pragma unroll 1
     for (int it = 0; it < Sh::ITER; ++it) {
-        u64 x[16];
+        typename A::V x[16];
         const u32 b = M::base(threadIdx.x + it * Sh::THREADS);
+        u64 raw[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = load(b + M::off(k));
-        inv_stages<S, 0, PHI, BIG, LAST_BIT>(x, goff + b, tw, m, wlast);
+        for (int k = 0; k < 16; ++k) raw[k] = load(b + M::off(k));
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = ar.from_load(raw[k]);
+        inv_stages<S, 0, PHI, LAST_BIT>(x, goff + b, tw, ar);
 #pragma unroll
         for (int k = 0; k < 16; ++k) sm[swz(b + M::off(k))] = x[k];
     }
     __syncthreads();
-    inv_full_passes<LOGL, BIG, LAST_BIT, 0>(store, tw, goff, m, wlast, sm);
+    inv_full_passes<LOGL, LAST_BIT, 0>(store, tw, goff, ar, sm);
 }
 
 }  // namespace hegpu

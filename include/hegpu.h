@@ -134,11 +134,20 @@ int hegpu_ntt_inverse_host(hegpu_ctx *ctx, uint64_t *host, uint32_t count, uint3
  * body he_fft.cpp:178-203 for plaintext diagonals:
  *   out_b = rescale( sum_g rot_{g*n1}( sum_k pt[g*n1+k] (.) rot_k(in_b) ) ),  k < n1, g < n2
  * diags holds n1*n2 plaintexts, diagonal g*n1+k pre-rotated right by g*n1 slots.
- * Needs Galois keys for steps 1..n1-1 and g*n1 (g = 1..n2-1).  rescale = 0 skips the
- * final rescale (multi-GPU partial sums are reduced first).
+ * Needs Galois keys for steps 1..n1-1 and g*n1 (g = 1..n2-1).
+ * flags: HEGPU_MATVEC_RESCALE  apply the final rescale (clear it when multi-GPU partial sums are
+ *                              reduced first);
+ *        HEGPU_MATVEC_HOIST    "fast" mode: the baby-step rotations share one digit
+ *                              decomposition (INTT + lift once per ciphertext, Galois permutation
+ *                              applied to the lifted digits) and the giant-step key-switches share
+ *                              one mod-down.  Same function up to key-switch noise, different bits
+ *                              than a chain of rotate_vector calls; without the flag the composite
+ *                              is exactly the chain of SEAL primitives.
  */
+#define HEGPU_MATVEC_RESCALE 1
+#define HEGPU_MATVEC_HOIST 2
 int hegpu_matvec_bsgs(hegpu_ctx *ctx, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, uint32_t n1,
-                      uint32_t n2, int rescale);
+                      uint32_t n2, int flags);
 
 /* hegpu_bmatmul_diag: BatchedMatrix::matmul (he_linalg.cpp:943-1006) in the reference's
  * own loop order ("exact" mode): res_i = rescale(relin( sum_j rot(x_{xi(i,j)}, steps(i,j)) * d_j )).

@@ -459,41 +459,54 @@ void orc_apply_galois_ntt(const orc_ctx *c, u32 limbs, u32 elt, const u64 *in, u
 }
 
 /* ---------------------------------------------------------------- key switching */
-/* Evaluator::switch_key_inplace (CKKS) -- evaluator.cpp; SURVEY 9.6.
- * ct [2][L][N] (in/out), target [L][N] NTT form, key [Lmax][2][K][N], Lmax = K-1. */
-void orc_switch_key(const orc_ctx *c, u32 L, u64 *ct, const u64 *target, const u64 *key)
+/* digit decomposition of switch_key_inplace:
+ * ext[j][I] = NTT_{m_I}( INTT_{q_j}(target_j) mod m_I ), I in [0,L] (I = L is the special prime);
+ * ext[j][j] = target_j itself.  ext layout [L][L+1][N]. */
+static void ks_decompose(const orc_ctx *c, u32 L, const u64 *target, u64 *ext)
 {
     const u32 n = c->n, K = c->K;
-    const u64 P = c->q[K - 1], halfP = P >> 1;
-    u64 *coef = (u64 *)malloc(sizeof(u64) * (size_t)L * n);        /* c_j = INTT(target_j) */
-    u64 *acc = (u64 *)malloc(sizeof(u64) * (size_t)2 * (L + 1) * n); /* [2][L+1][N] */
-    u64 *tmp = (u64 *)malloc(sizeof(u64) * n);
+    u64 *coef = (u64 *)malloc(sizeof(u64) * n);
+    for (u32 J = 0; J < L; ++J) {
+        memcpy(coef, target + (size_t)J * n, sizeof(u64) * n);
+        orc_ntt_inv(c, J, coef);
+        for (u32 I = 0; I <= L; ++I) {
+            u64 *e = ext + ((size_t)J * (L + 1) + I) * n;
+            if (I == J) {
+                memcpy(e, target + (size_t)J * n, sizeof(u64) * n);
+                continue;
+            }
+            const u32 ki = (I == L) ? K - 1 : I;
+            const u64 m = c->q[ki];
+            if (c->q[J] <= m)
+                memcpy(e, coef, sizeof(u64) * n);
+            else
+                for (u32 x = 0; x < n; ++x) e[x] = coef[x] % m;
+            orc_ntt_fwd(c, ki, e);
+        }
+    }
+    free(coef);
+}
+
+/* key inner product (SURVEY 9.6 step 2, 128-bit lazy sums, one reduction):
+ * acc[comp][I] = sum_j ext[j][I][tab[x]] * key[j][comp][idx(I)][x] mod m_I; tab = Galois gather
+ * table applied to the lifted digits (hoisted rotation) or NULL.  acc layout [2][L+1][N]. */
+static void ks_inner(const orc_ctx *c, u32 L, const u64 *ext, const u32 *tab, const u64 *key, u64 *acc)
+{
+    const u32 n = c->n, K = c->K;
     u128 *lazy = (u128 *)malloc(sizeof(u128) * (size_t)2 * n);
-
-    memcpy(coef, target, sizeof(u64) * (size_t)L * n);
-    for (u32 j = 0; j < L; ++j) orc_ntt_inv(c, j, coef + (size_t)j * n);
-
     for (u32 I = 0; I <= L; ++I) {
-        const u32 ki = (I == L) ? K - 1 : I; /* key-level limb index */
+        const u32 ki = (I == L) ? K - 1 : I;
         const u64 m = c->q[ki];
         memset(lazy, 0, sizeof(u128) * (size_t)2 * n);
         for (u32 J = 0; J < L; ++J) {
-            const u64 *op;
-            if (I == J) {
-                op = target + (size_t)J * n;
-            } else {
-                const u64 *cj = coef + (size_t)J * n;
-                if (c->q[J] <= m)
-                    memcpy(tmp, cj, sizeof(u64) * n);
-                else
-                    for (u32 x = 0; x < n; ++x) tmp[x] = cj[x] % m;
-                orc_ntt_fwd(c, ki, tmp);
-                op = tmp;
-            }
+            const u64 *op = ext + ((size_t)J * (L + 1) + I) * n;
             for (u32 comp = 0; comp < 2; ++comp) {
                 const u64 *kp = key + (((size_t)J * 2 + comp) * K + ki) * n;
                 u128 *l = lazy + (size_t)comp * n;
-                for (u32 x = 0; x < n; ++x) l[x] += (u128)op[x] * kp[x];
+                if (tab)
+                    for (u32 x = 0; x < n; ++x) l[x] += (u128)op[tab[x]] * kp[x];
+                else
+                    for (u32 x = 0; x < n; ++x) l[x] += (u128)op[x] * kp[x];
             }
         }
         for (u32 comp = 0; comp < 2; ++comp) {
@@ -502,7 +515,17 @@ void orc_switch_key(const orc_ctx *c, u32 L, u64 *ct, const u64 *target, const u
             for (u32 x = 0; x < n; ++x) a[x] = (u64)(l[x] % m);
         }
     }
-    /* mod-down by P with rounding, add into ct */
+    free(lazy);
+}
+
+/* mod-down by P with rounding: out[comp][i] = base[comp][i] +
+ * (acc[comp][i] - NTT_{q_i}((t mod q_i) - (floor(P/2) mod q_i))) * P^-1, t = INTT_P(acc[comp][L]) + floor(P/2).
+ * acc [2][L+1][N] is destroyed; base/out [2][L][N] may alias. */
+static void ks_mod_down_add(const orc_ctx *c, u32 L, u64 *acc, const u64 *base, u64 *out)
+{
+    const u32 n = c->n, K = c->K;
+    const u64 P = c->q[K - 1], halfP = P >> 1;
+    u64 *tmp = (u64 *)malloc(sizeof(u64) * n);
     for (u32 comp = 0; comp < 2; ++comp) {
         u64 *t = acc + ((size_t)comp * (L + 1) + L) * n;
         orc_ntt_inv(c, K - 1, t);
@@ -513,14 +536,26 @@ void orc_switch_key(const orc_ctx *c, u32 L, u64 *ct, const u64 *target, const u
             for (u32 x = 0; x < n; ++x) tmp[x] = submod(t[x] % q, hq, q);
             orc_ntt_fwd(c, i, tmp);
             const u64 *a = acc + ((size_t)comp * (L + 1) + i) * n;
-            u64 *o = POLY(ct, L, n, comp, i);
-            for (u32 x = 0; x < n; ++x) o[x] = addmod(o[x], mulmod(submod(a[x], tmp[x], q), pinv, q), q);
+            const u64 *b = POLY(base, L, n, comp, i);
+            u64 *o = POLY(out, L, n, comp, i);
+            for (u32 x = 0; x < n; ++x) o[x] = addmod(b[x], mulmod(submod(a[x], tmp[x], q), pinv, q), q);
         }
     }
-    free(coef);
-    free(acc);
     free(tmp);
-    free(lazy);
+}
+
+/* Evaluator::switch_key_inplace (CKKS) -- evaluator.cpp; SURVEY 9.6.
+ * ct [2][L][N] (in/out), target [L][N] NTT form, key [Lmax][2][K][N], Lmax = K-1. */
+void orc_switch_key(const orc_ctx *c, u32 L, u64 *ct, const u64 *target, const u64 *key)
+{
+    const u32 n = c->n;
+    u64 *ext = (u64 *)malloc(sizeof(u64) * (size_t)L * (L + 1) * n);
+    u64 *acc = (u64 *)malloc(sizeof(u64) * (size_t)2 * (L + 1) * n);
+    ks_decompose(c, L, target, ext);
+    ks_inner(c, L, ext, NULL, key, acc);
+    ks_mod_down_add(c, L, acc, ct, ct);
+    free(ext);
+    free(acc);
 }
 
 /* Evaluator::relinearize_internal (size 3 -> 2) -- he_operators.cpp:149,159 */
@@ -767,4 +802,87 @@ void orc_matvec_bsgs(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1, u32
         free(prod);
         free(acc);
     }
+}
+
+/* "Fast" BSGS matvec = the restatement of hegpu_matvec_bsgs with HEGPU_MATVEC_HOIST:
+ *  - hoisted baby steps: the digits of c1 are decomposed once (ks_decompose, no permutation) and
+ *    every rotation applies its Galois permutation to the lifted digits:
+ *       baby_k = mod_down( ks_inner(pi_k(ext), key_k) ) + (pi_k(c0), 0)
+ *  - lazy giant steps: acc = sum_g ks_inner(decompose(pi_g(inner_g.c1)), key_g) in the extended
+ *    basis, ONE mod-down, base = (inner_0.c0 + sum_g pi_g(inner_g.c0), inner_0.c1).
+ * Same function as orc_matvec_bsgs up to key-switch noise; different bits. */
+void orc_matvec_bsgs_fast(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1, u32 n2, const u64 *pts,
+                          const u64 *const *baby_keys, const u64 *const *giant_keys, u64 *out, int threads)
+{
+    const u32 n = c->n, K = c->K;
+    const size_t ctw = (size_t)2 * L * n, ptw = (size_t)L * n, accw = (size_t)2 * (L + 1) * n;
+    u32 *tabs = (u32 *)malloc(sizeof(u32) * (size_t)(n1 + n2) * n);
+    for (u32 k = 1; k < n1; ++k) orc_galois_table(n, orc_galois_elt_from_step(n, (int)k), tabs + (size_t)k * n);
+    for (u32 g = 1; g < n2; ++g) orc_galois_table(n, orc_galois_elt_from_step(n, (int)(g * n1)), tabs + (size_t)(n1 + g) * n);
+    (void)threads;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(dynamic, 1)
+#endif
+    for (u32 b = 0; b < B; ++b) {
+        const u64 *ct = cts + (size_t)b * ctw;
+        u64 *ext = (u64 *)malloc(sizeof(u64) * (size_t)L * (L + 1) * n);
+        u64 *acc = (u64 *)malloc(sizeof(u64) * accw);
+        u64 *accsum = (u64 *)calloc(accw, sizeof(u64));
+        u64 *baby = (u64 *)malloc(sizeof(u64) * ctw * n1);
+        u64 *inner = (u64 *)malloc(sizeof(u64) * ctw * n2);
+        u64 *prod = (u64 *)malloc(sizeof(u64) * ctw);
+        u64 *base = (u64 *)calloc(ctw, sizeof(u64));
+        memcpy(baby, ct, sizeof(u64) * ctw);
+        ks_decompose(c, L, ct + (size_t)L * n, ext);
+        for (u32 k = 1; k < n1; ++k) {
+            const u32 *tab = tabs + (size_t)k * n;
+            ks_inner(c, L, ext, tab, baby_keys[k], acc);
+            memset(base, 0, sizeof(u64) * ctw);
+            for (u32 i = 0; i < L; ++i)
+                for (u32 x = 0; x < n; ++x) base[(size_t)i * n + x] = ct[(size_t)i * n + tab[x]];
+            ks_mod_down_add(c, L, acc, base, baby + (size_t)k * ctw);
+        }
+        for (u32 g = 0; g < n2; ++g) {
+            u64 *ig = inner + (size_t)g * ctw;
+            for (u32 i = 0; i < n1; ++i) {
+                const u64 *pt = pts + (size_t)(g * n1 + i) * ptw;
+                if (i == 0) {
+                    orc_multiply_plain(c, L, baby, 2, pt, ig);
+                } else {
+                    orc_multiply_plain(c, L, baby + (size_t)i * ctw, 2, pt, prod);
+                    orc_add(c, L, ig, 2, prod, 2, ig);
+                }
+            }
+        }
+        u64 *res = (u64 *)malloc(sizeof(u64) * ctw);
+        if (n2 == 1) {
+            memcpy(res, inner, sizeof(u64) * ctw);
+        } else {
+            memcpy(base, inner, sizeof(u64) * ctw); /* inner_0 */
+            for (u32 g = 1; g < n2; ++g) {
+                const u32 *tab = tabs + (size_t)(n1 + g) * n;
+                const u64 *ig = inner + (size_t)g * ctw;
+                /* target = pi_g(c1) */
+                for (u32 i = 0; i < L; ++i)
+                    for (u32 x = 0; x < n; ++x) prod[(size_t)i * n + x] = ig[(size_t)(L + i) * n + tab[x]];
+                ks_decompose(c, L, prod, ext);
+                ks_inner(c, L, ext, NULL, giant_keys[g], acc);
+                for (u32 comp = 0; comp < 2; ++comp)
+                    for (u32 I = 0; I <= L; ++I) {
+                        const u64 m = c->q[I == L ? K - 1 : I];
+                        u64 *s = accsum + ((size_t)comp * (L + 1) + I) * n;
+                        const u64 *a = acc + ((size_t)comp * (L + 1) + I) * n;
+                        for (u32 x = 0; x < n; ++x) s[x] = addmod(s[x], a[x], m);
+                    }
+                for (u32 i = 0; i < L; ++i) {
+                    const u64 q = c->q[i];
+                    for (u32 x = 0; x < n; ++x) base[(size_t)i * n + x] = addmod(base[(size_t)i * n + x], ig[(size_t)i * n + tab[x]], q);
+                }
+            }
+            ks_mod_down_add(c, L, accsum, base, res);
+        }
+        orc_rescale(c, L, res, 2, out + (size_t)b * 2 * (L - 1) * n);
+        free(ext); free(acc); free(accsum); free(baby); free(inner); free(prod); free(base); free(res);
+    }
+    free(tabs);
 }

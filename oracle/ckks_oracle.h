@@ -103,6 +103,10 @@ void orc_decrypt(const orc_ctx *ctx, uint32_t L, const uint64_t *ct, uint32_t si
 void orc_matvec_bsgs(const orc_ctx *ctx, uint32_t L, uint32_t B, const uint64_t *cts, uint32_t n1, uint32_t n2,
                      const uint64_t *pts, const uint64_t *const *baby_keys, const uint64_t *const *giant_keys,
                      uint64_t *out, int threads);
+/* restatement of the HEGPU_MATVEC_HOIST mode (hoisted baby steps, one mod-down for all giant steps) */
+void orc_matvec_bsgs_fast(const orc_ctx *ctx, uint32_t L, uint32_t B, const uint64_t *cts, uint32_t n1, uint32_t n2,
+                          const uint64_t *pts, const uint64_t *const *baby_keys, const uint64_t *const *giant_keys,
+                          uint64_t *out, int threads);
 int orc_max_threads(void);
 
 #ifdef __cplusplus

@@ -277,8 +277,9 @@ class Oracle:
         return o
 
     # ---- composites
-    def matvec_bsgs(self, cts, n1: int, n2: int, pts, baby_keys, giant_keys, threads: int = 1):
-        """cts [B][2][L][N]; pts [n1*n2][L][N]; baby_keys[b], giant_keys[g] lists (index 0 unused)."""
+    def matvec_bsgs(self, cts, n1: int, n2: int, pts, baby_keys, giant_keys, threads: int = 1, fast: bool = False):
+        """cts [B][2][L][N]; pts [n1*n2][L][N]; baby_keys[b], giant_keys[g] lists (index 0 unused).
+        fast=True restates the HEGPU_MATVEC_HOIST mode."""
         cts = np.ascontiguousarray(cts)
         pts = np.ascontiguousarray(pts)
         B, _, L, _ = cts.shape
@@ -286,8 +287,8 @@ class Oracle:
         bk = (u64p * n1)(*[null if k is None else _p(k) for k in baby_keys])
         gk = (u64p * n2)(*[null if k is None else _p(k) for k in giant_keys])
         o = self._out(B, 2, L - 1, self.n)
-        lib().orc_matvec_bsgs(self._h, C.c_uint32(L), C.c_uint32(B), _p(cts), C.c_uint32(n1), C.c_uint32(n2), _p(pts),
-                              bk, gk, _p(o), C.c_int(threads))
+        fn = lib().orc_matvec_bsgs_fast if fast else lib().orc_matvec_bsgs
+        fn(self._h, C.c_uint32(L), C.c_uint32(B), _p(cts), C.c_uint32(n1), C.c_uint32(n2), _p(pts), bk, gk, _p(o), C.c_int(threads))
         return o
 
 

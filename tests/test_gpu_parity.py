@@ -206,7 +206,7 @@ def _diag_plaintexts(S, M, n1, n2, scale, L):
     return pts
 
 
-@pytest.mark.parametrize("n,dim,n1,n2", [(8192, 16, 4, 4), (16384, 32, 8, 4)])
+@pytest.mark.parametrize("n,dim,n1,n2", [(8192, 16, 4, 4), (16384, 32, 8, 4), (8192, 8, 8, 1), (8192, 8, 1, 8)])
 def test_matvec_bsgs_bit_exact_and_decrypts(hg, n, dim, n1, n2):
     S = setup(n, (60, 40, 40, 60))
     ctx = make_ctx(hg, S)
@@ -222,17 +222,23 @@ def test_matvec_bsgs_bit_exact_and_decrypts(hg, n, dim, n1, n2):
     ctx.load_galois_keys(gk)
     bk = [None] + [gk[orc.galois_elt_from_step(n, s)] for s in bsteps]
     gkeys = [None] + [gk[orc.galois_elt_from_step(n, s)] for s in gsteps]
-    want = S.o.matvec_bsgs(cts, n1, n2, pts, bk, gkeys, threads=4)
     X = ctx.upload_ct(cts, scale)
     D = ctx.upload_pt(pts, scale)
     out = ctx.ct(B, 2)
-    ctx.matvec_bsgs(out, X, D, n1, n2)
-    got = out.download()
-    assert np.array_equal(got, want)
     tol = ckks_tol(dim, n, scale)
-    for i in range(B):
-        dec = S.decrypt(got[i], out.scale).real[:dim]
-        assert np.max(np.abs(dec - M @ V[i])) < tol
+    for fast in (False, True):  # exact chain of SEAL primitives / hoisted mode vs its own restatement
+        want = S.o.matvec_bsgs(cts, n1, n2, pts, bk, gkeys, threads=4, fast=fast)
+        ctx.matvec_bsgs(out, X, D, n1, n2, hoist=fast)
+        got = out.download()
+        assert np.array_equal(got, want)
+        for i in range(B):
+            dec = S.decrypt(got[i], out.scale).real[:dim]
+            assert np.max(np.abs(dec - M @ V[i])) < tol
+    # without the final rescale (multi-GPU partial sums): same ciphertext before rescale
+    ctx.matvec_bsgs(out, X, D, n1, n2, rescale=False, hoist=True)
+    assert out.L == L
+    part = out.download()
+    assert np.array_equal(np.stack([S.o.rescale(part[i]) for i in range(B)]), got)
 
 
 @pytest.mark.parametrize("case_b", [False, True])

@@ -154,7 +154,29 @@ def test_matvec_bsgs_decrypts_to_matvec():
             pts[d] = enc.encode(np.roll(np.tile(diag, slots // dim), g * n1), scale, 3)
     bk = [None] + [o.gen_galois_key(200 + b, s, orc.galois_elt_from_step(n, b)) for b in range(1, n1)]
     gkeys = [None] + [o.gen_galois_key(300 + g, s, orc.galois_elt_from_step(n, g * n1)) for g in range(1, n2)]
-    out = o.matvec_bsgs(ct[None], n1, n2, pts, bk, gkeys, threads=2)
-    got = enc.decode(o.decrypt(out[0], s), scale * scale / moduli[2]).real[:dim]
     tol = ckks_tol(dim, n, scale)
-    assert np.max(np.abs(got - M @ v)) < tol
+    outs = []
+    for fast in (False, True):
+        out = o.matvec_bsgs(ct[None], n1, n2, pts, bk, gkeys, threads=2, fast=fast)
+        got = enc.decode(o.decrypt(out[0], s), scale * scale / moduli[2]).real[:dim]
+        assert np.max(np.abs(got - M @ v)) < tol
+        outs.append(out)
+    # hoisting changes the digit representatives: same plaintext, different ciphertext bits
+    assert not np.array_equal(outs[0], outs[1])
+
+
+def test_key_switch_phases_compose_to_switch_key():
+    """The hoisted restatement is built from the same three phases as orc_switch_key; with one giant
+    step and no baby rotation the fast matvec must equal the exact one bit-for-bit."""
+    n = 4096
+    moduli = orc.coeff_modulus_create(n, [36, 36, 37])
+    o = orc.Oracle(n, moduli)
+    rng = np.random.default_rng(4)
+    s = o.sample_secret(5)
+    cts = _rand_poly(rng, moduli[:2], (2, 2), n)
+    pts = _rand_poly(rng, moduli[:2], (2,), n)
+    gk = o.gen_galois_key(9, s, orc.galois_elt_from_step(n, 1))
+    # n1 = 1, n2 = 2: a single giant rotation, the lazy mod-down degenerates to one ordinary key-switch
+    a = o.matvec_bsgs(cts, 1, 2, pts, [None], [None, gk], fast=False)
+    b = o.matvec_bsgs(cts, 1, 2, pts, [None], [None, gk], fast=True)
+    assert np.array_equal(a, b)
