@@ -148,10 +148,14 @@ struct hegpu_ctx {
     std::map<u32, u64 *> galois_keys;
     std::map<u32, u32 *> perms;
     Arena arena;
+    u64 *park = nullptr;  // [jobs][N/2] scratch of the N = 16384 park kernels (L2-resident in practice)
+    size_t park_words = 0;
+    int use_park = 1;
     u64 *stage = nullptr;  // host<->device staging
     size_t stage_words = 0;
     u64 launches = 0;
     int sms = 148;
+    int loge = 3;  // NTT register-set size at N = 16384: 3 = radix-8 passes, 256 threads x 80 registers, 3 CTAs per SM (HEGPU_LOGE=4: radix-16, 2 CTAs)
     size_t ws_budget = (size_t)24 << 30;  // scratch budget per composite chunk
 };
 
@@ -175,6 +179,8 @@ struct hegpu_pt {
     u64 *d;
     u32 count, L_cap, L;
     double scale;
+    u64 *d_mont = nullptr;  // lazily built copy in Montgomery form (matvec diagonals)
+    bool mont_valid = false;
     size_t stride() const { return (size_t)L_cap * ctx->n; }
 };
 
@@ -238,6 +244,19 @@ struct ArenaPlan {  // first pass sizes the scratch, second pass hands out point
 };
 static inline size_t align256(size_t words) { return ((words * sizeof(u64) + 255) & ~(size_t)255); }
 
+static int park_reserve(hegpu_ctx *c, size_t words)
+{
+    if (words <= c->park_words) return HEGPU_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->park) CU(cudaFree(c->park));
+    c->park = nullptr;
+    c->park_words = 0;
+    words += words >> 2;
+    CU(cudaMalloc(&c->park, words * sizeof(u64)));
+    c->park_words = words;
+    return HEGPU_OK;
+}
+
 static int stage_reserve(hegpu_ctx *c, size_t words)
 {
     if (words <= c->stage_words) return HEGPU_OK;
@@ -284,6 +303,8 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->sms = prop.multiProcessorCount;
+    if (const char *e = getenv("HEGPU_LOGE")) c->loge = atoi(e) == 3 ? 3 : 4;
+    if (const char *e = getenv("HEGPU_PARK")) c->use_park = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 
     // bit counts of q_0..q_{L-1} products (SEAL total_coeff_modulus_bit_count)
@@ -331,6 +352,14 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
         // bit 0: forward needs corrections; bit 1: inverse needs corrections; bit 2: FP64 butterflies
         m.big = (q >> 58 ? 1u : 0u) | (q >> 46 ? 2u : 0u) | ((q >> 43) == 0 && !getenv("HEGPU_NO_FP64") ? 4u : 0u);
         m.pad = 0;
+        {   // -q^-1 mod 2^64 by Newton iteration; 2^64 mod q
+            u64 inv = q;  // q*q = 1 mod 8
+            for (int it = 0; it < 6; ++it) inv *= 2 - q * inv;
+            m.qinv_neg = (u64)0 - inv;
+            m.rmod = (u64)((((u128)1) << 64) % q);
+            m.rmod_sh = h_shoup(m.rmod, q);
+            m.pad2 = 0;
+        }
         const u64 wl = h_mulmod(inv[(size_t)i * n + 1].x, m.ninv, q);
         inv_last[i] = make_ulonglong2(wl, h_shoup(wl, q));
         modsd[i] = ModF64{ (double)q, 1.0 / (double)q, (double)m.ninv, (double)wl };
@@ -390,6 +419,7 @@ extern "C" int hegpu_ctx_destroy(hegpu_ctx *c)
     for (auto &kv : c->perms) cudaFree(kv.second);
     cudaFree(c->arena.base);
     cudaFree(c->stage);
+    cudaFree(c->park);
     cudaStreamDestroy(c->stream);
     delete c;
     return HEGPU_OK;
@@ -459,6 +489,15 @@ extern "C" int hegpu_profile_read(hegpu_ctx *c, int kind, double *ms, uint64_t *
 
 // ------------------------------------------------------------------------- keys
 static size_t key_words(hegpu_ctx *c) { return (size_t)(c->K - 1) * 2 * c->K * c->n; }
+// device copies of key-switching keys are kept in Montgomery form (k * 2^64 mod m) for ks_inner
+static int key_to_montgomery(hegpu_ctx *c, u64 *key)
+{
+    const size_t rows = (size_t)(c->K - 1) * 2 * c->K;
+    to_montgomery_kernel<<<ew_grid(c, rows * c->n), 256, 0, c->stream>>>(key, key, rows, c->K, c->n, c->n, c->n, c->d_mods);
+    c->launches++;
+    CU(cudaGetLastError());
+    return HEGPU_OK;
+}
 
 extern "C" int hegpu_load_relin_key(hegpu_ctx *c, const uint64_t *host)
 {
@@ -467,6 +506,7 @@ extern "C" int hegpu_load_relin_key(hegpu_ctx *c, const uint64_t *host)
     TRY(set_device(c));
     if (!c->relin_key) CU(cudaMalloc(&c->relin_key, key_words(c) * sizeof(u64)));
     CU(cudaMemcpyAsync(c->relin_key, host, key_words(c) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    TRY(key_to_montgomery(c, c->relin_key));
     CU(cudaStreamSynchronize(c->stream));
     return HEGPU_OK;
 }
@@ -499,6 +539,7 @@ extern "C" int hegpu_load_galois_key(hegpu_ctx *c, uint32_t elt, const uint64_t 
     u64 *&slot = c->galois_keys[elt];
     if (!slot) CU(cudaMalloc(&slot, key_words(c) * sizeof(u64)));
     CU(cudaMemcpyAsync(slot, host, key_words(c) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    TRY(key_to_montgomery(c, slot));
     CU(cudaStreamSynchronize(c->stream));
     const u32 *pm;
     TRY(get_perm(c, elt, &pm));
@@ -700,13 +741,29 @@ extern "C" int hegpu_pt_destroy(hegpu_pt *t)
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     cudaFree(t->d);
+    cudaFree(t->d_mont);
     delete t;
+    return HEGPU_OK;
+}
+static int pt_montgomery(hegpu_pt *t, const u64 **out)
+{
+    hegpu_ctx *c = t->ctx;
+    if (!t->d_mont) CU(cudaMalloc(&t->d_mont, (size_t)t->count * t->L_cap * c->n * sizeof(u64)));
+    if (!t->mont_valid) {
+        const size_t rows = (size_t)t->count * t->L_cap;
+        to_montgomery_kernel<<<ew_grid(c, rows * c->n), 256, 0, c->stream>>>(t->d, t->d_mont, rows, t->L_cap, c->n, c->n, c->n, c->d_mods);
+        c->launches++;
+        CU(cudaGetLastError());
+        t->mont_valid = true;
+    }
+    *out = t->d_mont;
     return HEGPU_OK;
 }
 static int pt_io(hegpu_pt *t, u32 i0, u32 cnt, u64 *host, bool upload)
 {
     hegpu_ctx *c = t->ctx;
     TRY(set_device(c));
+    if (upload) t->mont_valid = false;
     const size_t row = (size_t)t->L * c->n * sizeof(u64);
     u64 *d = t->d + i0 * t->stride();
     if (upload)
@@ -739,46 +796,83 @@ extern "C" int hegpu_pt_download_one(hegpu_pt *t, uint32_t index, uint64_t *host
 }
 
 // ------------------------------------------------------------------------- NTT launchers
-template <int LOGL, int SPLIT, class Job>
+template <int LOGL, int SPLIT, int LOGE, class Job>
 static int launch_fwd_shape(hegpu_ctx *c, const Job &job, u32 jobs, int kind, u64 words_per_job)
 {
     Prof pf(c, kind, jobs, (u64)jobs * words_per_job * 8 * c->n);
-    auto kern = ntt_fwd_kernel<LOGL, SPLIT, Job>;
+    auto kern = ntt_fwd_kernel<LOGL, SPLIT, LOGE, Job>;
     static bool configured[16] = {};
     if (!configured[c->device]) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL>::SMEM));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL, LOGE>::SMEM));
         configured[c->device] = true;
     }
-    kern<<<jobs << SPLIT, NttShape<LOGL>::THREADS, NttShape<LOGL>::SMEM, c->stream>>>(job, c->tabs);
+    kern<<<jobs << SPLIT, NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::SMEM, c->stream>>>(job, c->tabs);
     c->launches++;
     CU(cudaGetLastError());
     return HEGPU_OK;
 }
+template <int LOGL, int LOGE, class Job>
+static int launch_fwd_park(hegpu_ctx *c, const Job &job, u32 jobs, int kind, u64 words_per_job)
+{
+    TRY(park_reserve(c, (size_t)jobs << LOGL));
+    Prof pf(c, kind, jobs, (u64)jobs * words_per_job * 8 * c->n);
+    auto kern = ntt_fwd_park_kernel<LOGL, LOGE, Job>;
+    static bool configured[16] = {};
+    if (!configured[c->device]) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL, LOGE>::SMEM));
+        configured[c->device] = true;
+    }
+    kern<<<jobs, NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::SMEM, c->stream>>>(job, c->tabs, c->park);
+    c->launches++;
+    CU(cudaGetLastError());
+    return HEGPU_OK;
+}
+template <int LOGL, int LOGE, class Job>
+static int launch_inv_park(hegpu_ctx *c, const Job &job, u32 jobs, int kind)
+{
+    TRY(park_reserve(c, (size_t)jobs << LOGL));
+    Prof pf(c, kind, jobs, (u64)jobs * 16 * c->n);
+    auto kern = ntt_inv_park_kernel<LOGL, LOGE, Job>;
+    static bool configured[16] = {};
+    if (!configured[c->device]) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL, LOGE>::SMEM));
+        configured[c->device] = true;
+    }
+    kern<<<jobs, NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::SMEM, c->stream>>>(job, c->tabs, c->park);
+    c->launches++;
+    CU(cudaGetLastError());
+    return HEGPU_OK;
+}
+
 // words_per_job: algorithmic HBM words per coefficient of one job (2 = read + write)
 template <class Job>
 static int launch_ntt_fwd(hegpu_ctx *c, const Job &job, u32 jobs, int kind, u64 words_per_job)
 {
     if (jobs == 0) return HEGPU_OK;
     switch (c->logn) {
-    case 12: return launch_fwd_shape<12, 0>(c, job, jobs, kind, words_per_job);
-    case 13: return launch_fwd_shape<13, 0>(c, job, jobs, kind, words_per_job);
-    case 14: return launch_fwd_shape<14, 0>(c, job, jobs, kind, words_per_job);
-    case 15: return launch_fwd_shape<14, 1>(c, job, jobs, kind, words_per_job);
+    case 12: return launch_fwd_shape<12, 0, 4>(c, job, jobs, kind, words_per_job);
+    case 13: return launch_fwd_shape<13, 0, 4>(c, job, jobs, kind, words_per_job);
+    case 14:
+        if (c->use_park)
+            return c->loge == 3 ? launch_fwd_park<13, 3>(c, job, jobs, kind, words_per_job)
+                                : launch_fwd_park<13, 4>(c, job, jobs, kind, words_per_job);
+        return launch_fwd_shape<14, 0, 4>(c, job, jobs, kind, words_per_job);
+    case 15: return launch_fwd_shape<14, 1, 4>(c, job, jobs, kind, words_per_job);
     }
     LOGIC("unsupported ring degree");
 }
 
-template <int LOGL, int SPLIT, class Job>
+template <int LOGL, int SPLIT, int LOGE, class Job>
 static int launch_inv_shape(hegpu_ctx *c, const Job &job, u32 jobs, u64 *scratch, int kind)
 {
     Prof pf(c, kind, jobs, (u64)jobs * 16 * c->n);
-    auto kern = ntt_inv_kernel<LOGL, SPLIT, Job>;
+    auto kern = ntt_inv_kernel<LOGL, SPLIT, LOGE, Job>;
     static bool configured[16] = {};
     if (!configured[c->device]) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL>::SMEM));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL, LOGE>::SMEM));
         configured[c->device] = true;
     }
-    kern<<<jobs << SPLIT, NttShape<LOGL>::THREADS, NttShape<LOGL>::SMEM, c->stream>>>(job, c->tabs, scratch);
+    kern<<<jobs << SPLIT, NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::SMEM, c->stream>>>(job, c->tabs, scratch);
     c->launches++;
     CU(cudaGetLastError());
     if (SPLIT) {
@@ -795,10 +889,13 @@ static int launch_ntt_inv(hegpu_ctx *c, const Job &job, u32 jobs, u64 *scratch, 
 {
     if (jobs == 0) return HEGPU_OK;
     switch (c->logn) {
-    case 12: return launch_inv_shape<12, 0>(c, job, jobs, scratch, kind);
-    case 13: return launch_inv_shape<13, 0>(c, job, jobs, scratch, kind);
-    case 14: return launch_inv_shape<14, 0>(c, job, jobs, scratch, kind);
-    case 15: return launch_inv_shape<14, 1>(c, job, jobs, scratch, kind);
+    case 12: return launch_inv_shape<12, 0, 4>(c, job, jobs, scratch, kind);
+    case 13: return launch_inv_shape<13, 0, 4>(c, job, jobs, scratch, kind);
+    case 14:
+        if (c->use_park)
+            return c->loge == 3 ? launch_inv_park<13, 3>(c, job, jobs, kind) : launch_inv_park<13, 4>(c, job, jobs, kind);
+        return launch_inv_shape<14, 0, 4>(c, job, jobs, scratch, kind);
+    case 15: return launch_inv_shape<14, 1, 4>(c, job, jobs, scratch, kind);
     }
     LOGIC("unsupported ring degree");
 }
@@ -1360,7 +1457,7 @@ extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in
             P.baby[0] = vin;
             for (u32 k = 1; k < n1; ++k) P.baby[k] = view_of(baby, (size_t)(k - 1) * Bn);
             P.inner = view_of(inner, 0);
-            P.diag = diags->d;
+            TRY(pt_montgomery(const_cast<hegpu_pt *>(diags), &P.diag));
             P.diag_si = diags->stride();
             P.diag_sl = n;
             P.n1 = n1;

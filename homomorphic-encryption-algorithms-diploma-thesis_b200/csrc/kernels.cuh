@@ -39,6 +39,9 @@ struct PlainJob {
     __device__ __forceinline__ u32 mod(u32 j) const { return first_mod + j % n_mods; }
     __device__ __forceinline__ u64 load(u32 j, u32 i, const ModConst &) const { return src[(size_t)j * n + i]; }
     __device__ __forceinline__ void store(u32 j, u32 i, u64 v, const ModConst &) const { dst[(size_t)j * n + i] = v; }
+    struct Ops {};
+    __device__ __forceinline__ Ops fetch(u32, u32, const ModConst &) const { return Ops{}; }
+    __device__ __forceinline__ void store(u32 j, u32 i, u64 v, const ModConst &m, const Ops &) const { store(j, i, v, m); }
 };
 
 // key-switch launch parameters (one launch handles ngroups rotations/relinearisations of
@@ -106,6 +109,9 @@ struct KsLiftJob {
         split(j, e, dj, di);
         P.ext[(((size_t)e * P.L + dj) * (P.L + 1) + di) * P.n + i] = x;
     }
+    struct Ops {};
+    __device__ __forceinline__ Ops fetch(u32, u32, const ModConst &) const { return Ops{}; }
+    __device__ __forceinline__ void store(u32 j, u32 i, u64 v, const ModConst &m, const Ops &) const { store(j, i, v, m); }
 };
 
 // INTT of a dropped limb with the rounding offset added: t = (INTT_d(src) + floor(d/2)) mod d.
@@ -146,23 +152,34 @@ struct KsModDownJob {
         if (mods[P.K - 1].q > m.q) v = barrett64(v, m);
         return submod(v, md[l].halfmod, m.q);
     }
-    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m) const
+    struct Ops {
+        u64 acc, base;
+    };
+    __device__ __forceinline__ Ops fetch(u32 j, u32 i, const ModConst &) const
     {
         u32 e, c, l;
         split(j, e, c, l);
         const u32 g = e / P.B, b = e % P.B;
-        const u64 a = P.acc[(((size_t)e * 2 + c) * (P.L + 1) + l) * P.n + i];
-        const u64 r = mul_shoup(submod(a, x, m.q), md[l].inv, md[l].inv_sh, m.q);
+        Ops o;
+        o.acc = P.acc[(((size_t)e * 2 + c) * (P.L + 1) + l) * P.n + i];
         const CtView &vi = P.in[g];
-        u64 base = 0;
+        o.base = 0;
         if (c == 0) {
             const u32 *pm = P.perm[g];
-            base = vi.p[b * vi.sb + l * vi.sl + (pm ? __ldg(pm + i) : i)];
+            o.base = vi.p[b * vi.sb + l * vi.sl + (pm ? __ldg(pm + i) : i)];
         } else if (P.has_base1) {
-            base = vi.p[b * vi.sb + vi.sp + l * vi.sl + i];
+            o.base = vi.p[b * vi.sb + vi.sp + l * vi.sl + i];
         }
+        return o;
+    }
+    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m, const Ops &o) const
+    {
+        u32 e, c, l;
+        split(j, e, c, l);
+        const u32 g = e / P.B, b = e % P.B;
+        const u64 r = mul_shoup(submod(o.acc, x, m.q), md[l].inv, md[l].inv_sh, m.q);
         const CtView &vo = P.out[g];
-        vo.p[b * vo.sb + c * vo.sp + l * vo.sl + i] = addmod(base, r, m.q);
+        vo.p[b * vo.sb + c * vo.sp + l * vo.sl + i] = addmod(o.base, r, m.q);
     }
 };
 
@@ -180,19 +197,26 @@ struct RescaleJob {
         if (mods[drop_mod].q > m.q) v = barrett64(v, m);
         return submod(v, md[j % Lm1].halfmod, m.q);
     }
-    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m) const
+    struct Ops {
+        u64 av;
+    };
+    __device__ __forceinline__ Ops fetch(u32 j, u32 i, const ModConst &) const
     {
         const u32 l = j % Lm1, bp = j / Lm1, p = bp % size, b = bp / size;
-        const u64 av = a.p[b * a.sb + p * a.sp + l * a.sl + i];
-        out.p[b * out.sb + p * out.sp + l * out.sl + i] = mul_shoup(submod(av, x, m.q), md[l].inv, md[l].inv_sh, m.q);
+        return Ops{ a.p[b * a.sb + p * a.sp + l * a.sl + i] };
+    }
+    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m, const Ops &o) const
+    {
+        const u32 l = j % Lm1, bp = j / Lm1, p = bp % size, b = bp / size;
+        out.p[b * out.sb + p * out.sp + l * out.sl + i] = mul_shoup(submod(o.av, x, m.q), md[l].inv, md[l].inv_sh, m.q);
     }
 };
 
 // ---------------------------------------------------------------------------------------
 // NTT kernels.  grid = jobs << SPLIT, block = 2^LOGL / 16, dynamic smem = 8 << LOGL.
 // ---------------------------------------------------------------------------------------
-template <int LOGL, int SPLIT, class Job>
-__global__ void __launch_bounds__(NttShape<LOGL>::THREADS, 1) ntt_fwd_kernel(const Job job, const NttTables T)
+template <int LOGL, int SPLIT, int LOGE, class Job>
+__global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::MINB) ntt_fwd_kernel(const Job job, const NttTables T)
 {
     extern __shared__ __align__(16) u64 sm[];
     const u32 jid = blockIdx.x >> SPLIT;
@@ -201,16 +225,17 @@ __global__ void __launch_bounds__(NttShape<LOGL>::THREADS, 1) ntt_fwd_kernel(con
     const ModConst m = T.mods[mi];
     const ulonglong2 *tw = T.fwd + (size_t)mi * T.n;
     const u32 boff = h << LOGL;
-    auto store = [&](u32 i, u64 v) { job.store(jid, boff + i, v, m); };
+    auto fetch = [&](u32 i) { return job.fetch(jid, boff + i, m); };
+    auto store = [&](u32 i, u64 v, const typename Job::Ops &o) { job.store(jid, boff + i, v, m, o); };
     const ulonglong2 nowl = make_ulonglong2(0, 0);
     if constexpr (SPLIT == 0) {
         auto load = [&](u32 i) -> u64 { return job.load(jid, i, m); };
         if (m.big & 4u)
-            ntt_fwd_cta<LOGL>(load, store, T.fwd_d + (size_t)mi * T.n, T.n, ArF64(T.modsd[mi]), sm);
+            ntt_fwd_cta<LOGL, LOGE>(load, fetch, store, T.fwd_d + (size_t)mi * T.n, T.n, ArF64(T.modsd[mi]), sm);
         else if (m.big & 1u)
-            ntt_fwd_cta<LOGL>(load, store, tw, T.n, ArI64<true>(m, nowl), sm);
+            ntt_fwd_cta<LOGL, LOGE>(load, fetch, store, tw, T.n, ArI64<true>(m, nowl), sm);
         else
-            ntt_fwd_cta<LOGL>(load, store, tw, T.n, ArI64<false>(m, nowl), sm);
+            ntt_fwd_cta<LOGL, LOGE>(load, fetch, store, tw, T.n, ArI64<false>(m, nowl), sm);
     } else {
         // stage 1 (stride N/2) redone from global memory by both halves
         const ulonglong2 W = __ldg(tw + 1);
@@ -222,16 +247,16 @@ __global__ void __launch_bounds__(NttShape<LOGL>::THREADS, 1) ntt_fwd_kernel(con
             return h ? X + q2 - Tm : X + Tm;
         };
         if (m.big & 1u)
-            ntt_fwd_cta<LOGL>(load, store, tw, T.n + boff, ArI64<true>(m, nowl), sm);
+            ntt_fwd_cta<LOGL, LOGE>(load, fetch, store, tw, T.n + boff, ArI64<true>(m, nowl), sm);
         else
-            ntt_fwd_cta<LOGL>(load, store, tw, T.n + boff, ArI64<false>(m, nowl), sm);
+            ntt_fwd_cta<LOGL, LOGE>(load, fetch, store, tw, T.n + boff, ArI64<false>(m, nowl), sm);
     }
 }
 
 // SPLIT = 1: the CTA transforms its half and leaves lazy values in `scratch`
 // ([jobs][N]); ntt_inv_final_kernel applies the last stage and the job's store.
-template <int LOGL, int SPLIT, class Job>
-__global__ void __launch_bounds__(NttShape<LOGL>::THREADS, 1)
+template <int LOGL, int SPLIT, int LOGE, class Job>
+__global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::MINB)
     ntt_inv_kernel(const Job job, const NttTables T, u64 *__restrict__ scratch)
 {
     extern __shared__ __align__(16) u64 sm[];
@@ -246,19 +271,109 @@ __global__ void __launch_bounds__(NttShape<LOGL>::THREADS, 1)
     if constexpr (SPLIT == 0) {
         auto store = [&](u32 i, u64 v) { job.store(jid, i, v, m); };
         if (m.big & 4u)
-            ntt_inv_cta<LOGL, LOGL - 1>(load, store, T.inv_d + (size_t)mi * T.n, T.n, ArF64(T.modsd[mi]), sm);
+            ntt_inv_cta<LOGL, LOGE, LOGL - 1>(load, store, T.inv_d + (size_t)mi * T.n, T.n, ArF64(T.modsd[mi]), sm);
         else if (m.big & 2u)
-            ntt_inv_cta<LOGL, LOGL - 1>(load, store, tw, T.n, ArI64<true>(m, wl), sm);
+            ntt_inv_cta<LOGL, LOGE, LOGL - 1>(load, store, tw, T.n, ArI64<true>(m, wl), sm);
         else
-            ntt_inv_cta<LOGL, LOGL - 1>(load, store, tw, T.n, ArI64<false>(m, wl), sm);
+            ntt_inv_cta<LOGL, LOGE, LOGL - 1>(load, store, tw, T.n, ArI64<false>(m, wl), sm);
     } else {
         u64 *dst = scratch + (size_t)jid * T.n + boff;
         auto store = [&](u32 i, u64 v) { dst[i] = v; };
         if (m.big & 2u)
-            ntt_inv_cta<LOGL, -1>(load, store, tw, T.n + boff, ArI64<true>(m, wl), sm);
+            ntt_inv_cta<LOGL, LOGE, -1>(load, store, tw, T.n + boff, ArI64<true>(m, wl), sm);
         else
-            ntt_inv_cta<LOGL, -1>(load, store, tw, T.n + boff, ArI64<false>(m, wl), sm);
+            ntt_inv_cta<LOGL, LOGE, -1>(load, store, tw, T.n + boff, ArI64<false>(m, wl), sm);
     }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// "park" kernels: N = 2^(LOGL+1) transformed by ONE CTA in 2^LOGL words of shared memory.
+// Forward: the stride-N/2 stage is computed while loading half 0; its bottom outputs are parked
+// in `park` ([jobs][N/2], written and re-read by the same thread, L2-resident) and transformed
+// second.  Inverse: half 0 is transformed and parked, half 1 is transformed and its last-pass
+// registers are combined with the parked half in the final stride-N/2 stage.
+// ---------------------------------------------------------------------------------------
+template <int LOGL, int LOGE, class Job>
+__global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::MINB)
+    ntt_fwd_park_kernel(const Job job, const NttTables T, u64 *__restrict__ park)
+{
+    extern __shared__ __align__(16) u64 sm[];
+    const u32 jid = blockIdx.x;
+    const u32 mi = job.mod(jid);
+    const ModConst m = T.mods[mi];
+    const ulonglong2 *tw = T.fwd + (size_t)mi * T.n;
+    constexpr u32 half = 1u << LOGL;
+    u64 *pk = park + (size_t)jid * half;
+    const ulonglong2 W = __ldg(tw + 1);
+    const u64 q2 = m.q << 1;
+    auto load0 = [&](u32 i) -> u64 {
+        const u64 X = job.load(jid, i, m);
+        const u64 Y = job.load(jid, i + half, m);
+        const u64 Tm = mul_shoup_lazy(Y, W.x, W.y, m.q);
+        pk[i] = X + q2 - Tm;
+        return X + Tm;
+    };
+    auto load1 = [&](u32 i) -> u64 { return pk[i]; };
+    auto fetch0 = [&](u32 i) { return job.fetch(jid, i, m); };
+    auto fetch1 = [&](u32 i) { return job.fetch(jid, half + i, m); };
+    auto store0 = [&](u32 i, u64 v, const typename Job::Ops &o) { job.store(jid, i, v, m, o); };
+    auto store1 = [&](u32 i, u64 v, const typename Job::Ops &o) { job.store(jid, half + i, v, m, o); };
+    const ulonglong2 nowl = make_ulonglong2(0, 0);
+    if (m.big & 4u) {
+        const ArF64 ar(T.modsd[mi]);
+        const double *twd = T.fwd_d + (size_t)mi * T.n;
+        ntt_fwd_cta<LOGL, LOGE>(load0, fetch0, store0, twd, T.n, ar, sm);
+        __syncthreads();
+        ntt_fwd_cta<LOGL, LOGE>(load1, fetch1, store1, twd, T.n + half, ar, sm);
+    } else if (m.big & 1u) {
+        const ArI64<true> ar(m, nowl);
+        ntt_fwd_cta<LOGL, LOGE>(load0, fetch0, store0, tw, T.n, ar, sm);
+        __syncthreads();
+        ntt_fwd_cta<LOGL, LOGE>(load1, fetch1, store1, tw, T.n + half, ar, sm);
+    } else {
+        const ArI64<false> ar(m, nowl);
+        ntt_fwd_cta<LOGL, LOGE>(load0, fetch0, store0, tw, T.n, ar, sm);
+        __syncthreads();
+        ntt_fwd_cta<LOGL, LOGE>(load1, fetch1, store1, tw, T.n + half, ar, sm);
+    }
+}
+
+template <int LOGL, int LOGE, class A, class TWP, class Job>
+__device__ __forceinline__ void inv_park_body(const Job &job, u32 jid, const ModConst &m, const A &ar, const TWP tw, u32 n,
+                                              typename A::V *pk, u64 *sm)
+{
+    constexpr u32 half = 1u << LOGL;
+    auto load0 = [&](u32 i) -> u64 { return job.load(jid, i, m); };
+    auto load1 = [&](u32 i) -> u64 { return job.load(jid, half + i, m); };
+    auto store0 = [&](u32 i, typename A::V v) { pk[i] = v; };
+    auto store1 = [&](u32 i, typename A::V y) {
+        typename A::V x = pk[i];
+        ar.template inv_bfly_last<LOGL>(x, y);
+        job.store(jid, i, ar.inv_final(x), m);
+        job.store(jid, half + i, ar.inv_final(y), m);
+    };
+    ntt_inv_cta<LOGL, LOGE, -1>(load0, store0, tw, n, ar, sm);
+    __syncthreads();
+    ntt_inv_cta<LOGL, LOGE, -1>(load1, store1, tw, n + half, ar, sm);
+}
+
+template <int LOGL, int LOGE, class Job>
+__global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::MINB)
+    ntt_inv_park_kernel(const Job job, const NttTables T, u64 *__restrict__ park)
+{
+    extern __shared__ __align__(16) u64 sm[];
+    const u32 jid = blockIdx.x;
+    const u32 mi = job.mod(jid);
+    const ModConst m = T.mods[mi];
+    const ulonglong2 *tw = T.inv + (size_t)mi * T.n;
+    u64 *pk = park + ((size_t)jid << LOGL);
+    if (m.big & 4u)
+        inv_park_body<LOGL, LOGE>(job, jid, m, ArF64(T.modsd[mi]), T.inv_d + (size_t)mi * T.n, T.n, reinterpret_cast<double *>(pk), sm);
+    else if (m.big & 2u)
+        inv_park_body<LOGL, LOGE>(job, jid, m, ArI64<true>(m, T.inv_last[mi]), tw, T.n, pk, sm);
+    else
+        inv_park_body<LOGL, LOGE>(job, jid, m, ArI64<false>(m, T.inv_last[mi]), tw, T.n, pk, sm);
 }
 
 // last (stride N/2) INTT stage for N = 2^(LOGL+1), element-wise over scratch
@@ -290,7 +405,9 @@ __global__ void __launch_bounds__(256) ntt_inv_final_kernel(const Job job, const
 // ---------------------------------------------------------------------------------------
 // K7 step 3: key inner product.  acc[e][c][i] = sum_j ext[e][j][i] (.) key[j][c][ki] mod m_i;
 // digit i == j reads the (permuted) target directly.  128-bit lazy accumulation, one
-// Barrett reduction (as SEAL).  A thread owns one (group, ext limb, coefficient), keeps the
+// reduction (SEAL: Barrett; here the device copy of every key is kept in Montgomery form
+// k*2^64 mod m, so one Montgomery reduction returns the same canonical residue at a third of
+// the multiplies).  A thread owns one (group, ext limb, coefficient), keeps the
 // 2L key words of that coefficient in registers and sweeps a chunk of the batch, so the keys
 // are read once per chunk instead of once per ciphertext.  grid = (x blocks, ngroups*(L+1),
 // batch chunks).  LT = L when L <= 4 (keys in registers), 0 = generic.
@@ -345,8 +462,8 @@ __global__ void __launch_bounds__(256) ks_inner_kernel(const KsParams P, const M
                 mac128(h1, l1, d, __ldg(key + (size_t)(2 * j + 1) * kstride));
             }
         }
-        P.acc[((e * 2 + 0) * (L + 1) + i) * n + x] = barrett128(h0, l0, m);
-        P.acc[((e * 2 + 1) * (L + 1) + i) * n + x] = barrett128(h1, l1, m);
+        P.acc[((e * 2 + 0) * (L + 1) + i) * n + x] = mont_reduce(h0, l0, m);  // keys are stored as k*2^64 mod m
+        P.acc[((e * 2 + 1) * (L + 1) + i) * n + x] = mont_reduce(h1, l1, m);
     }
 }
 
@@ -469,7 +586,7 @@ __global__ void __launch_bounds__(256) fixup_kernel(const CtView v, u32 B, u32 p
 struct BsgsParams {
     CtView baby[MAXG];  // baby[0] = the input batch
     CtView inner;       // batch index = g*B + b
-    const u64 *diag;    // [n1*n2][Lcap][N]
+    const u64 *diag;    // [n1*n2][Lcap][N], Montgomery form (d * 2^64 mod q_l)
     size_t diag_si, diag_sl;
     u32 n1, n2, B, L, n;
 };
@@ -544,7 +661,7 @@ __global__ void __launch_bounds__(32 * BSGS_GT) bsgs_inner_kernel(const BsgsPara
 #pragma unroll
                     for (int k = 0; k < N1; ++k) mac128(h, lo, buf[s][ci][k][threadIdx.x], d[k]);
                     P.inner.p[((size_t)g * P.B + (it >> 1)) * P.inner.sb + (it & 1) * P.inner.sp + l * P.inner.sl + x0 + threadIdx.x] =
-                        barrett128(h, lo, m);
+                        mont_reduce(h, lo, m);  // diag holds d*2^64 mod q
                 }
             }
         }
@@ -616,6 +733,22 @@ __global__ void __launch_bounds__(256) base_gather_sum_kernel(const BaseSumParam
             for (u32 g = 0; g < P.groups; ++g)
                 s = addmod(s, P.rest.p[((size_t)g * P.B + b) * P.rest.sb + l * P.rest.sl + __ldg(P.perm[g] + x)], q);
         P.out.p[b * P.out.sb + p * P.out.sp + l * P.out.sl + x] = s;
+    }
+}
+
+// x -> x * 2^64 mod q (Montgomery form) for `rows` limb polynomials; row r uses modulus
+// mod_of_row = (r % limbs_per_item) mapped through `last_is_special` (key layout: K limbs, limb
+// K-1 = special prime; plaintext layout: limb l = modulus l)
+__global__ void __launch_bounds__(256) to_montgomery_kernel(const u64 *__restrict__ src, u64 *__restrict__ dst, size_t rows,
+                                                            u32 limbs_per_item, size_t row_stride_src, size_t row_stride_dst, u32 n,
+                                                            const ModConst *__restrict__ mods)
+{
+    const size_t total = rows * n;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = idx / n;
+        const u32 x = (u32)(idx % n);
+        const ModConst m = mods[r % limbs_per_item];
+        dst[r * row_stride_dst + x] = mul_shoup(src[r * row_stride_src + x], m.rmod, m.rmod_sh, m.q);
     }
 }
 

@@ -17,8 +17,12 @@ struct ModConst {
     u64 mu_lo;    // floor(2^128 / q) low word
     u64 ninv;     // N^{-1} mod q
     u64 ninv_sh;  // Shoup quotient of ninv
-    u32 big;      // q >= 2^48: lazy ranges need per-stage corrections
+    u32 big;      // bit 0/1: forward / inverse NTT needs lazy-range corrections; bit 2: FP64 butterflies
     u32 pad;
+    u64 qinv_neg; // -q^-1 mod 2^64 (Montgomery reduction)
+    u64 rmod;     // 2^64 mod q, and its Shoup quotient: x -> x*2^64 mod q (Montgomery form)
+    u64 rmod_sh;
+    u64 pad2;
 };
 
 __device__ __forceinline__ u64 csub(u64 v, u64 c) { return v >= c ? v - c : v; }
@@ -59,12 +63,22 @@ __device__ __forceinline__ u64 mulmod(u64 a, u64 b, const ModConst &m)
     return barrett128(__umul64hi(a, b), a * b, m);
 }
 
-// 128-bit accumulate acc += a*b
+// 128-bit accumulate acc += a*b (one 4-IMAD.WIDE product with carry chains)
 __device__ __forceinline__ void mac128(u64 &hi, u64 &lo, u64 a, u64 b)
 {
-    u64 pl = a * b, ph = __umul64hi(a, b);
-    lo += pl;
-    hi += ph + (lo < pl);
+    unsigned __int128 acc = ((unsigned __int128)hi << 64) | lo;
+    acc += (unsigned __int128)a * b;
+    lo = (u64)acc;
+    hi = (u64)(acc >> 64);
+}
+
+// Montgomery reduction: (hi:lo) * 2^-64 mod q, canonical; needs hi:lo < q * 2^64.
+// One low product + one high product instead of Barrett's five.
+__device__ __forceinline__ u64 mont_reduce(u64 hi, u64 lo, const ModConst &m)
+{
+    const u64 t = lo * m.qinv_neg;
+    const u64 r = hi + __umul64hi(t, m.q) + (lo != 0 ? 1ull : 0ull);
+    return csub(r, m.q);
 }
 
 __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { return csub(a + b, q); }

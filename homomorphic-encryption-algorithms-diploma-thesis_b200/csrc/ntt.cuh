@@ -22,6 +22,11 @@
 //                    B200) -- exact integer arithmetic in doubles: h = y*w, l = fma(y,w,-h),
 //                    t = rint(h/q), r = fma(-t,q,h) + l == y*w - t*q exactly; 8 FP64 ops per
 //                    butterfly instead of ~41 integer-multiply issue cycles;
+//  * N = 16384 runs as ONE CTA that transforms the two halves one after the other in 64 KiB of
+//    shared memory ("park" kernels): the stride-N/2 stage is done on the fly while loading, the
+//    half that is not being worked on is parked in an L2-resident scratch (+8*N bytes of L2
+//    traffic, no extra HBM pass), and 2-3 such CTAs share an SM so that their load, exchange and
+//    store phases overlap (measured +35 % over one 128 KiB CTA per SM);
 //  * N = 32768 runs as two CTAs that each redo the first (stride N/2) stage from global
 //    memory and then own one half (forward), or finish with one element-wise stage kernel
 //    (inverse) -- see ntt_fwd_kernel / ntt_inv_kernel SPLIT.
@@ -47,37 +52,44 @@ struct NttTables {
     u32 logn;
 };
 
-template <int LOGL>
+// LOGE = log2 of the coefficients a thread keeps in registers per set: 4 (radix-16 passes, 512
+// threads x 128 registers) or 3 (radix-8 passes, 1024 threads x 64 registers: twice the warps).
+template <int LOGL, int LOGE>
 struct NttShape {
     static constexpr int LSIZE = 1 << LOGL;
-    static constexpr int SETS = LSIZE / 16;                       // 16-coefficient register sets per pass
-    static constexpr int THREADS = SETS > 512 ? 512 : SETS;       // 512 threads leave 128 registers each
+    static constexpr int E = 1 << LOGE;
+    static constexpr int SETS = LSIZE / E;                        // register sets per pass
+    // <= 64 KiB transforms run 256 threads so that 2 (LOGE = 4, 128 registers) or 3 (LOGE = 3, 64
+    // registers) CTAs share an SM and overlap their load / exchange / store phases
+    static constexpr int MAXT = (LOGL <= 13) ? 256 : ((LOGE == 4) ? 512 : 1024);
+    static constexpr int MINB = (LOGL <= 13) ? ((LOGE == 4) ? 2 : 3) : 1;
+    static constexpr int THREADS = SETS > MAXT ? MAXT : SETS;
     static constexpr int ITER = SETS / THREADS;
-    static constexpr int REM = (LOGL % 4 == 0) ? 4 : (LOGL % 4);  // stages of the partial pass
-    static constexpr int NFULL = (LOGL - REM) / 4;                // number of full radix-16 passes
+    static constexpr int REM = (LOGL % LOGE == 0) ? LOGE : (LOGL % LOGE);  // stages of the partial pass
+    static constexpr int NFULL = (LOGL - REM) / LOGE;                      // number of full passes
     static constexpr size_t SMEM = sizeof(u64) << LOGL;
 };
 
 __device__ __forceinline__ u32 swz(u32 idx) { return idx ^ ((idx >> 4) & 15u); }
 
-// Position of the 16 coefficients a thread owns in a pass.  The low S bits of the register
-// index k sit at index bits [PLO+S-1:PLO]; the remaining 4-S bits sit at [PHI+3-S:PHI];
+// Position of the 2^LOGE coefficients a thread owns in a pass.  The low S bits of the register
+// index k sit at index bits [PLO+S-1:PLO]; the remaining LOGE-S bits sit at [PHI+LOGE-1-S:PHI];
 // the thread id fills every other bit, low to high.
-template <int LOGL, int S, int PLO, int PHI>
+template <int LOGL, int LOGE, int S, int PLO, int PHI>
 struct PassMap {
     __device__ static __forceinline__ u32 base(u32 t)
     {
         u32 lo = t & ((1u << PLO) - 1u);
         u32 mid = (t >> PLO) & ((1u << (PHI - PLO - S)) - 1u);
-        u32 hi = (S == 4) ? 0u : (t >> (PHI - S));
+        u32 hi = (S == LOGE) ? 0u : (t >> (PHI - S));
         u32 r = lo | (mid << (PLO + S));
-        if (S != 4) r |= hi << (PHI + 4 - S);
+        if (S != LOGE) r |= hi << (PHI + LOGE - S);
         return r;
     }
     __device__ static __forceinline__ u32 off(int k)
     {
         u32 r = (u32)(k & ((1 << S) - 1)) << PLO;
-        if (S != 4) r |= (u32)(k >> S) << PHI;
+        if (S != LOGE) r |= (u32)(k >> S) << PHI;
         return r;
     }
 };
@@ -205,15 +217,15 @@ struct ArF64 {
 
 // ------------------------------------------------------------------ forward butterflies
 // S stages on register bits S-1..0 (descending).  gbase = N + (global index of x[0]).
-template <int S, int PLO, int PHI, class A>
-__device__ __forceinline__ void fwd_stages(typename A::V (&x)[16], u32 gbase, const typename A::TW *__restrict__ tw, const A &ar)
+template <int LOGE, int S, int PLO, int PHI, class A>
+__device__ __forceinline__ void fwd_stages(typename A::V (&x)[1 << LOGE], u32 gbase, const typename A::TW *__restrict__ tw, const A &ar)
 {
 #pragma unroll
     for (int ss = 0; ss < S; ++ss) {
         const int s = S - 1 - ss;
 #pragma unroll
-        for (int kh = 0; kh < (1 << (4 - S)); ++kh) {
-            const u32 g = (S == 4) ? gbase : gbase + ((u32)kh << PHI);
+        for (int kh = 0; kh < (1 << (LOGE - S)); ++kh) {
+            const u32 g = (S == LOGE) ? gbase : gbase + ((u32)kh << PHI);
 #pragma unroll
             for (int hi = 0; hi < (1 << ss); ++hi) {
                 const typename A::TW W = __ldg(tw + (g >> (PLO + s + 1)) + hi);
@@ -228,35 +240,36 @@ __device__ __forceinline__ void fwd_stages(typename A::V (&x)[16], u32 gbase, co
 }
 
 // full radix-16 passes of the forward transform, field position descending
-template <int LOGL, int PASS, class A, class Load>
+template <int LOGL, int LOGE, int PASS, class A, class Load>
 __device__ __forceinline__ void fwd_full_passes(Load &load, const typename A::TW *__restrict__ tw, u32 goff, const A &ar,
                                                 typename A::V *sm)
 {
-    typedef NttShape<LOGL> Sh;
+    typedef NttShape<LOGL, LOGE> Sh;
+    constexpr int E = 1 << LOGE;
     if constexpr (PASS < Sh::NFULL) {
-        constexpr int P = LOGL - 4 * (PASS + 1);
-        typedef PassMap<LOGL, 4, P, LOGL> M;
+        constexpr int P = LOGL - LOGE * (PASS + 1);
+        typedef PassMap<LOGL, LOGE, LOGE, P, LOGL> M;
 #pragma unroll 1
         for (int it = 0; it < Sh::ITER; ++it) {
-            typename A::V x[16];
+            typename A::V x[E];
             const u32 b = M::base(threadIdx.x + it * Sh::THREADS);
             if constexpr (PASS == 0) {
-                u64 raw[16];
+                u64 raw[E];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) raw[k] = load(b + M::off(k));
+                for (int k = 0; k < E; ++k) raw[k] = load(b + M::off(k));
 #pragma unroll
-                for (int k = 0; k < 16; ++k) x[k] = ar.from_load(raw[k]);
+                for (int k = 0; k < E; ++k) x[k] = ar.from_load(raw[k]);
             } else {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) x[k] = ar.fwd_fix(sm[swz(b + M::off(k))]);
+                for (int k = 0; k < E; ++k) x[k] = ar.fwd_fix(sm[swz(b + M::off(k))]);
             }
-            fwd_stages<4, P, LOGL>(x, goff + b, tw, ar);
+            fwd_stages<LOGE, LOGE, P, LOGL>(x, goff + b, tw, ar);
             // in-place: a thread only overwrites the slots it read itself
 #pragma unroll
-            for (int k = 0; k < 16; ++k) sm[swz(b + M::off(k))] = x[k];
+            for (int k = 0; k < E; ++k) sm[swz(b + M::off(k))] = x[k];
         }
         __syncthreads();
-        fwd_full_passes<LOGL, PASS + 1>(load, tw, goff, ar, sm);
+        fwd_full_passes<LOGL, LOGE, PASS + 1>(load, tw, goff, ar, sm);
     }
 }
 
@@ -264,39 +277,46 @@ __device__ __forceinline__ void fwd_full_passes(Load &load, const typename A::TW
 //  load(i)  -> coefficient i of this CTA's block, any value < 3q
 //  store(i, v) receives the canonical result for position i of the block
 //  goff = N_total + block offset (global index of local coefficient 0)
-template <int LOGL, class A, class Load, class Store>
-__device__ __forceinline__ void ntt_fwd_cta(Load load, Store store, const typename A::TW *__restrict__ tw, u32 goff, const A &ar,
-                                            u64 *smraw)
+//  fetch(i) -> the epilogue operands of position i (issued for the whole register set before the
+//  last stages run, so their latency hides behind the butterflies instead of serialising behind
+//  the stores); store(i, v, ops) receives the canonical result and those operands
+template <int LOGL, int LOGE, class A, class Load, class Fetch, class Store>
+__device__ __forceinline__ void ntt_fwd_cta(Load load, Fetch fetch, Store store, const typename A::TW *__restrict__ tw, u32 goff,
+                                            const A &ar, u64 *smraw)
 {
-    typedef NttShape<LOGL> Sh;
+    typedef NttShape<LOGL, LOGE> Sh;
+    constexpr int E = 1 << LOGE;
     typename A::V *sm = reinterpret_cast<typename A::V *>(smraw);
-    fwd_full_passes<LOGL, 0>(load, tw, goff, ar, sm);
+    fwd_full_passes<LOGL, LOGE, 0>(load, tw, goff, ar, sm);
     // last pass: REM stages on the low bits; the other register bits are the top index bits
     constexpr int S = Sh::REM;
-    constexpr int PHI = (S == 4) ? LOGL : LOGL - (4 - S);
-    typedef PassMap<LOGL, S, 0, PHI> M;
+    constexpr int PHI = (S == LOGE) ? LOGL : LOGL - (LOGE - S);
+    typedef PassMap<LOGL, LOGE, S, 0, PHI> M;
 #pragma unroll 1
     for (int it = 0; it < Sh::ITER; ++it) {
-        typename A::V x[16];
+        typename A::V x[E];
         const u32 b = M::base(threadIdx.x + it * Sh::THREADS);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = ar.fwd_fix(sm[swz(b + M::off(k))]);
-        fwd_stages<S, 0, PHI>(x, goff + b, tw, ar);
+        for (int k = 0; k < E; ++k) x[k] = ar.fwd_fix(sm[swz(b + M::off(k))]);
+        decltype(fetch(0u)) ops[E];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) store(b + M::off(k), ar.fwd_final(x[k]));
+        for (int k = 0; k < E; ++k) ops[k] = fetch(b + M::off(k));
+        fwd_stages<LOGE, S, 0, PHI>(x, goff + b, tw, ar);
+#pragma unroll
+        for (int k = 0; k < E; ++k) store(b + M::off(k), ar.fwd_final(x[k]), ops[k]);
     }
 }
 
 // ------------------------------------------------------------------ inverse butterflies
 // S stages on register bits 0..S-1 (ascending); global stage number = PLO + s.
-template <int S, int PLO, int PHI, int LAST_BIT, class A>
-__device__ __forceinline__ void inv_stages(typename A::V (&x)[16], u32 gbase, const typename A::TW *__restrict__ tw, const A &ar)
+template <int LOGE, int S, int PLO, int PHI, int LAST_BIT, class A>
+__device__ __forceinline__ void inv_stages(typename A::V (&x)[1 << LOGE], u32 gbase, const typename A::TW *__restrict__ tw, const A &ar)
 {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
 #pragma unroll
-        for (int kh = 0; kh < (1 << (4 - S)); ++kh) {
-            const u32 g = (S == 4) ? gbase : gbase + ((u32)kh << PHI);
+        for (int kh = 0; kh < (1 << (LOGE - S)); ++kh) {
+            const u32 g = (S == LOGE) ? gbase : gbase + ((u32)kh << PHI);
 #pragma unroll
             for (int hi = 0; hi < (1 << (S - 1 - s)); ++hi) {
                 if (PLO + s == LAST_BIT) {
@@ -325,24 +345,25 @@ __device__ __forceinline__ void inv_stages(typename A::V (&x)[16], u32 gbase, co
 }
 
 // full radix-16 passes of the inverse transform, field position ascending
-template <int LOGL, int LAST_BIT, int PASS, class A, class Store>
+template <int LOGL, int LOGE, int LAST_BIT, int PASS, class A, class Store>
 __device__ __forceinline__ void inv_full_passes(Store &store, const typename A::TW *__restrict__ tw, u32 goff, const A &ar,
                                                 typename A::V *sm)
 {
-    typedef NttShape<LOGL> Sh;
+    typedef NttShape<LOGL, LOGE> Sh;
+    constexpr int E = 1 << LOGE;
     if constexpr (PASS < Sh::NFULL) {
-        constexpr int P = Sh::REM + 4 * PASS;
-        typedef PassMap<LOGL, 4, P, LOGL> M;
+        constexpr int P = Sh::REM + LOGE * PASS;
+        typedef PassMap<LOGL, LOGE, LOGE, P, LOGL> M;
 #pragma unroll 1
         for (int it = 0; it < Sh::ITER; ++it) {
-            typename A::V x[16];
+            typename A::V x[E];
             const u32 b = M::base(threadIdx.x + it * Sh::THREADS);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) x[k] = ar.inv_fix(sm[swz(b + M::off(k))]);
-            inv_stages<4, P, LOGL, LAST_BIT>(x, goff + b, tw, ar);
+            for (int k = 0; k < E; ++k) x[k] = ar.inv_fix(sm[swz(b + M::off(k))]);
+            inv_stages<LOGE, LOGE, P, LOGL, LAST_BIT>(x, goff + b, tw, ar);
             if constexpr (PASS == Sh::NFULL - 1) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
+                for (int k = 0; k < E; ++k) {
                     if constexpr (LAST_BIT >= 0)
                         store(b + M::off(k), ar.inv_final(x[k]));
                     else
@@ -350,12 +371,12 @@ __device__ __forceinline__ void inv_full_passes(Store &store, const typename A::
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) sm[swz(b + M::off(k))] = x[k];
+                for (int k = 0; k < E; ++k) sm[swz(b + M::off(k))] = x[k];
             }
         }
         if constexpr (PASS != Sh::NFULL - 1) {
             __syncthreads();
-            inv_full_passes<LOGL, LAST_BIT, PASS + 1>(store, tw, goff, ar, sm);
+            inv_full_passes<LOGL, LOGE, LAST_BIT, PASS + 1>(store, tw, goff, ar, sm);
         }
     }
 }
@@ -364,30 +385,31 @@ __device__ __forceinline__ void inv_full_passes(Store &store, const typename A::
 // transform (logN-1) if this CTA performs it (store receives canonical values), else -1
 // (SPLIT, integer policies only: values leave in [0,2q) (BIG) or [0, 2q*2^LOGL) (!BIG);
 // ntt_inv_final_kernel finishes).  load(i) must return canonical residues.
-template <int LOGL, int LAST_BIT, class A, class Load, class Store>
+template <int LOGL, int LOGE, int LAST_BIT, class A, class Load, class Store>
 __device__ __forceinline__ void ntt_inv_cta(Load load, Store store, const typename A::TW *__restrict__ tw, u32 goff, const A &ar,
                                             u64 *smraw)
 {
-    typedef NttShape<LOGL> Sh;
+    typedef NttShape<LOGL, LOGE> Sh;
+    constexpr int E = 1 << LOGE;
     typename A::V *sm = reinterpret_cast<typename A::V *>(smraw);
     constexpr int S = Sh::REM;
-    constexpr int PHI = (S == 4) ? LOGL : LOGL - (4 - S);
-    typedef PassMap<LOGL, S, 0, PHI> M;
+    constexpr int PHI = (S == LOGE) ? LOGL : LOGL - (LOGE - S);
+    typedef PassMap<LOGL, LOGE, S, 0, PHI> M;
 #pragma unroll 1
     for (int it = 0; it < Sh::ITER; ++it) {
-        typename A::V x[16];
+        typename A::V x[E];
         const u32 b = M::base(threadIdx.x + it * Sh::THREADS);
-        u64 raw[16];
+        u64 raw[E];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) raw[k] = load(b + M::off(k));
+        for (int k = 0; k < E; ++k) raw[k] = load(b + M::off(k));
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = ar.from_load(raw[k]);
-        inv_stages<S, 0, PHI, LAST_BIT>(x, goff + b, tw, ar);
+        for (int k = 0; k < E; ++k) x[k] = ar.from_load(raw[k]);
+        inv_stages<LOGE, S, 0, PHI, LAST_BIT>(x, goff + b, tw, ar);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) sm[swz(b + M::off(k))] = x[k];
+        for (int k = 0; k < E; ++k) sm[swz(b + M::off(k))] = x[k];
     }
     __syncthreads();
-    inv_full_passes<LOGL, LAST_BIT, 0>(store, tw, goff, ar, sm);
+    inv_full_passes<LOGL, LOGE, LAST_BIT, 0>(store, tw, goff, ar, sm);
 }
 
 }  // namespace hegpu
