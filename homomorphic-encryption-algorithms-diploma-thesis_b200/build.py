@@ -24,8 +24,36 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+HOST = os.path.join(HERE, "host")
+HOST_SRC = ["ckks_encoder.cpp", "he_operators.cpp", "he_linalg.cpp", "he_fft.cpp"]
+HOST_LIB = os.path.join(HERE, "libhe_host.so")
+HOST_TEST = os.path.join(HERE, "he_host_test")
+
+
+def build_host(force: bool = False) -> str:
+    """C++ host mirror of the reference's interface (he_operators / he_linalg / he_fft / he_util)
+    over the C ABI, plus the test driver binary."""
+    deps = [os.path.join(HOST, f) for f in os.listdir(HOST)] + [LIB]
+    if not force and os.path.exists(HOST_LIB) and os.path.exists(HOST_TEST):
+        t = min(os.path.getmtime(HOST_LIB), os.path.getmtime(HOST_TEST))
+        if all(os.path.getmtime(d) <= t for d in deps):
+            return HOST_LIB
+    cxx = os.environ.get("CXX", "/usr/bin/g++")
+    inc = ["-I", os.path.join(HERE, "..", "include"), "-I", HOST]
+    common = [cxx, "-std=c++20", "-O2", "-fPIC", "-Wall"] + inc
+    link = ["-L", HERE, "-lhegpu", "-Wl,-rpath,$ORIGIN"]
+    for cmd in (common + ["-shared", "-o", HOST_LIB] + [os.path.join(HOST, f) for f in HOST_SRC] + link,
+                common + ["-o", HOST_TEST, os.path.join(HOST, "he_host_test.cpp"), "-L", HERE, "-lhe_host", "-lhegpu", "-Wl,-rpath,$ORIGIN"]):
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout)
+            raise RuntimeError("g++ failed building the host mirror")
+    return HOST_LIB
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
+        build_host()
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
@@ -35,6 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("nvcc failed building libhegpu.so")
+    build_host(force=True)
     return LIB
 
 
