@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
             "hegpu_ntt_forward_host": [vp, vp, u32, u32, u32],
             "hegpu_ntt_inverse_host": [vp, vp, u32, u32, u32],
             "hegpu_matvec_bsgs": [vp, vp, vp, vp, u32, u32, i32],
+            "hegpu_matvec_bsgs_range": [vp, vp, vp, vp, u32, u32, u32, i32],
             "hegpu_bmatmul": [vp, vp, vp, vp, u32, u32, i32],
             "hegpu_matmul_elemwise": [vp, vp, vp, vp, u32, u32, u32, i32, i32],
             "hegpu_bfft_stage": [vp, vp, vp, i32, i32],
@@ -280,9 +281,13 @@ class Context:
         _ck(lib().hegpu_apply_galois(self._h, out._h, a._h, elt))
 
     # ---- composites
-    def matvec_bsgs(self, out, a, diags, n1: int, n2: int, rescale: bool = True, hoist: bool = False):
-        """hoist=True selects HEGPU_MATVEC_HOIST (hoisted baby steps + one mod-down for the giant steps)."""
-        _ck(lib().hegpu_matvec_bsgs(self._h, out._h, a._h, diags._h, n1, n2, (1 if rescale else 0) | (2 if hoist else 0)))
+    def matvec_bsgs(self, out, a, diags, n1: int, n2: int, rescale: bool = True, hoist: bool = False, lazy: bool | None = None,
+                    g_first: int = 0):
+        """hoist: HEGPU_MATVEC_HOIST (hoisted baby steps); lazy: HEGPU_MATVEC_LAZY (one mod-down for all giant
+        steps; defaults to `hoist`); g_first: first global giant step of a diagonal-sharded call."""
+        lazy = hoist if lazy is None else lazy
+        flags = (1 if rescale else 0) | (2 if hoist else 0) | (4 if lazy else 0)
+        _ck(lib().hegpu_matvec_bsgs_range(self._h, out._h, a._h, diags._h, n1, n2, g_first, flags))
 
     def bmatmul(self, out, this_cts, other_cts, n: int, p: int, case_b: bool):
         _ck(lib().hegpu_bmatmul(self._h, out._h, this_cts._h, other_cts._h, n, p, int(case_b)))

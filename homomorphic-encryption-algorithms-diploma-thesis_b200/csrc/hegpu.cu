@@ -1396,7 +1396,16 @@ static void launch_bsgs_inner(hegpu_ctx *c, const BsgsParams &P, size_t)
 extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, uint32_t n1,
                                  uint32_t n2, int flags)
 {
-    const bool rescale = (flags & HEGPU_MATVEC_RESCALE) != 0, fast = (flags & HEGPU_MATVEC_HOIST) != 0;
+    return hegpu_matvec_bsgs_range(c, out, in, diags, n1, n2, 0, flags);
+}
+
+extern "C" int hegpu_matvec_bsgs_range(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, uint32_t n1,
+                                       uint32_t n2, uint32_t g_first, int flags)
+{
+    const bool rescale = (flags & HEGPU_MATVEC_RESCALE) != 0, hoist = (flags & HEGPU_MATVEC_HOIST) != 0,
+               lazy = (flags & HEGPU_MATVEC_LAZY) != 0;
+    // giant step g' of this call is global giant step g_first + g'; only global step 0 is unrotated
+    const u32 first_rot = g_first == 0 ? 1u : 0u;
     if (!c || !out || !diags) INVALID("null argument");
     TRY(check_ct(in));
     if (in->size != 2) INVALID("encrypted size must be 2");
@@ -1414,17 +1423,18 @@ extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in
         TRY(hegpu_galois_elt_from_step(c, (int)k, &belt[k]));
         if (!c->galois_keys.count(belt[k])) INVALID("Galois key not present");
     }
-    for (u32 g = 1; g < n2; ++g) {
-        TRY(hegpu_galois_elt_from_step(c, (int)(g * n1), &gelt[g]));
+    for (u32 g = first_rot; g < n2; ++g) {
+        TRY(hegpu_galois_elt_from_step(c, (int)((g_first + g) * n1), &gelt[g]));
         if (!c->galois_keys.count(gelt[g])) INVALID("Galois key not present");
     }
+    const u32 nrot = n2 - first_rot;  // rotated giant steps
     const size_t n = c->n, ctw = (size_t)2 * L * n;
     // chunk the batch so that the scratch stays within the budget
     auto need = [&](u32 Bc) {
         const u32 gmax = std::min<u32>(MAXG, std::max(n1 - 1, n2 - 1));
         return ks_scratch(c, (size_t)gmax * Bc, L) + align256((size_t)(n1 - 1) * Bc * ctw) + align256((size_t)n2 * Bc * ctw) +
-               align256((size_t)(n2 - 1) * Bc * ctw) + align256((size_t)Bc * ctw) + rescale_scratch(c, Bc, 2) +
-               align256((size_t)Bc * 2 * (L + 1) * n) + align256((size_t)Bc * 2 * n);
+               align256((size_t)std::max<u32>(nrot, 1) * Bc * ctw) + align256((size_t)Bc * ctw) + rescale_scratch(c, Bc, 2) +
+               align256((size_t)Bc * 2 * (L + 1) * n) + align256((size_t)Bc * 2 * n) + align256((size_t)Bc * ctw);
     };
     u32 Bc = B;
     while (Bc > 1 && need(Bc) > c->ws_budget) Bc = (Bc + 1) / 2;
@@ -1434,7 +1444,7 @@ extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in
         ArenaPlan ap{ c };
         u64 *baby = ap.take((size_t)(n1 - 1) * Bc * ctw);
         u64 *inner = ap.take((size_t)n2 * Bc * ctw);
-        u64 *rot = ap.take((size_t)(n2 - 1) * Bc * ctw);
+        u64 *rot = ap.take((size_t)std::max<u32>(nrot, 1) * Bc * ctw);
         u64 *accb = ap.take((size_t)Bc * ctw);
         const size_t ks_off = ap.off;
         auto view_of = [&](u64 *p, size_t batch_off) { return CtView{ p + batch_off * ctw, ctw, (size_t)L * n, n }; };
@@ -1449,7 +1459,7 @@ extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in
                 gs[ng] = KsGroupDesc{ vin, view_of(baby, (size_t)(k - 1) * Bn), c->galois_keys[belt[k]], pm };
             }
             ap.off = ks_off;
-            TRY(keyswitch(c, gs, ng, Bn, L, 1, false, ap, fast));
+            TRY(keyswitch(c, gs, ng, Bn, L, 1, false, ap, hoist));
         }
         // 2. inner sums for every giant step
         {
@@ -1490,20 +1500,26 @@ extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in
             CU(cudaGetLastError());
         }
         CtView dst = rescale ? view_of(accb, 0) : out->view_at(b0);
-        if (!fast || n2 == 1) {
+        // rotated giant step r (r < nrot) is local step first_rot + r: input inner[first_rot + r], output rot[r]
+        if (nrot == 0) {
+            TRY(launch_ew<EW_COPY>(c, dst, view_of(inner, 0), view_of(inner, 0), Bn, 2, L));
+        } else if (!lazy) {
             // 3. giant steps, 4. accumulate
-            for (u32 g0 = 1; g0 < n2; g0 += MAXG) {
+            for (u32 r0 = 0; r0 < nrot; r0 += MAXG) {
                 KsGroupDesc gs[MAXG];
                 u32 ng = 0;
-                for (u32 g = g0; g < n2 && ng < (u32)MAXG; ++g, ++ng) {
+                for (u32 r = r0; r < nrot && ng < (u32)MAXG; ++r, ++ng) {
+                    const u32 g = first_rot + r;
                     const u32 *pm;
                     TRY(get_perm(c, gelt[g], &pm));
-                    gs[ng] = KsGroupDesc{ view_of(inner, (size_t)g * Bn), view_of(rot, (size_t)(g - 1) * Bn), c->galois_keys[gelt[g]], pm };
+                    gs[ng] = KsGroupDesc{ view_of(inner, (size_t)g * Bn), view_of(rot, (size_t)r * Bn), c->galois_keys[gelt[g]], pm };
                 }
                 ap.off = ks_off;
                 TRY(keyswitch(c, gs, ng, Bn, L, 1, false, ap));
             }
-            SumParams S{ view_of(inner, 0), view_of(rot, 0), dst, n2, Bn, 2, L, c->n };
+            // sum of inner[0] (if unrotated) and every rot[r]
+            SumParams S{ first_rot ? view_of(inner, 0) : view_of(rot, 0), first_rot ? view_of(rot, 0) : view_of(rot, (size_t)Bn), dst,
+                         first_rot ? nrot + 1 : nrot, Bn, 2, L, c->n };
             const size_t total = (size_t)Bn * ctw;
             Prof pf(c, PK_ELEMENTWISE, total, total * 8 * (n2 + 1));
             sum_terms_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(S, c->d_mods);
@@ -1512,45 +1528,46 @@ extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in
         } else {
             // 3'. giant steps with ONE mod-down: the key inner products of all giant steps are summed
             // in the extended basis (mod q_0..q_{L-1}, P) and divided by P once.
-            if (n2 - 1 > (u32)MAXG) INVALID("hoisted matvec supports at most 17 giant steps");
+            if (nrot > (u32)MAXG) INVALID("lazy giant steps support at most 16 rotated giant steps per call");
             ap.off = ks_off;
             u64 *accsum = ap.take((size_t)Bn * 2 * (L + 1) * n);
             u64 *tsum = ap.take((size_t)Bn * 2 * n);
+            u64 *basebuf = ap.take((size_t)Bn * ctw);
             KsGroupDesc gs[MAXG];
             BaseSumParams BS{};
-            const u32 ng = n2 - 1;
-            for (u32 g = 1; g < n2; ++g) {
+            for (u32 r = 0; r < nrot; ++r) {
+                const u32 g = first_rot + r;
                 const u32 *pm;
                 TRY(get_perm(c, gelt[g], &pm));
-                gs[g - 1] = KsGroupDesc{ view_of(inner, (size_t)g * Bn), view_of(rot, (size_t)(g - 1) * Bn), c->galois_keys[gelt[g]], pm };
-                BS.perm[g - 1] = pm;
+                gs[r] = KsGroupDesc{ view_of(inner, (size_t)g * Bn), view_of(rot, (size_t)r * Bn), c->galois_keys[gelt[g]], pm };
+                BS.perm[r] = pm;
             }
             KsPlan pl;
-            TRY(ks_setup(c, pl, gs, ng, Bn, L, 1, false, false, ap));
+            TRY(ks_setup(c, pl, gs, nrot, Bn, L, 1, false, false, ap));
             TRY(ks_decompose(c, pl));
             TRY(ks_inner(c, pl));
             {
                 const size_t total = (size_t)Bn * 2 * (L + 1) * n;
-                Prof pf(c, PK_ELEMENTWISE, total, total * 8 * (ng + 1));
-                acc_group_sum_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(pl.P.acc, accsum, ng, Bn, L, c->K, c->n, c->d_mods);
+                Prof pf(c, PK_ELEMENTWISE, total, total * 8 * (nrot + 1));
+                acc_group_sum_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(pl.P.acc, accsum, nrot, Bn, L, c->K, c->n, c->d_mods);
                 c->launches++;
                 CU(cudaGetLastError());
             }
-            {   // base = inner_0 + sum_g pi_g(inner_g.c0)   (written into rot[0..Bn), free by now)
+            {   // base = [inner_0 if unrotated] + sum_r pi_r(inner_r.c0)
                 BS.first = view_of(inner, 0);
-                BS.rest = view_of(inner, (size_t)Bn);
-                BS.out = view_of(rot, 0);
-                BS.groups = ng;
+                BS.has_first = first_rot;
+                BS.rest = view_of(inner, (size_t)first_rot * Bn);
+                BS.out = view_of(basebuf, 0);
+                BS.groups = nrot;
                 BS.B = Bn;
                 BS.L = L;
                 BS.n = c->n;
                 const size_t total = (size_t)Bn * ctw;
-                Prof pf(c, PK_ELEMENTWISE, total, total * 8 * 2 + (size_t)Bn * L * n * 8 * ng);
+                Prof pf(c, PK_ELEMENTWISE, total, total * 8 * 2 + (size_t)Bn * L * n * 8 * nrot);
                 base_gather_sum_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(BS, c->d_mods);
                 c->launches++;
                 CU(cudaGetLastError());
             }
-            KsGroupDesc one{ view_of(rot, 0), dst, nullptr, nullptr };
             KsPlan pm1;
             pm1.P = KsParams{};
             pm1.P.ngroups = 1;
@@ -1560,8 +1577,8 @@ extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in
             pm1.P.n = c->n;
             pm1.P.target_poly = 1;
             pm1.P.has_base1 = 1;
-            pm1.P.in[0] = one.in;
-            pm1.P.out[0] = one.out;
+            pm1.P.in[0] = view_of(basebuf, 0);
+            pm1.P.out[0] = dst;
             pm1.P.acc = accsum;
             pm1.P.t = tsum;
             pm1.E = Bn;

@@ -716,6 +716,7 @@ struct BaseSumParams {
     CtView first, rest, out;
     const u32 *perm[MAXG];
     u32 groups, B, L, n;
+    u32 has_first;  // 0: there is no unrotated term (diagonal-sharded ranks other than the first)
 };
 __global__ void __launch_bounds__(256) base_gather_sum_kernel(const BaseSumParams P, const ModConst *__restrict__ mods)
 {
@@ -728,7 +729,7 @@ __global__ void __launch_bounds__(256) base_gather_sum_kernel(const BaseSumParam
         r /= P.n;
         const u32 l = r % P.L, p = r / P.L;
         const u64 q = mods[l].q;
-        u64 s = P.first.p[b * P.first.sb + p * P.first.sp + l * P.first.sl + x];
+        u64 s = P.has_first ? P.first.p[b * P.first.sb + p * P.first.sp + l * P.first.sl + x] : 0;
         if (p == 0)
             for (u32 g = 0; g < P.groups; ++g)
                 s = addmod(s, P.rest.p[((size_t)g * P.B + b) * P.rest.sb + l * P.rest.sl + __ldg(P.perm[g] + x)], q);

@@ -1,0 +1,70 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed over NCCL/NVLink.
+
+The path shards by independent units.  Two shardings are provided:
+
+* batch sharding -- every rank runs the whole matvec on its own slice of the ciphertext batch;
+  keys and diagonals are replicated, there is no data-path collective (bench.py, "weak");
+* diagonal sharding -- rank r owns a contiguous range of giant steps (its n1*cnt diagonals and
+  the Galois keys of those giant steps), recomputes the shared baby-step rotations locally and
+  produces a partial ciphertext at level L *before* rescale.  The partials are summed with ONE
+  collective (uint64 sum == int64 sum bit for bit; residues < q <= 2^60 so up to 16 terms
+  cannot wrap), reduced back to [0,q) by hegpu_reduce_fixup and rescaled.  Sum-then-reduce
+  equals SEAL's chain of add_inplace bit for bit because modular addition is associative on
+  canonical residues.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def giant_step_range(n2: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous split of the n2 giant steps: (first global giant step, count) of `rank`."""
+    base, extra = divmod(n2, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+class _CudaArray:
+    """__cuda_array_interface__ wrapper so torch can alias library-owned device memory."""
+
+    def __init__(self, ptr: int, nwords: int):
+        self.__cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+
+def as_torch_i64(ct):
+    """Zero-copy int64 view of a CtBatch's whole device buffer [B][size_cap][L_cap][N]."""
+    import torch
+
+    ptr, sb, _, _ = ct.device_view()
+    return torch.as_tensor(_CudaArray(ptr, ct.batch * sb), device=f"cuda:{ct.ctx.device}")
+
+
+def allreduce_sum(ct, world: int, group=None):
+    """In-place sum of a partial ciphertext batch over all ranks, canonical residues on return."""
+    import torch
+    import torch.distributed as dist
+
+    ctx = ct.ctx
+    if world > 16:
+        raise ValueError("at most 16 partial sums of 60-bit residues fit in 64 bits; reduce hierarchically")
+    t = as_torch_i64(ct)
+    with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream, device=ctx.device)):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)  # NCCL over NVLink / NVSwitch
+    ctx.reduce_fixup(ct, world)
+
+
+def matvec_bsgs_diag_sharded(ctx, out, x, diags_local, n1: int, n2_total: int, rank: int, world: int, hoist: bool = True,
+                             partial=None, group=None):
+    """Diagonal-sharded BSGS matvec.  diags_local holds the n1*cnt pre-rotated diagonals of this
+    rank's giant steps (giant_step_range).  Every rank ends with the full result in `out`."""
+    g_first, cnt = giant_step_range(n2_total, world, rank)
+    _, _, L, _ = x.info()
+    part = partial if partial is not None else ctx.ct(x.batch, 2, L)
+    if cnt:
+        ctx.matvec_bsgs(part, x, diags_local, n1, cnt, rescale=False, hoist=hoist, lazy=False, g_first=g_first)
+    else:  # more ranks than giant steps: contribute zero
+        part.upload(np.zeros((x.batch, 2, L, ctx.n), dtype=np.uint64), x.scale * diags_local.scale if diags_local else x.scale)
+    if world > 1:
+        allreduce_sum(part, world, group)
+    ctx.rescale_to_next(out, part)
+    return out

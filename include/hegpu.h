@@ -137,17 +137,25 @@ int hegpu_ntt_inverse_host(hegpu_ctx *ctx, uint64_t *host, uint32_t count, uint3
  * Needs Galois keys for steps 1..n1-1 and g*n1 (g = 1..n2-1).
  * flags: HEGPU_MATVEC_RESCALE  apply the final rescale (clear it when multi-GPU partial sums are
  *                              reduced first);
- *        HEGPU_MATVEC_HOIST    "fast" mode: the baby-step rotations share one digit
- *                              decomposition (INTT + lift once per ciphertext, Galois permutation
- *                              applied to the lifted digits) and the giant-step key-switches share
- *                              one mod-down.  Same function up to key-switch noise, different bits
- *                              than a chain of rotate_vector calls; without the flag the composite
- *                              is exactly the chain of SEAL primitives.
+ *        HEGPU_MATVEC_HOIST    hoisted baby steps: the baby-step rotations share one
+ *                              digit decomposition (INTT + lift once per ciphertext, the Galois
+ *                              permutation is applied to the lifted digits);
+ *        HEGPU_MATVEC_LAZY     the giant-step key-switches are summed in the extended basis and
+ *                              share ONE mod-down.
+ * HOIST / LAZY compute the same function up to key-switch noise but different bits than a
+ * chain of rotate_vector calls; with neither flag the composite is exactly the chain of SEAL
+ * primitives.  hegpu_matvec_bsgs_range is the diagonal-sharded form: this call
+ * owns the n2 giant steps g_first .. g_first+n2-1 (diags holds their n1*n2 diagonals); the
+ * partial results of all ranks are summed (NCCL uint64 sum + hegpu_reduce_fixup) before the
+ * rescale.  Without LAZY the sum over ranks is bit-identical to the single-call result.
  */
 #define HEGPU_MATVEC_RESCALE 1
 #define HEGPU_MATVEC_HOIST 2
+#define HEGPU_MATVEC_LAZY 4
 int hegpu_matvec_bsgs(hegpu_ctx *ctx, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, uint32_t n1,
                       uint32_t n2, int flags);
+int hegpu_matvec_bsgs_range(hegpu_ctx *ctx, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, uint32_t n1,
+                            uint32_t n2, uint32_t g_first, int flags);
 
 /* hegpu_bmatmul_diag: BatchedMatrix::matmul (he_linalg.cpp:943-1006) in the reference's
  * own loop order ("exact" mode): res_i = rescale(relin( sum_j rot(x_{xi(i,j)}, steps(i,j)) * d_j )).

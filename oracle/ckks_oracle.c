@@ -804,21 +804,27 @@ void orc_matvec_bsgs(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1, u32
     }
 }
 
-/* "Fast" BSGS matvec = the restatement of hegpu_matvec_bsgs with HEGPU_MATVEC_HOIST:
+/* General BSGS matvec = the restatement of hegpu_matvec_bsgs_range.  flags: 1 = hoisted baby steps,
+ * 2 = lazy giant steps (one mod-down), 4 = final rescale.  This call owns global giant steps
+ * g_first .. g_first+n2-1 (diagonal sharding); giant_keys[g'] is the key of rotation
+ * (g_first+g')*n1 and is unused for global step 0.
  *  - hoisted baby steps: the digits of c1 are decomposed once (ks_decompose, no permutation) and
  *    every rotation applies its Galois permutation to the lifted digits:
  *       baby_k = mod_down( ks_inner(pi_k(ext), key_k) ) + (pi_k(c0), 0)
  *  - lazy giant steps: acc = sum_g ks_inner(decompose(pi_g(inner_g.c1)), key_g) in the extended
- *    basis, ONE mod-down, base = (inner_0.c0 + sum_g pi_g(inner_g.c0), inner_0.c1).
- * Same function as orc_matvec_bsgs up to key-switch noise; different bits. */
-void orc_matvec_bsgs_fast(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1, u32 n2, const u64 *pts,
-                          const u64 *const *baby_keys, const u64 *const *giant_keys, u64 *out, int threads)
+ *    basis, ONE mod-down, base = ([inner_0.c0] + sum_g pi_g(inner_g.c0), [inner_0.c1]).
+ * Same function as the chain of primitives up to key-switch noise; different bits.
+ * out: [B][2][L-1][N] with rescale, [B][2][L][N] without. */
+void orc_matvec_bsgs_ex(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1, u32 n2, u32 g_first, const u64 *pts,
+                        const u64 *const *baby_keys, const u64 *const *giant_keys, int flags, u64 *out, int threads)
 {
     const u32 n = c->n, K = c->K;
+    const int hoist = flags & 1, lazy = flags & 2, rescale = flags & 4;
     const size_t ctw = (size_t)2 * L * n, ptw = (size_t)L * n, accw = (size_t)2 * (L + 1) * n;
     u32 *tabs = (u32 *)malloc(sizeof(u32) * (size_t)(n1 + n2) * n);
     for (u32 k = 1; k < n1; ++k) orc_galois_table(n, orc_galois_elt_from_step(n, (int)k), tabs + (size_t)k * n);
-    for (u32 g = 1; g < n2; ++g) orc_galois_table(n, orc_galois_elt_from_step(n, (int)(g * n1)), tabs + (size_t)(n1 + g) * n);
+    for (u32 g = 0; g < n2; ++g)
+        if (g_first + g) orc_galois_table(n, orc_galois_elt_from_step(n, (int)((g_first + g) * n1)), tabs + (size_t)(n1 + g) * n);
     (void)threads;
 #ifdef _OPENMP
 #pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(dynamic, 1)
@@ -832,9 +838,14 @@ void orc_matvec_bsgs_fast(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1
         u64 *inner = (u64 *)malloc(sizeof(u64) * ctw * n2);
         u64 *prod = (u64 *)malloc(sizeof(u64) * ctw);
         u64 *base = (u64 *)calloc(ctw, sizeof(u64));
+        u64 *res = (u64 *)calloc(ctw, sizeof(u64));
         memcpy(baby, ct, sizeof(u64) * ctw);
-        ks_decompose(c, L, ct + (size_t)L * n, ext);
+        if (hoist) ks_decompose(c, L, ct + (size_t)L * n, ext);
         for (u32 k = 1; k < n1; ++k) {
+            if (!hoist) {
+                orc_apply_galois(c, L, ct, orc_galois_elt_from_step(n, (int)k), baby_keys[k], baby + (size_t)k * ctw);
+                continue;
+            }
             const u32 *tab = tabs + (size_t)k * n;
             ks_inner(c, L, ext, tab, baby_keys[k], acc);
             memset(base, 0, sizeof(u64) * ctw);
@@ -854,35 +865,52 @@ void orc_matvec_bsgs_fast(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1
                 }
             }
         }
-        u64 *res = (u64 *)malloc(sizeof(u64) * ctw);
-        if (n2 == 1) {
-            memcpy(res, inner, sizeof(u64) * ctw);
-        } else {
-            memcpy(base, inner, sizeof(u64) * ctw); /* inner_0 */
-            for (u32 g = 1; g < n2; ++g) {
-                const u32 *tab = tabs + (size_t)(n1 + g) * n;
-                const u64 *ig = inner + (size_t)g * ctw;
-                /* target = pi_g(c1) */
-                for (u32 i = 0; i < L; ++i)
-                    for (u32 x = 0; x < n; ++x) prod[(size_t)i * n + x] = ig[(size_t)(L + i) * n + tab[x]];
-                ks_decompose(c, L, prod, ext);
-                ks_inner(c, L, ext, NULL, giant_keys[g], acc);
-                for (u32 comp = 0; comp < 2; ++comp)
-                    for (u32 I = 0; I <= L; ++I) {
-                        const u64 m = c->q[I == L ? K - 1 : I];
-                        u64 *s = accsum + ((size_t)comp * (L + 1) + I) * n;
-                        const u64 *a = acc + ((size_t)comp * (L + 1) + I) * n;
-                        for (u32 x = 0; x < n; ++x) s[x] = addmod(s[x], a[x], m);
-                    }
-                for (u32 i = 0; i < L; ++i) {
-                    const u64 q = c->q[i];
-                    for (u32 x = 0; x < n; ++x) base[(size_t)i * n + x] = addmod(base[(size_t)i * n + x], ig[(size_t)i * n + tab[x]], q);
-                }
+        int rotated = 0;
+        memset(base, 0, sizeof(u64) * ctw);
+        for (u32 g = 0; g < n2; ++g) {
+            const u64 *ig = inner + (size_t)g * ctw;
+            if (g_first + g == 0) { /* unrotated term */
+                if (lazy) orc_add(c, L, base, 2, ig, 2, base);
+                else orc_add(c, L, res, 2, ig, 2, res);
+                continue;
             }
-            ks_mod_down_add(c, L, accsum, base, res);
+            if (!lazy) {
+                orc_apply_galois(c, L, ig, orc_galois_elt_from_step(n, (int)((g_first + g) * n1)), giant_keys[g], prod);
+                orc_add(c, L, res, 2, prod, 2, res);
+                continue;
+            }
+            rotated = 1;
+            const u32 *tab = tabs + (size_t)(n1 + g) * n;
+            for (u32 i = 0; i < L; ++i) /* target = pi_g(c1) */
+                for (u32 x = 0; x < n; ++x) prod[(size_t)i * n + x] = ig[(size_t)(L + i) * n + tab[x]];
+            ks_decompose(c, L, prod, ext);
+            ks_inner(c, L, ext, NULL, giant_keys[g], acc);
+            for (u32 comp = 0; comp < 2; ++comp)
+                for (u32 I = 0; I <= L; ++I) {
+                    const u64 m = c->q[I == L ? K - 1 : I];
+                    u64 *s = accsum + ((size_t)comp * (L + 1) + I) * n;
+                    const u64 *a = acc + ((size_t)comp * (L + 1) + I) * n;
+                    for (u32 x = 0; x < n; ++x) s[x] = addmod(s[x], a[x], m);
+                }
+            for (u32 i = 0; i < L; ++i) {
+                const u64 q = c->q[i];
+                for (u32 x = 0; x < n; ++x) base[(size_t)i * n + x] = addmod(base[(size_t)i * n + x], ig[(size_t)i * n + tab[x]], q);
+            }
         }
-        orc_rescale(c, L, res, 2, out + (size_t)b * 2 * (L - 1) * n);
+        if (lazy) {
+            if (rotated) ks_mod_down_add(c, L, accsum, base, res);
+            else memcpy(res, base, sizeof(u64) * ctw);
+        }
+        if (rescale) orc_rescale(c, L, res, 2, out + (size_t)b * 2 * (L - 1) * n);
+        else memcpy(out + (size_t)b * ctw, res, sizeof(u64) * ctw);
         free(ext); free(acc); free(accsum); free(baby); free(inner); free(prod); free(base); free(res);
     }
     free(tabs);
+}
+
+/* the HEGPU_MATVEC_HOIST | HEGPU_MATVEC_LAZY | HEGPU_MATVEC_RESCALE mode */
+void orc_matvec_bsgs_fast(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1, u32 n2, const u64 *pts,
+                          const u64 *const *baby_keys, const u64 *const *giant_keys, u64 *out, int threads)
+{
+    orc_matvec_bsgs_ex(c, L, B, cts, n1, n2, 0, pts, baby_keys, giant_keys, 1 | 2 | 4, out, threads);
 }

@@ -103,7 +103,12 @@ void orc_decrypt(const orc_ctx *ctx, uint32_t L, const uint64_t *ct, uint32_t si
 void orc_matvec_bsgs(const orc_ctx *ctx, uint32_t L, uint32_t B, const uint64_t *cts, uint32_t n1, uint32_t n2,
                      const uint64_t *pts, const uint64_t *const *baby_keys, const uint64_t *const *giant_keys,
                      uint64_t *out, int threads);
-/* restatement of the HEGPU_MATVEC_HOIST mode (hoisted baby steps, one mod-down for all giant steps) */
+/* restatement of hegpu_matvec_bsgs_range: flags 1 = hoisted baby steps, 2 = lazy giant steps (one
+ * mod-down), 4 = final rescale; global giant steps g_first .. g_first+n2-1 */
+void orc_matvec_bsgs_ex(const orc_ctx *ctx, uint32_t L, uint32_t B, const uint64_t *cts, uint32_t n1, uint32_t n2,
+                        uint32_t g_first, const uint64_t *pts, const uint64_t *const *baby_keys,
+                        const uint64_t *const *giant_keys, int flags, uint64_t *out, int threads);
+/* = orc_matvec_bsgs_ex with flags 1|2|4 and g_first 0 */
 void orc_matvec_bsgs_fast(const orc_ctx *ctx, uint32_t L, uint32_t B, const uint64_t *cts, uint32_t n1, uint32_t n2,
                           const uint64_t *pts, const uint64_t *const *baby_keys, const uint64_t *const *giant_keys,
                           uint64_t *out, int threads);

@@ -226,9 +226,10 @@ def test_matvec_bsgs_bit_exact_and_decrypts(hg, n, dim, n1, n2):
     D = ctx.upload_pt(pts, scale)
     out = ctx.ct(B, 2)
     tol = ckks_tol(dim, n, scale)
-    for fast in (False, True):  # exact chain of SEAL primitives / hoisted mode vs its own restatement
-        want = S.o.matvec_bsgs(cts, n1, n2, pts, bk, gkeys, threads=4, fast=fast)
-        ctx.matvec_bsgs(out, X, D, n1, n2, hoist=fast)
+    # exact chain of SEAL primitives, and every fast mode against its own oracle restatement
+    for hoist, lazy in ((False, False), (True, True), (True, False), (False, True)):
+        want = S.o.matvec_bsgs(cts, n1, n2, pts, bk, gkeys, threads=4, hoist=hoist, lazy=lazy)
+        ctx.matvec_bsgs(out, X, D, n1, n2, hoist=hoist, lazy=lazy)
         got = out.download()
         assert np.array_equal(got, want)
         for i in range(B):
