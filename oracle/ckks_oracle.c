@@ -26,6 +26,7 @@ struct orc_ctx {
     u64 q[ORC_MAXK];
     u64 psi[ORC_MAXK];
     u64 ninv[ORC_MAXK], ninv_sh[ORC_MAXK];
+    u64 r0[ORC_MAXK], r1[ORC_MAXK]; /* floor(2^128 / q) low / high word (SEAL Modulus::const_ratio) */
     u64 *w[ORC_MAXK];    /* psi^{brev(i)}            i in [0,N) */
     u64 *wsh[ORC_MAXK];  /* Shoup quotients of w     */
     u64 *iw[ORC_MAXK];   /* (psi^{brev(i)})^{-1}     */
@@ -62,6 +63,32 @@ static inline u32 brev(u32 x, u32 bits)
     for (u32 i = 0; i < bits; ++i) r |= ((x >> i) & 1u) << (bits - 1 - i);
     return r;
 }
+
+/* SEAL util::barrett_reduce_128 / barrett_reduce_64 with the modulus' const_ratio */
+static inline u64 barrett128(u128 z, u64 q, u64 r0, u64 r1)
+{
+    const u64 lo = (u64)z, hi = (u64)(z >> 64);
+    u64 carry = (u64)(((u128)lo * r0) >> 64);
+    u128 t2 = (u128)lo * r1;
+    u64 tmp1 = (u64)t2 + carry;
+    u64 tmp3 = (u64)(t2 >> 64) + (tmp1 < carry);
+    t2 = (u128)hi * r0;
+    u64 s = tmp1 + (u64)t2;
+    carry = (u64)(t2 >> 64) + (s < tmp1);
+    u64 qhat = hi * r1 + tmp3 + carry;
+    u64 r = lo - qhat * q;
+    r -= (r >= q) ? q : 0;
+    r -= (r >= q) ? q : 0;
+    return r;
+}
+static inline u64 barrett64(u64 x, u64 q, u64 r1)
+{
+    u64 h = (u64)(((u128)x * r1) >> 64);
+    u64 r = x - h * q;
+    return r >= q ? r - q : r;
+}
+#define MULMOD(c, i, a, b) barrett128((u128)(a) * (b), (c)->q[i], (c)->r0[i], (c)->r1[i])
+#define REDUCE64(c, i, x) barrett64((x), (c)->q[i], (c)->r1[i])
 
 /* ---------------------------------------------------------------- primes */
 /* deterministic Miller-Rabin for 64-bit (SEAL util::is_prime is probabilistic; same set) */
@@ -172,6 +199,11 @@ orc_ctx *orc_ctx_create(u32 n, const u64 *moduli, u32 K)
             c->iwsh[i][r] = shoup(ip, q);
             p = mulmod(p, c->psi[i], q);
             ip = mulmod(ip, ipsi, q);
+        }
+        {
+            u128 ratio = (~(u128)0) / q; /* == floor(2^128 / q) for odd q */
+            c->r0[i] = (u64)ratio;
+            c->r1[i] = (u64)(ratio >> 64);
         }
         c->ninv[i] = invmod(n % q, q);
         c->ninv_sh[i] = shoup(c->ninv[i], q);
@@ -345,7 +377,8 @@ void orc_multiply_plain(const orc_ctx *c, u32 L, const u64 *ct, u32 size, const 
             const u64 q = c->q[i];
             const u64 *x = POLY(ct, L, n, k, i), *p = pt + (size_t)i * n;
             u64 *o = POLY(out, L, n, k, i);
-            for (u32 j = 0; j < n; ++j) o[j] = mulmod(x[j], p[j], q);
+            for (u32 j = 0; j < n; ++j) o[j] = MULMOD(c, i, x[j], p[j]);
+            (void)q;
         }
 }
 
@@ -363,7 +396,7 @@ void orc_multiply(const orc_ctx *c, u32 L, const u64 *a, u32 sa, const u64 *b, u
                 u64 acc = 0;
                 for (u32 ia = 0; ia < sa; ++ia) {
                     if (k < ia || k - ia >= sb) continue;
-                    acc = addmod(acc, mulmod(POLY(a, L, n, ia, i)[j], POLY(b, L, n, k - ia, i)[j], q), q);
+                    acc = addmod(acc, MULMOD(c, i, POLY(a, L, n, ia, i)[j], POLY(b, L, n, k - ia, i)[j]), q);
                 }
                 o[j] = acc;
             }
@@ -388,11 +421,11 @@ void orc_rescale(const orc_ctx *c, u32 L, const u64 *ct, u32 size, u64 *out)
         for (u32 i = 0; i + 1 < L; ++i) {
             const u64 q = c->q[i];
             const u64 hq = half % q, inv = invmod(ql % q, q);
-            for (u32 j = 0; j < n; ++j) d[j] = submod(t[j] % q, hq, q);
+            for (u32 j = 0; j < n; ++j) d[j] = submod(REDUCE64(c, i, t[j]), hq, q);
             orc_ntt_fwd(c, i, d);
             const u64 *x = POLY(ct, L, n, k, i);
             u64 *o = POLY(out, L - 1, n, k, i);
-            for (u32 j = 0; j < n; ++j) o[j] = mulmod(submod(x[j], d[j], q), inv, q);
+            for (u32 j = 0; j < n; ++j) o[j] = MULMOD(c, i, submod(x[j], d[j], q), inv);
         }
     }
     free(t);
@@ -480,7 +513,8 @@ static void ks_decompose(const orc_ctx *c, u32 L, const u64 *target, u64 *ext)
             if (c->q[J] <= m)
                 memcpy(e, coef, sizeof(u64) * n);
             else
-                for (u32 x = 0; x < n; ++x) e[x] = coef[x] % m;
+                for (u32 x = 0; x < n; ++x) e[x] = REDUCE64(c, ki, coef[x]);
+            (void)m;
             orc_ntt_fwd(c, ki, e);
         }
     }
@@ -512,7 +546,7 @@ static void ks_inner(const orc_ctx *c, u32 L, const u64 *ext, const u32 *tab, co
         for (u32 comp = 0; comp < 2; ++comp) {
             u64 *a = acc + ((size_t)comp * (L + 1) + I) * n;
             const u128 *l = lazy + (size_t)comp * n;
-            for (u32 x = 0; x < n; ++x) a[x] = (u64)(l[x] % m);
+            for (u32 x = 0; x < n; ++x) a[x] = barrett128(l[x], m, c->r0[ki], c->r1[ki]);
         }
     }
     free(lazy);
@@ -533,12 +567,12 @@ static void ks_mod_down_add(const orc_ctx *c, u32 L, u64 *acc, const u64 *base, 
         for (u32 i = 0; i < L; ++i) {
             const u64 q = c->q[i];
             const u64 hq = halfP % q, pinv = invmod(P % q, q);
-            for (u32 x = 0; x < n; ++x) tmp[x] = submod(t[x] % q, hq, q);
+            for (u32 x = 0; x < n; ++x) tmp[x] = submod(REDUCE64(c, i, t[x]), hq, q);
             orc_ntt_fwd(c, i, tmp);
             const u64 *a = acc + ((size_t)comp * (L + 1) + i) * n;
             const u64 *b = POLY(base, L, n, comp, i);
             u64 *o = POLY(out, L, n, comp, i);
-            for (u32 x = 0; x < n; ++x) o[x] = addmod(b[x], mulmod(submod(a[x], tmp[x], q), pinv, q), q);
+            for (u32 x = 0; x < n; ++x) o[x] = addmod(b[x], MULMOD(c, i, submod(a[x], tmp[x], q), pinv), q);
         }
     }
     free(tmp);
