@@ -82,6 +82,9 @@ def lib() -> C.CDLL:
             "hegpu_ct_download": [vp, vp],
             "hegpu_ct_upload_one": [vp, u32, vp],
             "hegpu_ct_download_one": [vp, u32, vp],
+            "hegpu_ct_upload_async": [vp, vp, u32, u32, dbl],
+            "hegpu_ct_download_async": [vp, vp],
+            "hegpu_ct_copy_wait": [vp],
             "hegpu_ct_info": [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(dbl)],
             "hegpu_ct_set_scale": [vp, dbl],
             "hegpu_ct_copy": [vp, vp, vp],
@@ -378,6 +381,16 @@ class CtBatch:
         _ck(lib().hegpu_ct_download(self._h, _hp(out)))
         return out
 
+    def upload_async(self, host_ptr: int, scale: float, size: int, L: int):
+        """asynchronous H2D from pinned host memory (raw address); see hegpu_ct_upload_async"""
+        _ck(lib().hegpu_ct_upload_async(self._h, C.c_void_p(int(host_ptr)), size, L, float(scale)))
+
+    def download_async(self, host_ptr: int):
+        _ck(lib().hegpu_ct_download_async(self._h, C.c_void_p(int(host_ptr))))
+
+    def copy_wait(self):
+        _ck(lib().hegpu_ct_copy_wait(self._h))
+
     def upload_one(self, index: int, host: np.ndarray):
         _ck(lib().hegpu_ct_upload_one(self._h, index, _hp(host)))
 
@@ -417,6 +430,16 @@ class PtSet:
     def upload(self, host: np.ndarray, scale: float):
         assert host.shape[0] == self.count and host.shape[2] == self.ctx.n
         _ck(lib().hegpu_pt_upload(self._h, _hp(host), host.shape[1], float(scale)))
+
+    def upload_async(self, host_ptr: int, scale: float, size: int, L: int):
+        """asynchronous H2D from pinned host memory (raw address); see hegpu_ct_upload_async"""
+        _ck(lib().hegpu_ct_upload_async(self._h, C.c_void_p(int(host_ptr)), size, L, float(scale)))
+
+    def download_async(self, host_ptr: int):
+        _ck(lib().hegpu_ct_download_async(self._h, C.c_void_p(int(host_ptr))))
+
+    def copy_wait(self):
+        _ck(lib().hegpu_ct_copy_wait(self._h))
 
     def upload_one(self, index: int, host: np.ndarray):
         _ck(lib().hegpu_pt_upload_one(self._h, index, _hp(host)))

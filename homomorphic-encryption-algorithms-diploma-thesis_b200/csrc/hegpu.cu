@@ -133,6 +133,8 @@ struct hegpu_ctx {
     u64 prof_launches[PK_COUNT] = {}, prof_units[PK_COUNT] = {}, prof_bytes[PK_COUNT] = {};
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_h2d = nullptr, copy_d2h = nullptr;  // async host<->device copies overlap compute
+    cudaEvent_t ev_fence = nullptr;
     u32 n = 0, logn = 0, K = 0;
     std::vector<u64> q, psi;
     std::vector<int> level_bits;  // total_coeff_modulus_bit_count for L = 1..K
@@ -165,6 +167,8 @@ struct hegpu_ct {
     u32 batch, size_cap, L_cap;
     u32 size, L;
     double scale;
+    cudaEvent_t ev_copy = nullptr;      // last asynchronous host<->device copy of this batch
+    mutable bool copy_pending = false;  // compute that touches the batch must wait for ev_copy first
     CtView view() const { return CtView{ d, (size_t)size_cap * L_cap * ctx->n, (size_t)L_cap * ctx->n, (size_t)ctx->n }; }
     CtView view_at(u32 b0) const
     {
@@ -306,6 +310,9 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     if (const char *e = getenv("HEGPU_LOGE")) c->loge = atoi(e) == 3 ? 3 : 4;
     if (const char *e = getenv("HEGPU_PARK")) c->use_park = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy_h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy_d2h, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_fence, cudaEventDisableTiming));
 
     // bit counts of q_0..q_{L-1} products (SEAL total_coeff_modulus_bit_count)
     {
@@ -420,6 +427,11 @@ extern "C" int hegpu_ctx_destroy(hegpu_ctx *c)
     cudaFree(c->arena.base);
     cudaFree(c->stage);
     cudaFree(c->park);
+    cudaStreamSynchronize(c->copy_h2d);
+    cudaStreamSynchronize(c->copy_d2h);
+    cudaStreamDestroy(c->copy_h2d);
+    cudaStreamDestroy(c->copy_d2h);
+    cudaEventDestroy(c->ev_fence);
     cudaStreamDestroy(c->stream);
     delete c;
     return HEGPU_OK;
@@ -430,6 +442,8 @@ extern "C" int hegpu_sync(hegpu_ctx *c)
     if (!c) INVALID("null context");
     TRY(set_device(c));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy_h2d));
+    CU(cudaStreamSynchronize(c->copy_d2h));
     return HEGPU_OK;
 }
 extern "C" void *hegpu_ctx_stream(hegpu_ctx *c) { return c ? (void *)c->stream : nullptr; }
@@ -581,8 +595,65 @@ extern "C" int hegpu_ct_destroy(hegpu_ct *t)
     if (!t) return HEGPU_OK;
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
+    if (t->ev_copy) {
+        cudaEventSynchronize(t->ev_copy);
+        cudaEventDestroy(t->ev_copy);
+    }
     cudaFree(t->d);
     delete t;
+    return HEGPU_OK;
+}
+
+// compute enqueued after an asynchronous copy of `t` waits for that copy
+static int await_copy(const hegpu_ct *t)
+{
+    if (t && t->copy_pending) {
+        CU(cudaStreamWaitEvent(t->ctx->stream, t->ev_copy, 0));
+        t->copy_pending = false;
+    }
+    return HEGPU_OK;
+}
+// Asynchronous copies run on dedicated copy streams: they start after all compute enqueued
+// before the call and overlap compute enqueued after it.  Needs the packed layout
+// (size == size_cap, L == L_cap) and pinned host memory to be truly asynchronous.
+static int ct_copy_async(hegpu_ct *t, u64 *host, bool upload)
+{
+    hegpu_ctx *c = t->ctx;
+    TRY(set_device(c));
+    if (t->size != t->size_cap || t->L != t->L_cap) INVALID("asynchronous copies need size == size_cap and L == L_cap");
+    if (!t->ev_copy) CU(cudaEventCreateWithFlags(&t->ev_copy, cudaEventDisableTiming));
+    cudaStream_t cs = upload ? c->copy_h2d : c->copy_d2h;
+    if (t->copy_pending) CU(cudaStreamWaitEvent(cs, t->ev_copy, 0));  // order after an earlier async copy
+    CU(cudaEventRecord(c->ev_fence, c->stream));
+    CU(cudaStreamWaitEvent(cs, c->ev_fence, 0));
+    const size_t bytes = (size_t)t->batch * t->size * t->L * c->n * sizeof(u64);
+    if (upload)
+        CU(cudaMemcpyAsync(t->d, host, bytes, cudaMemcpyHostToDevice, cs));
+    else
+        CU(cudaMemcpyAsync(host, t->d, bytes, cudaMemcpyDeviceToHost, cs));
+    CU(cudaEventRecord(t->ev_copy, cs));
+    t->copy_pending = true;
+    return HEGPU_OK;
+}
+extern "C" int hegpu_ct_upload_async(hegpu_ct *t, const uint64_t *host, uint32_t size, uint32_t L, double scale)
+{
+    if (!t || !host) INVALID("null argument");
+    if (size < 2 || size > t->size_cap || L == 0 || L > t->L_cap) INVALID("ciphertext does not fit the batch capacity");
+    t->size = size;
+    t->L = L;
+    t->scale = scale;
+    return ct_copy_async(t, const_cast<u64 *>((const u64 *)host), true);
+}
+extern "C" int hegpu_ct_download_async(hegpu_ct *t, uint64_t *host)
+{
+    if (!t || !host) INVALID("null argument");
+    if (!t->L) INVALID("ciphertext batch is uninitialised");
+    return ct_copy_async(t, (u64 *)host, false);
+}
+extern "C" int hegpu_ct_copy_wait(hegpu_ct *t)
+{
+    if (!t) INVALID("null argument");
+    if (t->ev_copy) CU(cudaEventSynchronize(t->ev_copy));
     return HEGPU_OK;
 }
 
@@ -600,6 +671,7 @@ static int ct_io(hegpu_ct *t, u32 b0, u32 nb, u64 *host, bool upload)
 {
     hegpu_ctx *c = t->ctx;
     TRY(set_device(c));
+    TRY(await_copy(t));
     const size_t words = (size_t)nb * t->size * t->L * c->n;
     const bool packed = (t->size == t->size_cap && t->L == t->L_cap);
     CtView dv = t->view_at(b0);
@@ -692,7 +764,7 @@ static int fits(const hegpu_ct *out, u32 batch, u32 size, u32 L)
 {
     if (out->batch != batch) INVALID("destination batch size mismatch");
     if (size > out->size_cap || L > out->L_cap) INVALID("destination capacity too small");
-    return HEGPU_OK;
+    return await_copy(out);
 }
 
 extern "C" int hegpu_ct_copy(hegpu_ctx *c, hegpu_ct *dst, const hegpu_ct *src)
@@ -956,7 +1028,7 @@ static int check_ct(const hegpu_ct *a)
 {
     if (!a) INVALID("null argument");
     if (!a->L || a->size < 2) INVALID("encrypted is not valid for encryption parameters");
-    return HEGPU_OK;
+    return await_copy(a);
 }
 static int batch_of(const hegpu_ct *a, const hegpu_ct *b, u32 *B, size_t *b_sb)
 {

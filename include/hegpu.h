@@ -74,6 +74,14 @@ int hegpu_ct_upload(hegpu_ct *ct, const uint64_t *host, uint32_t size, uint32_t 
 int hegpu_ct_download(hegpu_ct *ct, uint64_t *host);
 int hegpu_ct_upload_one(hegpu_ct *ct, uint32_t index, const uint64_t *host);
 int hegpu_ct_download_one(hegpu_ct *ct, uint32_t index, uint64_t *host);
+/* Asynchronous variants for pipelining (pinned host memory, packed layout size == size_cap and
+ * L == L_cap): the copy runs on a dedicated copy stream, starts after all compute enqueued
+ * before the call and overlaps compute enqueued after it; later compute that touches the batch
+ * waits for the copy on the device.  hegpu_ct_copy_wait blocks the host until the batch's last
+ * asynchronous copy has finished (call it before reading a downloaded host buffer). */
+int hegpu_ct_upload_async(hegpu_ct *ct, const uint64_t *host, uint32_t size, uint32_t L, double scale);
+int hegpu_ct_download_async(hegpu_ct *ct, uint64_t *host);
+int hegpu_ct_copy_wait(hegpu_ct *ct);
 int hegpu_ct_info(const hegpu_ct *ct, uint32_t *batch, uint32_t *size, uint32_t *L, double *scale);
 int hegpu_ct_set_scale(hegpu_ct *ct, double scale);
 int hegpu_ct_copy(hegpu_ctx *ctx, hegpu_ct *dst, const hegpu_ct *src);

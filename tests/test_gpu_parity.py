@@ -365,3 +365,36 @@ def test_reduce_fixup(hg):
     for k in range(1, 8):
         want = np.stack([S.o.add(want[0], parts[k][0])])
     assert np.array_equal(T.download(), want)
+
+
+def test_async_copies_pipeline(hg):
+    """hegpu_ct_upload_async / download_async: double-buffered pipeline equals the synchronous path."""
+    import torch
+
+    S = setup(8192, (60, 40, 40, 60))
+    ctx = make_ctx(hg, S)
+    rng = np.random.default_rng(71)
+    L, B, sc = 3, 4, 2.0**40
+    ins = [torch.from_numpy(rand_residues(rng, S.moduli[:L], (B, 2), S.n)).pin_memory() for _ in range(4)]
+    outs = [torch.empty((B, 2, L, S.n), dtype=torch.int64).pin_memory() for _ in range(2)]
+    X = [ctx.ct(B, 2, L) for _ in range(2)]
+    O = [ctx.ct(B, 2, L) for _ in range(2)]
+    results = []
+    X[0].upload_async(ins[0].data_ptr(), sc, 2, L)
+    for i in range(4):
+        cur, nxt = i & 1, (i + 1) & 1
+        if i + 1 < 4:
+            X[nxt].upload_async(ins[i + 1].data_ptr(), sc, 2, L)
+        if i >= 2:
+            O[cur].copy_wait()
+            results.append(outs[cur].numpy().view(np.uint64).copy())
+        ctx.add(O[cur], X[cur], X[cur])
+        O[cur].download_async(outs[cur].data_ptr())
+    for k in (0, 1):
+        O[k].copy_wait()
+        results.append(outs[k].numpy().view(np.uint64).copy())
+    ctx.sync()
+    for i in range(4):
+        a = ins[i].numpy()
+        want = np.stack([S.o.add(a[b], a[b]) for b in range(B)])
+        assert np.array_equal(results[i], want), i
