@@ -323,13 +323,15 @@ def run_gpu(args):
         o = orc.Oracle(c["N"], moduli)
         bk = [None] + [gk[ctx.galois_elt_from_step(k)] for k in range(1, c["n1"])]
         gkeys = [None] + [gk[ctx.galois_elt_from_step(g * c["n1"])] for g in range(1, c["n2"])]
-        sample_n = min(B, max(threads, 1) * 2)
+        sample_n = min(B, max(threads, 1) * 4)
         sub = np.ascontiguousarray(cts[:sample_n])
-        t0 = time.perf_counter()
-        ref_out = o.matvec_bsgs(sub, c["n1"], c["n2"], pts, bk, gkeys, threads=threads, fast=True)
-        dt = time.perf_counter() - t0
+        dt = None
+        for _ in range(2):  # best of two passes over the sample (the host is shared and noisy)
+            t0 = time.perf_counter()
+            ref_out = o.matvec_bsgs(sub, c["n1"], c["n2"], pts, bk, gkeys, threads=threads, fast=True)
+            dt = min(dt, time.perf_counter() - t0) if dt else time.perf_counter() - t0
         line["cpu_baseline"] = {"value": sample_n / dt, "unit": "matvecs/s", "cores": threads, "kind": "port",
-                                "sample": f"first {sample_n} of the {B} ciphertexts of one step, same keys/diagonals, {dt:.1f} s wall",
+                                "sample": f"first {sample_n} of the {B} ciphertexts of one step, same keys/diagonals, best of 2 passes, {dt:.2f} s wall each",
                                 "bit_exact_vs_gpu": bool(np.array_equal(ref_out, got[:sample_n]))}
     if rank == 0:
         print(json.dumps(line))

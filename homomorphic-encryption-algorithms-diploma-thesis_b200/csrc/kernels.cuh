@@ -33,11 +33,13 @@ struct MdConst {
 
 // plain transform of `count` limb polynomials [count][N] (measurement API, host tooling)
 struct PlainJob {
+    static constexpr bool PIPE = true;  // software-pipelined first-pass loads (no epilogue operands -> no spills)
     const u64 *src;
     u64 *dst;
     u32 first_mod, n_mods, n;
     __device__ __forceinline__ u32 mod(u32 j) const { return first_mod + j % n_mods; }
-    __device__ __forceinline__ u64 load(u32 j, u32 i, const ModConst &) const { return src[(size_t)j * n + i]; }
+    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const { return src[(size_t)j * n + i]; }
+    __device__ __forceinline__ u64 load_fix(u32, u64 v, const ModConst &) const { return v; }
     __device__ __forceinline__ void store(u32 j, u32 i, u64 v, const ModConst &) const { dst[(size_t)j * n + i] = v; }
     struct Ops {};
     __device__ __forceinline__ Ops fetch(u32, u32, const ModConst &) const { return Ops{}; }
@@ -64,9 +66,10 @@ struct KsParams {
 
 // K7 step 1: c_j = INTT_{q_j}( pi(target)[j] )
 struct KsInttJob {
+    static constexpr bool PIPE = false;
     KsParams P;
     __device__ __forceinline__ u32 mod(u32 j) const { return j % P.L; }
-    __device__ __forceinline__ u64 load(u32 j, u32 i, const ModConst &) const
+    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const
     {
         const u32 e = j / P.L, l = j % P.L, g = e / P.B, b = e % P.B;
         const CtView &v = P.in[g];
@@ -74,11 +77,13 @@ struct KsInttJob {
         const u32 src = pm ? __ldg(pm + i) : i;
         return v.p[b * v.sb + P.target_poly * v.sp + l * v.sl + src];
     }
+    __device__ __forceinline__ u64 load_fix(u32, u64 v, const ModConst &) const { return v; }
     __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &) const { P.coef[(size_t)j * P.n + i] = x; }
 };
 
 // K7 step 2: ext[e][j][i] = NTT_{m_i}( c_j mod m_i ), i != j, i in [0, L]
 struct KsLiftJob {
+    static constexpr bool PIPE = false;
     KsParams P;
     const ModConst *mods;
     __device__ __forceinline__ void split(u32 j, u32 &e, u32 &dj, u32 &di) const
@@ -96,11 +101,16 @@ struct KsLiftJob {
         split(j, e, dj, di);
         return di == P.L ? P.K - 1 : di;
     }
-    __device__ __forceinline__ u64 load(u32 j, u32 i, const ModConst &m) const
+    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const
     {
         u32 e, dj, di;
         split(j, e, dj, di);
-        const u64 v = P.coef[((size_t)e * P.L + dj) * P.n + i];
+        return P.coef[((size_t)e * P.L + dj) * P.n + i];
+    }
+    __device__ __forceinline__ u64 load_fix(u32 j, u64 v, const ModConst &m) const
+    {
+        u32 e, dj, di;
+        split(j, e, dj, di);
         return (mods[dj].q > m.q) ? barrett64(v, m) : v;
     }
     __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &) const
@@ -117,15 +127,14 @@ struct KsLiftJob {
 // INTT of a dropped limb with the rounding offset added: t = (INTT_d(src) + floor(d/2)) mod d.
 // Used by K7 step 4 (d = special prime) and by rescale (d = q_{L-1}).
 struct HalfInttJob {
+    static constexpr bool PIPE = false;
     const u64 *src;  // job j at src + (j / inner) * s_outer + (j % inner) * s_inner
     u64 *dst;        // [jobs][N]
     size_t s_outer, s_inner;
     u32 inner, drop_mod, n;
     __device__ __forceinline__ u32 mod(u32) const { return drop_mod; }
-    __device__ __forceinline__ u64 load(u32 j, u32 i, const ModConst &) const
-    {
-        return src[(j / inner) * s_outer + (j % inner) * s_inner + i];
-    }
+    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const { return src[(j / inner) * s_outer + (j % inner) * s_inner + i]; }
+    __device__ __forceinline__ u64 load_fix(u32, u64 v, const ModConst &) const { return v; }
     __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m) const
     {
         dst[(size_t)j * n + i] = addmod(x, m.q >> 1, m.q);
@@ -134,6 +143,7 @@ struct HalfInttJob {
 
 // K7 step 5: out[c][i] = base_c[i] + (acc[c][i] - NTT_{q_i}((t_c mod q_i) - half)) * P^-1
 struct KsModDownJob {
+    static constexpr bool PIPE = false;
     KsParams P;
     const MdConst *md;  // [K] constants of the dropped modulus (special prime) per target limb
     const ModConst *mods;
@@ -144,13 +154,11 @@ struct KsModDownJob {
         e = j / (2 * P.L);
     }
     __device__ __forceinline__ u32 mod(u32 j) const { return j % P.L; }
-    __device__ __forceinline__ u64 load(u32 j, u32 i, const ModConst &m) const
+    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const { return P.t[(size_t)(j / P.L) * P.n + i]; }
+    __device__ __forceinline__ u64 load_fix(u32 j, u64 v, const ModConst &m) const
     {
-        u32 e, c, l;
-        split(j, e, c, l);
-        u64 v = P.t[((size_t)e * 2 + c) * P.n + i];
         if (mods[P.K - 1].q > m.q) v = barrett64(v, m);
-        return submod(v, md[l].halfmod, m.q);
+        return submod(v, md[j % P.L].halfmod, m.q);
     }
     struct Ops {
         u64 acc, base;
@@ -185,15 +193,16 @@ struct KsModDownJob {
 
 // rescale step 2: out[b][p][i] = (a[b][p][i] - NTT_{q_i}((t mod q_i) - half)) * q_last^-1
 struct RescaleJob {
+    static constexpr bool PIPE = false;
     CtView a, out;
     const u64 *t;       // [B*size][N]
     const MdConst *md;  // constants of dropped modulus q_{L-1} per target limb
     const ModConst *mods;
     u32 size, Lm1, drop_mod, n;  // Lm1 = L-1 target limbs
     __device__ __forceinline__ u32 mod(u32 j) const { return j % Lm1; }
-    __device__ __forceinline__ u64 load(u32 j, u32 i, const ModConst &m) const
+    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const { return t[(size_t)(j / Lm1) * n + i]; }
+    __device__ __forceinline__ u64 load_fix(u32 j, u64 v, const ModConst &m) const
     {
-        u64 v = t[(size_t)(j / Lm1) * n + i];
         if (mods[drop_mod].q > m.q) v = barrett64(v, m);
         return submod(v, md[j % Lm1].halfmod, m.q);
     }
@@ -213,7 +222,53 @@ struct RescaleJob {
 };
 
 // ---------------------------------------------------------------------------------------
-// NTT kernels.  grid = jobs << SPLIT, block = 2^LOGL / 16, dynamic smem = 8 << LOGL.
+// Loaders (protocol in ntt.cuh): raw() = memory only, fix() = arithmetic only.
+// ---------------------------------------------------------------------------------------
+template <class Job>
+struct PlainLoader {  // coefficient boff + i of job jid
+    typedef u64 Raw;
+    static constexpr bool PIPE = Job::PIPE;
+    const Job &job;
+    const ModConst &m;
+    u32 jid, boff;
+    __device__ __forceinline__ Raw raw(u32 i) const { return job.load_raw(jid, boff + i); }
+    __device__ __forceinline__ u64 fix(Raw r, u32) const { return job.load_fix(jid, r, m); }
+};
+struct Pair64 {
+    u64 x, y;
+};
+// first (stride-N/2) forward stage folded into the load: returns the half selected by `h`
+// (SPLIT kernels) and, when park != null, stores the other half there (park kernels, h = 0)
+template <class Job, int LOGL>
+struct FoldLoader {
+    typedef Pair64 Raw;
+    static constexpr bool PIPE = Job::PIPE;
+    const Job &job;
+    const ModConst &m;
+    u32 jid, h;
+    ulonglong2 W;  // twiddle of the first stage
+    u64 *park;
+    __device__ __forceinline__ Raw raw(u32 i) const { return Pair64{ job.load_raw(jid, i), job.load_raw(jid, i + (1u << LOGL)) }; }
+    __device__ __forceinline__ u64 fix(Raw r, u32 i) const
+    {
+        const u64 X = job.load_fix(jid, r.x, m), Y = job.load_fix(jid, r.y, m);
+        const u64 Tm = mul_shoup_lazy(Y, W.x, W.y, m.q);
+        const u64 top = X + Tm, bot = X + (m.q << 1) - Tm;
+        if (park) park[i] = h ? top : bot;
+        return h ? bot : top;
+    }
+};
+template <bool PIPE_>
+struct ParkLoader {  // second half of a park kernel: what FoldLoader parked (same thread wrote it)
+    typedef u64 Raw;
+    static constexpr bool PIPE = PIPE_;
+    const u64 *park;
+    __device__ __forceinline__ Raw raw(u32 i) const { return park[i]; }
+    __device__ __forceinline__ u64 fix(Raw r, u32) const { return r; }
+};
+
+// ---------------------------------------------------------------------------------------
+// NTT kernels.  grid = jobs << SPLIT, dynamic smem = 8 << LOGL.
 // ---------------------------------------------------------------------------------------
 template <int LOGL, int SPLIT, int LOGE, class Job>
 __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::MINB) ntt_fwd_kernel(const Job job, const NttTables T)
@@ -229,7 +284,7 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
     auto store = [&](u32 i, u64 v, const typename Job::Ops &o) { job.store(jid, boff + i, v, m, o); };
     const ulonglong2 nowl = make_ulonglong2(0, 0);
     if constexpr (SPLIT == 0) {
-        auto load = [&](u32 i) -> u64 { return job.load(jid, i, m); };
+        PlainLoader<Job> load{ job, m, jid, 0 };
         if (m.big & 4u)
             ntt_fwd_cta<LOGL, LOGE>(load, fetch, store, T.fwd_d + (size_t)mi * T.n, T.n, ArF64(T.modsd[mi]), sm);
         else if (m.big & 1u)
@@ -238,14 +293,7 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
             ntt_fwd_cta<LOGL, LOGE>(load, fetch, store, tw, T.n, ArI64<false>(m, nowl), sm);
     } else {
         // stage 1 (stride N/2) redone from global memory by both halves
-        const ulonglong2 W = __ldg(tw + 1);
-        const u64 q2 = m.q << 1;
-        auto load = [&](u32 i) -> u64 {
-            const u64 X = job.load(jid, i, m);
-            const u64 Y = job.load(jid, i + (1u << LOGL), m);
-            const u64 Tm = mul_shoup_lazy(Y, W.x, W.y, m.q);
-            return h ? X + q2 - Tm : X + Tm;
-        };
+        FoldLoader<Job, LOGL> load{ job, m, jid, h, __ldg(tw + 1), nullptr };
         if (m.big & 1u)
             ntt_fwd_cta<LOGL, LOGE>(load, fetch, store, tw, T.n + boff, ArI64<true>(m, nowl), sm);
         else
@@ -267,7 +315,7 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
     const ulonglong2 *tw = T.inv + (size_t)mi * T.n;
     const ulonglong2 wl = T.inv_last[mi];
     const u32 boff = h << LOGL;
-    auto load = [&](u32 i) -> u64 { return job.load(jid, boff + i, m); };
+    PlainLoader<Job> load{ job, m, jid, boff };
     if constexpr (SPLIT == 0) {
         auto store = [&](u32 i, u64 v) { job.store(jid, i, v, m); };
         if (m.big & 4u)
@@ -305,16 +353,8 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
     const ulonglong2 *tw = T.fwd + (size_t)mi * T.n;
     constexpr u32 half = 1u << LOGL;
     u64 *pk = park + (size_t)jid * half;
-    const ulonglong2 W = __ldg(tw + 1);
-    const u64 q2 = m.q << 1;
-    auto load0 = [&](u32 i) -> u64 {
-        const u64 X = job.load(jid, i, m);
-        const u64 Y = job.load(jid, i + half, m);
-        const u64 Tm = mul_shoup_lazy(Y, W.x, W.y, m.q);
-        pk[i] = X + q2 - Tm;
-        return X + Tm;
-    };
-    auto load1 = [&](u32 i) -> u64 { return pk[i]; };
+    FoldLoader<Job, LOGL> load0{ job, m, jid, 0, __ldg(tw + 1), pk };
+    ParkLoader<Job::PIPE> load1{ pk };
     auto fetch0 = [&](u32 i) { return job.fetch(jid, i, m); };
     auto fetch1 = [&](u32 i) { return job.fetch(jid, half + i, m); };
     auto store0 = [&](u32 i, u64 v, const typename Job::Ops &o) { job.store(jid, i, v, m, o); };
@@ -344,8 +384,7 @@ __device__ __forceinline__ void inv_park_body(const Job &job, u32 jid, const Mod
                                               typename A::V *pk, u64 *sm)
 {
     constexpr u32 half = 1u << LOGL;
-    auto load0 = [&](u32 i) -> u64 { return job.load(jid, i, m); };
-    auto load1 = [&](u32 i) -> u64 { return job.load(jid, half + i, m); };
+    PlainLoader<Job> load0{ job, m, jid, 0 }, load1{ job, m, jid, half };
     auto store0 = [&](u32 i, typename A::V v) { pk[i] = v; };
     auto store1 = [&](u32 i, typename A::V y) {
         typename A::V x = pk[i];

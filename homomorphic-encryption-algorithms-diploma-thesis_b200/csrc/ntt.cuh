@@ -62,7 +62,10 @@ struct NttShape {
     // <= 64 KiB transforms run 256 threads so that 2 (LOGE = 4, 128 registers) or 3 (LOGE = 3, 64
     // registers) CTAs share an SM and overlap their load / exchange / store phases
     static constexpr int MAXT = (LOGL <= 13) ? 256 : ((LOGE == 4) ? 512 : 1024);
-    static constexpr int MINB = (LOGL <= 13) ? ((LOGE == 4) ? 2 : 3) : 1;
+#ifndef HEGPU_MINB_LOGE3
+#define HEGPU_MINB_LOGE3 3
+#endif
+    static constexpr int MINB = (LOGL <= 13) ? ((LOGE == 4) ? 2 : HEGPU_MINB_LOGE3) : 1;
     static constexpr int THREADS = SETS > MAXT ? MAXT : SETS;
     static constexpr int ITER = SETS / THREADS;
     static constexpr int REM = (LOGL % LOGE == 0) ? LOGE : (LOGL % LOGE);  // stages of the partial pass
@@ -240,8 +243,12 @@ __device__ __forceinline__ void fwd_stages(typename A::V (&x)[1 << LOGE], u32 gb
 }
 
 // full radix-16 passes of the forward transform, field position descending
+// Loader protocol: ld.raw(i) issues the global load(s) of coefficient i and returns them untouched
+// (type Loader::Raw); ld.fix(raw) is the arithmetic that turns them into a value < 3q.  Keeping
+// the two apart lets pass 0 issue the loads of register set it+1 before it computes set it
+// (Loader::PIPE; used where the extra registers do not spill: the plain transforms).
 template <int LOGL, int LOGE, int PASS, class A, class Load>
-__device__ __forceinline__ void fwd_full_passes(Load &load, const typename A::TW *__restrict__ tw, u32 goff, const A &ar,
+__device__ __forceinline__ void fwd_full_passes(Load &ld, const typename A::TW *__restrict__ tw, u32 goff, const A &ar,
                                                 typename A::V *sm)
 {
     typedef NttShape<LOGL, LOGE> Sh;
@@ -249,32 +256,62 @@ __device__ __forceinline__ void fwd_full_passes(Load &load, const typename A::TW
     if constexpr (PASS < Sh::NFULL) {
         constexpr int P = LOGL - LOGE * (PASS + 1);
         typedef PassMap<LOGL, LOGE, LOGE, P, LOGL> M;
+        if constexpr (PASS == 0 && Load::PIPE) {
+            typename Load::Raw raw[2][E];
+            {
+                const u32 b0 = M::base(threadIdx.x);
+#pragma unroll
+                for (int k = 0; k < E; ++k) raw[0][k] = ld.raw(b0 + M::off(k));
+            }
+#pragma unroll
+            for (int it = 0; it < Sh::ITER; ++it) {
+                const u32 b = M::base(threadIdx.x + it * Sh::THREADS);
+                if (it + 1 < Sh::ITER) {  // software pipeline: next set's loads fly during this set's butterflies
+                    const u32 bn = M::base(threadIdx.x + (it + 1) * Sh::THREADS);
+#pragma unroll
+                    for (int k = 0; k < E; ++k) raw[(it + 1) & 1][k] = ld.raw(bn + M::off(k));
+                }
+                typename A::V x[E];
+#pragma unroll
+                for (int k = 0; k < E; ++k) x[k] = ar.from_load(ld.fix(raw[it & 1][k], b + M::off(k)));
+                fwd_stages<LOGE, LOGE, P, LOGL>(x, goff + b, tw, ar);
+#pragma unroll
+                for (int k = 0; k < E; ++k) sm[swz(b + M::off(k))] = x[k];
+            }
+        } else if constexpr (PASS == 0) {
 #pragma unroll 1
-        for (int it = 0; it < Sh::ITER; ++it) {
-            typename A::V x[E];
-            const u32 b = M::base(threadIdx.x + it * Sh::THREADS);
-            if constexpr (PASS == 0) {
-                u64 raw[E];
+            for (int it = 0; it < Sh::ITER; ++it) {
+                const u32 b = M::base(threadIdx.x + it * Sh::THREADS);
+                typename Load::Raw raw[E];
 #pragma unroll
-                for (int k = 0; k < E; ++k) raw[k] = load(b + M::off(k));
+                for (int k = 0; k < E; ++k) raw[k] = ld.raw(b + M::off(k));
+                typename A::V x[E];
 #pragma unroll
-                for (int k = 0; k < E; ++k) x[k] = ar.from_load(raw[k]);
-            } else {
+                for (int k = 0; k < E; ++k) x[k] = ar.from_load(ld.fix(raw[k], b + M::off(k)));
+                fwd_stages<LOGE, LOGE, P, LOGL>(x, goff + b, tw, ar);
+#pragma unroll
+                for (int k = 0; k < E; ++k) sm[swz(b + M::off(k))] = x[k];
+            }
+        } else {
+#pragma unroll 1
+            for (int it = 0; it < Sh::ITER; ++it) {
+                typename A::V x[E];
+                const u32 b = M::base(threadIdx.x + it * Sh::THREADS);
 #pragma unroll
                 for (int k = 0; k < E; ++k) x[k] = ar.fwd_fix(sm[swz(b + M::off(k))]);
-            }
-            fwd_stages<LOGE, LOGE, P, LOGL>(x, goff + b, tw, ar);
-            // in-place: a thread only overwrites the slots it read itself
+                fwd_stages<LOGE, LOGE, P, LOGL>(x, goff + b, tw, ar);
+                // in-place: a thread only overwrites the slots it read itself
 #pragma unroll
-            for (int k = 0; k < E; ++k) sm[swz(b + M::off(k))] = x[k];
+                for (int k = 0; k < E; ++k) sm[swz(b + M::off(k))] = x[k];
+            }
         }
         __syncthreads();
-        fwd_full_passes<LOGL, LOGE, PASS + 1>(load, tw, goff, ar, sm);
+        fwd_full_passes<LOGL, LOGE, PASS + 1>(ld, tw, goff, ar, sm);
     }
 }
 
 // One limb polynomial (or one 2^LOGL block of it), forward.
-//  load(i)  -> coefficient i of this CTA's block, any value < 3q
+//  load: loader object (raw / fix, see above) for coefficient i of this CTA's block
 //  store(i, v) receives the canonical result for position i of the block
 //  goff = N_total + block offset (global index of local coefficient 0)
 //  fetch(i) -> the epilogue operands of position i (issued for the whole register set before the
@@ -395,18 +432,42 @@ __device__ __forceinline__ void ntt_inv_cta(Load load, Store store, const typena
     constexpr int S = Sh::REM;
     constexpr int PHI = (S == LOGE) ? LOGL : LOGL - (LOGE - S);
     typedef PassMap<LOGL, LOGE, S, 0, PHI> M;
+    if constexpr (Load::PIPE) {
+        typename Load::Raw raw[2][E];
+        {
+            const u32 b0 = M::base(threadIdx.x);
+#pragma unroll
+            for (int k = 0; k < E; ++k) raw[0][k] = load.raw(b0 + M::off(k));
+        }
+#pragma unroll
+        for (int it = 0; it < Sh::ITER; ++it) {
+            const u32 b = M::base(threadIdx.x + it * Sh::THREADS);
+            if (it + 1 < Sh::ITER) {
+                const u32 bn = M::base(threadIdx.x + (it + 1) * Sh::THREADS);
+#pragma unroll
+                for (int k = 0; k < E; ++k) raw[(it + 1) & 1][k] = load.raw(bn + M::off(k));
+            }
+            typename A::V x[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) x[k] = ar.from_load(load.fix(raw[it & 1][k], b + M::off(k)));
+            inv_stages<LOGE, S, 0, PHI, LAST_BIT>(x, goff + b, tw, ar);
+#pragma unroll
+            for (int k = 0; k < E; ++k) sm[swz(b + M::off(k))] = x[k];
+        }
+    } else {
 #pragma unroll 1
-    for (int it = 0; it < Sh::ITER; ++it) {
-        typename A::V x[E];
-        const u32 b = M::base(threadIdx.x + it * Sh::THREADS);
-        u64 raw[E];
+        for (int it = 0; it < Sh::ITER; ++it) {
+            const u32 b = M::base(threadIdx.x + it * Sh::THREADS);
+            typename Load::Raw raw[E];
 #pragma unroll
-        for (int k = 0; k < E; ++k) raw[k] = load(b + M::off(k));
+            for (int k = 0; k < E; ++k) raw[k] = load.raw(b + M::off(k));
+            typename A::V x[E];
 #pragma unroll
-        for (int k = 0; k < E; ++k) x[k] = ar.from_load(raw[k]);
-        inv_stages<LOGE, S, 0, PHI, LAST_BIT>(x, goff + b, tw, ar);
+            for (int k = 0; k < E; ++k) x[k] = ar.from_load(load.fix(raw[k], b + M::off(k)));
+            inv_stages<LOGE, S, 0, PHI, LAST_BIT>(x, goff + b, tw, ar);
 #pragma unroll
-        for (int k = 0; k < E; ++k) sm[swz(b + M::off(k))] = x[k];
+            for (int k = 0; k < E; ++k) sm[swz(b + M::off(k))] = x[k];
+        }
     }
     __syncthreads();
     inv_full_passes<LOGL, LOGE, LAST_BIT, 0>(store, tw, goff, ar, sm);
