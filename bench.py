@@ -34,7 +34,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(N=16384, bits=(60, 40, 40, 60), dim=128, n1=16, n2=8, batch=64, scale=2.0**40, L=3)
+CFG = dict(N=16384, bits=(60, 40, 40, 60), dim=128, n1=16, n2=8, batch=64, scale=2.0**40, L=3, mode="hoist")
+MODES = {
+    "hoist": "HEGPU_MATVEC_HOIST|LAZY (hoisted baby steps, one mod-down for the giant steps)",
+    "dh": "HEGPU_MATVEC_DH (double-hoisted: baby rotations stay in the extended basis, one mod-down per giant step)",
+}
 METRIC = "CKKS matvecs/s (N=2^14, 128x128)"
 
 
@@ -102,10 +106,16 @@ def synth_problem(client, seed):
         for b in range(n1):
             d = g * n1 + b
             rows[d] = np.roll(np.tile(M[r, (r + d) % dim], slots // dim), g * n1)
-    pts = client.encode_many(rows, c["scale"], c["L"])
+    pts = client.encode_many(rows, c["scale"], c["L"], special=c["mode"] == "dh")
     plains = client.encode_many(np.tile(V, (1, slots // dim)), c["scale"], c["L"])
     cts = client.encrypt_many(plains)
     return M, V, pts, cts
+
+
+def workload_name():
+    c = CFG
+    return (f"cfg2: CKKS N={c['N']} {{60,40,40,60}}, {c['dim']}x{c['dim']} plaintext diagonals x encrypted vector, "
+            f"BSGS {c['n1']}x{c['n2']}")
 
 
 def rotation_steps():
@@ -129,27 +139,28 @@ def run_reference(args):
     bk = [None] + [gk[orc.galois_elt_from_step(c["N"], k)] for k in range(1, c["n1"])]
     gkeys = [None] + [gk[orc.galois_elt_from_step(c["N"], g * c["n1"])] for g in range(1, c["n2"])]
     mods = moduli[: c["L"]]
-    pts = np.empty((c["dim"], c["L"], c["N"]), dtype=np.uint64)
-    for i, q in enumerate(mods):
+    dh = c["mode"] == "dh"
+    pmods = mods + [moduli[-1]] if dh else mods
+    pts = np.empty((c["dim"], len(pmods), c["N"]), dtype=np.uint64)
+    for i, q in enumerate(pmods):
         pts[:, i, :] = rng.integers(0, q, size=(c["dim"], c["N"]), dtype=np.uint64)
     per_step = threads  # one ciphertext per host thread per step (bounded sample of the 64-batch)
     cts = np.empty((per_step, 2, c["L"], c["N"]), dtype=np.uint64)
     for i, q in enumerate(mods):
         cts[:, :, i, :] = rng.integers(0, q, size=(per_step, 2, c["N"]), dtype=np.uint64)
     for _ in range(args.warmup):
-        o.matvec_bsgs(cts, c["n1"], c["n2"], pts, bk, gkeys, threads=threads, fast=True)
+        o.matvec_bsgs(cts, c["n1"], c["n2"], pts, bk, gkeys, threads=threads, fast=not dh, dh=dh)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        o.matvec_bsgs(cts, c["n1"], c["n2"], pts, bk, gkeys, threads=threads, fast=True)
+        o.matvec_bsgs(cts, c["n1"], c["n2"], pts, bk, gkeys, threads=threads, fast=not dh, dh=dh)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
-    sample = f"{per_step} ciphertexts per step (1 per host thread) of the 64-ciphertext batch, same BSGS 16x8 matvec"
+    sample = f"{per_step} ciphertexts per step (1 per host thread) of the 64-ciphertext batch, same BSGS {c['n1']}x{c['n2']} matvec ({c['mode']})"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "matvecs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "cfg2: CKKS N=16384 {60,40,40,60}, 128x128 plaintext diagonals x encrypted vector, BSGS 16x8",
-                   "batch_per_step": per_step, "note": "CPU port of SEAL 4.1's algorithms (oracle/); real SEAL is not installable here"},
+        "config": {"workload": workload_name(), "batch_per_step": per_step, "mode": MODES[c["mode"]], "note": "CPU port of SEAL 4.1's algorithms (oracle/); real SEAL is not installable here"},
         "cpu_baseline": {"value": value, "unit": "matvecs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "matvecs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -187,13 +198,14 @@ def run_gpu(args):
     M, V, pts, cts = synth_problem(client, seed=0xC0FFEE + 2 + 1000 * rank)
     B = c["batch"]
 
-    D = ctx.upload_pt(pts, c["scale"])
+    dh = c["mode"] == "dh"
+    D = ctx.upload_pt_ext(pts, c["scale"]) if dh else ctx.upload_pt(pts, c["scale"])
     X = ctx.upload_ct(cts, c["scale"], size_cap=2, L_cap=c["L"])
     OUT = ctx.ct(B, 2, c["L"] - 1)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
 
     def step():
-        ctx.matvec_bsgs(OUT, X, D, c["n1"], c["n2"], hoist=True)
+        ctx.matvec_bsgs(OUT, X, D, c["n1"], c["n2"], hoist=not dh, dh=dh)
 
     def barrier():
         if dist is not None:
@@ -254,7 +266,7 @@ def run_gpu(args):
                 XS[nxt].upload_async(h_in[nxt].data_ptr(), c["scale"], 2, c["L"])
             if i >= 2:
                 OS[cur].copy_wait()  # host buffer h_out[cur] of step i-2 is complete (a consumer would read it here)
-            ctx.matvec_bsgs(OS[cur], XS[cur], D, c["n1"], c["n2"], hoist=True)
+            ctx.matvec_bsgs(OS[cur], XS[cur], D, c["n1"], c["n2"], hoist=not dh, dh=dh)
             OS[cur].download_async(h_out[cur].data_ptr())
         for o_ in OS:
             o_.copy_wait()
@@ -302,9 +314,8 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": "matvecs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": "cfg2: CKKS N=16384 {60,40,40,60}, 128x128 plaintext diagonals x encrypted vector, BSGS 16x8",
-                   "batch_per_gpu_per_step": B, "parallelism": f"batch-sharded x{world}, keys and diagonals replicated",
-                   "mode": "HEGPU_MATVEC_HOIST (hoisted baby steps, one mod-down for the 7 giant steps); CPU arm runs the same algorithm",
+        "config": {"workload": workload_name(), "batch_per_gpu_per_step": B, "parallelism": f"batch-sharded x{world}, keys and diagonals replicated",
+                   "mode": MODES[c["mode"]] + "; the CPU arm runs the same algorithm",
                    "l2": "no flush: each step streams ~3.5 GB of key-switch scratch per GPU, far beyond the 126 MB L2",
                    "tolerance": tol, "max_abs_err_vs_numpy": max_err},
         "clocks": clocks,
@@ -328,7 +339,7 @@ def run_gpu(args):
         dt = None
         for _ in range(2):  # best of two passes over the sample (the host is shared and noisy)
             t0 = time.perf_counter()
-            ref_out = o.matvec_bsgs(sub, c["n1"], c["n2"], pts, bk, gkeys, threads=threads, fast=True)
+            ref_out = o.matvec_bsgs(sub, c["n1"], c["n2"], pts, bk, gkeys, threads=threads, fast=not dh, dh=dh)
             dt = min(dt, time.perf_counter() - t0) if dt else time.perf_counter() - t0
         line["cpu_baseline"] = {"value": sample_n / dt, "unit": "matvecs/s", "cores": threads, "kind": "port",
                                 "sample": f"first {sample_n} of the {B} ciphertexts of one step, same keys/diagonals, best of 2 passes, {dt:.2f} s wall each",
@@ -346,7 +357,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hegpu", choices=["hegpu", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default=CFG["mode"], choices=sorted(MODES))
+    ap.add_argument("--n1", type=int, default=None, help="baby steps (n1 * n2 = 128)")
     args = ap.parse_args()
+    CFG["mode"] = args.mode
+    if args.n1:
+        assert CFG["dim"] % args.n1 == 0
+        CFG["n1"], CFG["n2"] = args.n1, CFG["dim"] // args.n1
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -93,6 +93,7 @@ def lib() -> C.CDLL:
             "hegpu_pt_create": [vp, C.POINTER(vp), u32, u32],
             "hegpu_pt_destroy": [vp],
             "hegpu_pt_upload": [vp, vp, u32, dbl],
+            "hegpu_pt_upload_ext": [vp, vp, u32, dbl],
             "hegpu_pt_upload_one": [vp, u32, vp],
             "hegpu_pt_download_one": [vp, u32, vp],
             "hegpu_negate": [vp, vp, vp],
@@ -230,6 +231,16 @@ class Context:
         t.upload(host, scale)
         return t
 
+    def upload_pt_ext(self, host: np.ndarray, scale: float) -> "PtSet":
+        """host [count][L+1][N]: L data limbs + one limb mod the special prime (plaintexts of the
+        double-hoisted matvec, hegpu_pt_upload_ext)."""
+        if host.ndim == 2:
+            host = host[None]
+        host = np.ascontiguousarray(host)
+        t = self.pt(host.shape[0], host.shape[1])
+        t.upload_ext(host, scale)
+        return t
+
     # ---- NTT (measurement / tooling)
     def ntt_forward_host(self, a: np.ndarray, first_mod: int, n_mods: int = 1):
         _ck(lib().hegpu_ntt_forward_host(self._h, _hp(a), a.size // self.n, first_mod, n_mods))
@@ -285,11 +296,12 @@ class Context:
 
     # ---- composites
     def matvec_bsgs(self, out, a, diags, n1: int, n2: int, rescale: bool = True, hoist: bool = False, lazy: bool | None = None,
-                    g_first: int = 0):
+                    g_first: int = 0, dh: bool = False):
         """hoist: HEGPU_MATVEC_HOIST (hoisted baby steps); lazy: HEGPU_MATVEC_LAZY (one mod-down for all giant
-        steps; defaults to `hoist`); g_first: first global giant step of a diagonal-sharded call."""
+        steps; defaults to `hoist`); dh: HEGPU_MATVEC_DH (double-hoisted, diags uploaded with upload_pt_ext);
+        g_first: first global giant step of a diagonal-sharded call."""
         lazy = hoist if lazy is None else lazy
-        flags = (1 if rescale else 0) | (2 if hoist else 0) | (4 if lazy else 0)
+        flags = (1 if rescale else 0) | (2 if hoist else 0) | (4 if lazy else 0) | (8 if dh else 0)
         _ck(lib().hegpu_matvec_bsgs_range(self._h, out._h, a._h, diags._h, n1, n2, g_first, flags))
 
     def bmatmul(self, out, this_cts, other_cts, n: int, p: int, case_b: bool):
@@ -431,15 +443,10 @@ class PtSet:
         assert host.shape[0] == self.count and host.shape[2] == self.ctx.n
         _ck(lib().hegpu_pt_upload(self._h, _hp(host), host.shape[1], float(scale)))
 
-    def upload_async(self, host_ptr: int, scale: float, size: int, L: int):
-        """asynchronous H2D from pinned host memory (raw address); see hegpu_ct_upload_async"""
-        _ck(lib().hegpu_ct_upload_async(self._h, C.c_void_p(int(host_ptr)), size, L, float(scale)))
-
-    def download_async(self, host_ptr: int):
-        _ck(lib().hegpu_ct_download_async(self._h, C.c_void_p(int(host_ptr))))
-
-    def copy_wait(self):
-        _ck(lib().hegpu_ct_copy_wait(self._h))
+    def upload_ext(self, host: np.ndarray, scale: float):
+        """host [count][L+1][N], limb L = residues mod the special prime"""
+        assert host.shape[0] == self.count and host.shape[2] == self.ctx.n
+        _ck(lib().hegpu_pt_upload_ext(self._h, _hp(host), host.shape[1] - 1, float(scale)))
 
     def upload_one(self, index: int, host: np.ndarray):
         _ck(lib().hegpu_pt_upload_one(self._h, index, _hp(host)))

@@ -193,8 +193,10 @@ class Client:
         self.ctx.ntt_forward_host(out, 0, L)
         return out
 
-    def encode_many(self, rows, scale: float, L: int) -> np.ndarray:
-        """rows: [count][<=slots] -> [count][L][N]; one batched NTT on the GPU"""
+    def encode_many(self, rows, scale: float, L: int, special: bool = False) -> np.ndarray:
+        """rows: [count][<=slots] -> [count][L][N]; one batched NTT on the GPU.  special=True appends a
+        limb mod the special prime ([count][L+1][N], the plaintexts of HEGPU_MATVEC_DH: an encode at the
+        key level restricted to the limbs q_0..q_{L-1}, P)."""
         rows = np.asarray(rows, dtype=np.complex128)
         cnt = rows.shape[0]
         v = np.zeros((cnt, self.n), dtype=np.complex128)
@@ -207,6 +209,10 @@ class Client:
         for i in range(L):
             out[:, i, :] = np.mod(coeff, np.int64(self.moduli[i])).astype(np.uint64)
         self.ctx.ntt_forward_host(out, 0, L)
+        if special:
+            sp = np.ascontiguousarray(np.mod(coeff, np.int64(self.moduli[self.K - 1])).astype(np.uint64))
+            self.ctx.ntt_forward_host(sp, self.K - 1, 1)
+            out = np.ascontiguousarray(np.concatenate([out, sp[:, None, :]], axis=1))
         return out
 
     def decode(self, plain_ntt: np.ndarray, scale: float) -> np.ndarray:

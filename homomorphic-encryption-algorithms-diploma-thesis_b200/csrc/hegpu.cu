@@ -185,6 +185,7 @@ struct hegpu_pt {
     double scale;
     u64 *d_mont = nullptr;  // lazily built copy in Montgomery form (matvec diagonals)
     bool mont_valid = false;
+    bool ext = false;       // limb L holds the residues mod the special prime (hegpu_pt_upload_ext)
     size_t stride() const { return (size_t)L_cap * ctx->n; }
 };
 
@@ -365,7 +366,7 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
             m.qinv_neg = (u64)0 - inv;
             m.rmod = (u64)((((u128)1) << 64) % q);
             m.rmod_sh = h_shoup(m.rmod, q);
-            m.pad2 = 0;
+            m.pmont = (i + 1 < K) ? h_mulmod(c->q[K - 1] % q, m.rmod, q) : 0;
         }
         const u64 wl = h_mulmod(inv[(size_t)i * n + 1].x, m.ninv, q);
         inv_last[i] = make_ulonglong2(wl, h_shoup(wl, q));
@@ -823,7 +824,8 @@ static int pt_montgomery(hegpu_pt *t, const u64 **out)
     if (!t->d_mont) CU(cudaMalloc(&t->d_mont, (size_t)t->count * t->L_cap * c->n * sizeof(u64)));
     if (!t->mont_valid) {
         const size_t rows = (size_t)t->count * t->L_cap;
-        to_montgomery_kernel<<<ew_grid(c, rows * c->n), 256, 0, c->stream>>>(t->d, t->d_mont, rows, t->L_cap, c->n, c->n, c->n, c->d_mods);
+        to_montgomery_kernel<<<ew_grid(c, rows * c->n), 256, 0, c->stream>>>(t->d, t->d_mont, rows, t->L_cap, c->n, c->n, c->n, c->d_mods,
+                                                                             t->ext ? t->L : ~0u, c->K);
         c->launches++;
         CU(cudaGetLastError());
         t->mont_valid = true;
@@ -836,7 +838,7 @@ static int pt_io(hegpu_pt *t, u32 i0, u32 cnt, u64 *host, bool upload)
     hegpu_ctx *c = t->ctx;
     TRY(set_device(c));
     if (upload) t->mont_valid = false;
-    const size_t row = (size_t)t->L * c->n * sizeof(u64);
+    const size_t row = (size_t)(t->L + (t->ext ? 1 : 0)) * c->n * sizeof(u64);
     u64 *d = t->d + i0 * t->stride();
     if (upload)
         CU(cudaMemcpy2DAsync(d, t->stride() * sizeof(u64), host, row, row, cnt, cudaMemcpyHostToDevice, c->stream));
@@ -852,6 +854,16 @@ extern "C" int hegpu_pt_upload(hegpu_pt *t, const uint64_t *host, uint32_t L, do
     if (L == 0 || L > t->L_cap) INVALID("plaintext does not fit the set capacity");
     t->L = L;
     t->scale = scale;
+    t->ext = false;
+    return pt_io(t, 0, t->count, const_cast<u64 *>((const u64 *)host), true);
+}
+extern "C" int hegpu_pt_upload_ext(hegpu_pt *t, const uint64_t *host, uint32_t L, double scale)
+{
+    if (!t || !host) INVALID("null argument");
+    if (L == 0 || L + 1 > t->L_cap || L + 1 > t->ctx->K) INVALID("plaintext does not fit the set capacity");
+    t->L = L;
+    t->scale = scale;
+    t->ext = true;
     return pt_io(t, 0, t->count, const_cast<u64 *>((const u64 *)host), true);
 }
 extern "C" int hegpu_pt_upload_one(hegpu_pt *t, uint32_t index, const uint64_t *host)
@@ -1459,10 +1471,220 @@ extern "C" int hegpu_reduce_fixup(hegpu_ctx *c, hegpu_ct *t, uint32_t terms)
 
 // ------------------------------------------------------------------------- composites
 template <int N1>
-static void launch_bsgs_inner(hegpu_ctx *c, const BsgsParams &P, size_t)
+static void launch_bsgs_inner(hegpu_ctx *c, const BsgsParams &P)
 {
     dim3 grid(P.n / 32, P.L, (P.n2 + BSGS_GT - 1) / BSGS_GT), block(32, BSGS_GT);
     bsgs_inner_kernel<N1><<<grid, block, 0, c->stream>>>(P, c->d_mods);
+}
+static void launch_bsgs_inner_n1(hegpu_ctx *c, const BsgsParams &P, u32 n1)
+{
+    switch (n1) {
+    case 1: launch_bsgs_inner<1>(c, P); break;
+    case 2: launch_bsgs_inner<2>(c, P); break;
+    case 3: launch_bsgs_inner<3>(c, P); break;
+    case 4: launch_bsgs_inner<4>(c, P); break;
+    case 5: launch_bsgs_inner<5>(c, P); break;
+    case 6: launch_bsgs_inner<6>(c, P); break;
+    case 7: launch_bsgs_inner<7>(c, P); break;
+    case 8: launch_bsgs_inner<8>(c, P); break;
+    case 9: launch_bsgs_inner<9>(c, P); break;
+    case 10: launch_bsgs_inner<10>(c, P); break;
+    case 11: launch_bsgs_inner<11>(c, P); break;
+    case 12: launch_bsgs_inner<12>(c, P); break;
+    case 13: launch_bsgs_inner<13>(c, P); break;
+    case 14: launch_bsgs_inner<14>(c, P); break;
+    case 15: launch_bsgs_inner<15>(c, P); break;
+    case 16: launch_bsgs_inner<16>(c, P); break;
+    case 24: launch_bsgs_inner<24>(c, P); break;
+    default: launch_bsgs_inner<32>(c, P); break;
+    }
+}
+
+// hegpu_matvec_bsgs_range with HEGPU_MATVEC_DH (double-hoisted; oracle: orc_matvec_bsgs_dh)
+static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, u32 n1, u32 n2, u32 g_first,
+                          bool rescale, const std::vector<u32> &belt, const std::vector<u32> &gelt)
+{
+    const u32 L = in->L, B = in->batch, first_rot = g_first == 0 ? 1u : 0u, nrot = n2 - first_rot;
+    const size_t n = c->n, ctw = (size_t)2 * L * n, accw = (size_t)2 * (L + 1) * n;
+    if (nrot > (u32)MAXG) INVALID("double-hoisted matvec supports at most 16 rotated giant steps per call");
+    const u32 nr1 = std::max<u32>(nrot, 1);
+    auto need = [&](u32 Bc) {
+        return align256((size_t)Bc * L * n) + align256((size_t)Bc * L * (L + 1) * n) + align256(inv_scratch_words(c, (size_t)Bc * std::max<u32>(L, 2))) +
+               align256((size_t)n1 * Bc * accw) + align256((size_t)n2 * Bc * accw) + align256((size_t)nr1 * Bc * ctw) +
+               align256((size_t)nr1 * Bc * 2 * n) + align256(inv_scratch_words(c, (size_t)nr1 * Bc * 2)) + align256((size_t)Bc * accw) +
+               align256((size_t)Bc * 2 * n) + 2 * align256((size_t)Bc * ctw) + ks_scratch(c, (size_t)nr1 * Bc, L) + rescale_scratch(c, Bc, 2);
+    };
+    u32 Bc = B;
+    while (Bc > 1 && need(Bc) > c->ws_budget) Bc = (Bc + 1) / 2;
+    TRY(arena_reserve(c, need(Bc)));
+    const u64 *dmont;
+    TRY(pt_montgomery(const_cast<hegpu_pt *>(diags), &dmont));
+    for (u32 b0 = 0; b0 < B; b0 += Bc) {
+        const u32 Bn = std::min(Bc, B - b0);
+        ArenaPlan ap{ c };
+        u64 *coef = ap.take((size_t)Bc * L * n);
+        u64 *ext = ap.take((size_t)Bc * L * (L + 1) * n);
+        u64 *scr0 = ap.take(inv_scratch_words(c, (size_t)Bc * std::max<u32>(L, 2)));
+        u64 *babyq = ap.take((size_t)n1 * Bc * accw);
+        u64 *u = ap.take((size_t)n2 * Bc * accw);
+        u64 *v = ap.take((size_t)nr1 * Bc * ctw);
+        u64 *tu = ap.take((size_t)nr1 * Bc * 2 * n);
+        u64 *scr1 = ap.take(inv_scratch_words(c, (size_t)nr1 * Bc * 2));
+        u64 *accsum = ap.take((size_t)Bc * accw);
+        u64 *tsum = ap.take((size_t)Bc * 2 * n);
+        u64 *basebuf = ap.take((size_t)Bc * ctw);
+        u64 *accb = ap.take((size_t)Bc * ctw);
+        auto view_of = [&](u64 *p, size_t batch_off) { return CtView{ p + batch_off * ctw, ctw, (size_t)L * n, n }; };
+        auto qp_view = [&](u64 *p, size_t batch_off) { return CtView{ p + batch_off * accw, accw, (size_t)(L + 1) * n, n }; };
+        const CtView vin = in->view_at(b0);
+        // 1. one digit decomposition of c1 for every baby step
+        KsPlan pl0;
+        pl0.P = KsParams{};
+        pl0.P.ngroups = 1;
+        pl0.P.B = Bn;
+        pl0.P.L = L;
+        pl0.P.K = c->K;
+        pl0.P.n = c->n;
+        pl0.P.target_poly = 1;
+        pl0.P.hoisted = 1;
+        pl0.P.in[0] = vin;
+        pl0.P.coef = coef;
+        pl0.P.ext = ext;
+        pl0.E = Bn;
+        pl0.scr = scr0;
+        TRY(ks_decompose(c, pl0));
+        // 2. baby step 0 = P * (c0, c1) in the extended basis
+        {
+            const size_t total = (size_t)Bn * accw;
+            Prof pf(c, PK_ELEMENTWISE, total, (size_t)Bn * ctw * 8 + total * 8);
+            scale_by_p_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(vin, babyq, Bn, L, c->n, c->d_mods);
+            c->launches++;
+            CU(cudaGetLastError());
+        }
+        // 3. baby steps k >= 1: key inner products of the permuted digits, + P * pi_k(c0); no mod-down
+        for (u32 k0 = 1; k0 < n1; k0 += MAXG) {
+            KsPlan pk = pl0;
+            u32 ng = 0;
+            for (u32 k = k0; k < n1 && ng < (u32)MAXG; ++k, ++ng) {
+                const u32 *pm;
+                TRY(get_perm(c, belt[k], &pm));
+                pk.P.in[ng] = vin;
+                pk.P.key[ng] = c->galois_keys[belt[k]];
+                pk.P.perm[ng] = pm;
+            }
+            pk.P.ngroups = ng;
+            pk.P.add_pc0 = 1;
+            pk.P.acc = babyq + (size_t)k0 * Bn * accw;
+            pk.E = (size_t)ng * Bn;
+            TRY(ks_inner(c, pk));
+        }
+        // 4. inner sums of every giant step in the extended basis
+        {
+            BsgsParams P{};
+            for (u32 k = 0; k < n1; ++k) P.baby[k] = qp_view(babyq, (size_t)k * Bn);
+            P.inner = qp_view(u, 0);
+            P.diag = dmont;
+            P.diag_si = diags->stride();
+            P.diag_sl = n;
+            P.n1 = n1;
+            P.n2 = n2;
+            P.B = Bn;
+            P.L = L + 1;
+            P.n = c->n;
+            P.special_limb = L;
+            P.K = c->K;
+            const size_t total = (size_t)Bn * accw;
+            Prof pf(c, PK_BSGS_INNER, total, total * 8 * (n1 + n2) + (u64)n1 * n2 * (L + 1) * n * 8);
+            launch_bsgs_inner_n1(c, P, n1);
+            c->launches++;
+            CU(cudaGetLastError());
+        }
+        CtView dst = rescale ? view_of(accb, 0) : out->view_at(b0);
+        KsPlan pf1;  // the final mod-down
+        pf1.P = KsParams{};
+        pf1.P.ngroups = 1;
+        pf1.P.B = Bn;
+        pf1.P.L = L;
+        pf1.P.K = c->K;
+        pf1.P.n = c->n;
+        pf1.P.target_poly = 1;
+        pf1.P.out[0] = dst;
+        pf1.P.t = tsum;
+        pf1.E = Bn;
+        pf1.scr = scr1;
+        if (nrot == 0) {
+            pf1.P.acc = u;  // the single unrotated step
+            pf1.P.no_base0 = 1;
+            pf1.P.in[0] = dst;
+        } else {
+            // 5. (v0, v1)_g = mod_down(u_g) for the rotated giant steps
+            KsPlan pm;
+            pm.P = KsParams{};
+            pm.P.ngroups = nrot;
+            pm.P.B = Bn;
+            pm.P.L = L;
+            pm.P.K = c->K;
+            pm.P.n = c->n;
+            pm.P.target_poly = 1;
+            pm.P.no_base0 = 1;
+            for (u32 r = 0; r < nrot; ++r) {
+                pm.P.in[r] = view_of(v, (size_t)r * Bn);
+                pm.P.out[r] = view_of(v, (size_t)r * Bn);
+            }
+            pm.P.acc = u + (size_t)first_rot * Bn * accw;
+            pm.P.t = tu;
+            pm.E = (size_t)nrot * Bn;
+            pm.scr = scr1;
+            TRY(ks_moddown(c, pm));
+            // 6. giant rotations: key-switch pi_g(v1_g) without mod-down, summed over g (+ u_0)
+            KsGroupDesc gs[MAXG];
+            BaseSumParams BS{};
+            for (u32 r = 0; r < nrot; ++r) {
+                const u32 g = first_rot + r;
+                const u32 *pmr;
+                TRY(get_perm(c, gelt[g], &pmr));
+                gs[r] = KsGroupDesc{ view_of(v, (size_t)r * Bn), view_of(v, (size_t)r * Bn), c->galois_keys[gelt[g]], pmr };
+                BS.perm[r] = pmr;
+            }
+            KsPlan pl;
+            TRY(ks_setup(c, pl, gs, nrot, Bn, L, 1, false, false, ap));
+            TRY(ks_decompose(c, pl));
+            TRY(ks_inner(c, pl));
+            {
+                const size_t total = (size_t)Bn * accw;
+                Prof pf(c, PK_ELEMENTWISE, total, total * 8 * (nrot + 1 + first_rot));
+                acc_group_sum_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(pl.P.acc, first_rot ? u : nullptr, accsum, nrot, Bn, L, c->K,
+                                                                               c->n, c->d_mods);
+                c->launches++;
+                CU(cudaGetLastError());
+            }
+            {   // base = (sum_r pi_r(v0_r), 0)
+                BS.first = view_of(v, 0);
+                BS.has_first = 0;
+                BS.rest = view_of(v, 0);
+                BS.out = view_of(basebuf, 0);
+                BS.groups = nrot;
+                BS.B = Bn;
+                BS.L = L;
+                BS.n = c->n;
+                const size_t total = (size_t)Bn * ctw;
+                Prof pf(c, PK_ELEMENTWISE, total, total * 8 + (size_t)Bn * L * n * 8 * nrot);
+                base_gather_sum_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(BS, c->d_mods);
+                c->launches++;
+                CU(cudaGetLastError());
+            }
+            pf1.P.acc = accsum;
+            pf1.P.has_base1 = 1;
+            pf1.P.in[0] = view_of(basebuf, 0);
+        }
+        TRY(ks_moddown(c, pf1));
+        if (rescale) {
+            ArenaPlan ar{ c };
+            ar.off = ap.off;
+            TRY(rescale_views(c, out->view_at(b0), dst, Bn, 2, L, ar));
+        }
+    }
+    return HEGPU_OK;
 }
 
 extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, uint32_t n1,
@@ -1475,14 +1697,16 @@ extern "C" int hegpu_matvec_bsgs_range(hegpu_ctx *c, hegpu_ct *out, const hegpu_
                                        uint32_t n2, uint32_t g_first, int flags)
 {
     const bool rescale = (flags & HEGPU_MATVEC_RESCALE) != 0, hoist = (flags & HEGPU_MATVEC_HOIST) != 0,
-               lazy = (flags & HEGPU_MATVEC_LAZY) != 0;
+               lazy = (flags & HEGPU_MATVEC_LAZY) != 0, dh = (flags & HEGPU_MATVEC_DH) != 0;
     // giant step g' of this call is global giant step g_first + g'; only global step 0 is unrotated
     const u32 first_rot = g_first == 0 ? 1u : 0u;
     if (!c || !out || !diags) INVALID("null argument");
     TRY(check_ct(in));
     if (in->size != 2) INVALID("encrypted size must be 2");
-    if (n1 == 0 || n2 == 0 || n1 > MAXG) INVALID("baby-step count must be in [1,16]");
+    if (n1 == 0 || n2 == 0 || n1 > (u32)(dh ? MAXB : MAXG)) INVALID("baby-step count must be in [1,16] ([1,32] double-hoisted)");
+    if (dh && !(n1 <= 16 || n1 == 24 || n1 == 32)) INVALID("double-hoisted baby-step count must be <= 16, 24 or 32");
     if (diags->count < n1 * n2 || diags->L != in->L) INVALID("encrypted_ntt and plain_ntt parameter mismatch");
+    if (dh != diags->ext) INVALID("HEGPU_MATVEC_DH needs plaintexts uploaded with hegpu_pt_upload_ext (and only DH takes them)");
     if (out == in) INVALID("matvec output must not alias its input");
     const u32 L = in->L, B = in->batch;
     if (rescale && L < 2) INVALID("end of modulus switching chain reached");
@@ -1498,6 +1722,13 @@ extern "C" int hegpu_matvec_bsgs_range(hegpu_ctx *c, hegpu_ct *out, const hegpu_
     for (u32 g = first_rot; g < n2; ++g) {
         TRY(hegpu_galois_elt_from_step(c, (int)((g_first + g) * n1), &gelt[g]));
         if (!c->galois_keys.count(gelt[g])) INVALID("Galois key not present");
+    }
+    if (dh) {
+        TRY(matvec_bsgs_dh(c, out, in, diags, n1, n2, g_first, rescale, belt, gelt));
+        out->size = 2;
+        out->L = rescale ? L - 1 : L;
+        out->scale = rescale ? ns / (double)c->q[L - 1] : ns;
+        return HEGPU_OK;
     }
     const u32 nrot = n2 - first_rot;  // rotated giant steps
     const size_t n = c->n, ctw = (size_t)2 * L * n;
@@ -1547,27 +1778,12 @@ extern "C" int hegpu_matvec_bsgs_range(hegpu_ctx *c, hegpu_ct *out, const hegpu_
             P.B = Bn;
             P.L = L;
             P.n = c->n;
+            P.special_limb = ~0u;
+            P.K = c->K;
             const size_t total = (size_t)Bn * ctw;
             // rotated ciphertexts read once, inner sums written once, diagonals read once per step
             Prof pf(c, PK_BSGS_INNER, total, total * 8 * (n1 + n2) + (u64)n1 * n2 * L * n * 8);
-            switch (n1) {
-            case 1: launch_bsgs_inner<1>(c, P, total); break;
-            case 2: launch_bsgs_inner<2>(c, P, total); break;
-            case 3: launch_bsgs_inner<3>(c, P, total); break;
-            case 4: launch_bsgs_inner<4>(c, P, total); break;
-            case 5: launch_bsgs_inner<5>(c, P, total); break;
-            case 6: launch_bsgs_inner<6>(c, P, total); break;
-            case 7: launch_bsgs_inner<7>(c, P, total); break;
-            case 8: launch_bsgs_inner<8>(c, P, total); break;
-            case 9: launch_bsgs_inner<9>(c, P, total); break;
-            case 10: launch_bsgs_inner<10>(c, P, total); break;
-            case 11: launch_bsgs_inner<11>(c, P, total); break;
-            case 12: launch_bsgs_inner<12>(c, P, total); break;
-            case 13: launch_bsgs_inner<13>(c, P, total); break;
-            case 14: launch_bsgs_inner<14>(c, P, total); break;
-            case 15: launch_bsgs_inner<15>(c, P, total); break;
-            default: launch_bsgs_inner<16>(c, P, total); break;
-            }
+            launch_bsgs_inner_n1(c, P, n1);
             c->launches++;
             CU(cudaGetLastError());
         }
@@ -1621,7 +1837,7 @@ extern "C" int hegpu_matvec_bsgs_range(hegpu_ctx *c, hegpu_ct *out, const hegpu_
             {
                 const size_t total = (size_t)Bn * 2 * (L + 1) * n;
                 Prof pf(c, PK_ELEMENTWISE, total, total * 8 * (nrot + 1));
-                acc_group_sum_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(pl.P.acc, accsum, nrot, Bn, L, c->K, c->n, c->d_mods);
+                acc_group_sum_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(pl.P.acc, nullptr, accsum, nrot, Bn, L, c->K, c->n, c->d_mods);
                 c->launches++;
                 CU(cudaGetLastError());
             }

@@ -14,6 +14,7 @@
 namespace hegpu {
 
 constexpr int MAXG = 16;  // rotation groups fused into one key-switch launch
+constexpr int MAXB = 32;  // baby steps of one BSGS matvec
 
 // strided view of a ciphertext batch in HBM: word (b, p, l, x) at p + b*sb + p*sp + l*sl + x
 struct CtView {
@@ -54,6 +55,9 @@ struct KsParams {
     u32 has_base1;    // add in[1] to component 1 (relinearise)
     u32 hoisted;      // all groups rotate the same input: INTT + lift run once per ciphertext (no
                       // gather) and the Galois permutation is applied to the lifted digits instead
+    u32 add_pc0;      // double-hoisted baby steps: acc[0][i] += P * pi(c0)[i] (i < L), the rotated
+                      // ciphertext stays in the extended basis scaled by P
+    u32 no_base0;     // mod-down without a base ciphertext for component 0 (double-hoisted inner sums)
     CtView in[MAXG];
     CtView out[MAXG];
     const u64 *key[MAXG];   // [Lmax][2][K][N]
@@ -173,8 +177,10 @@ struct KsModDownJob {
         const CtView &vi = P.in[g];
         o.base = 0;
         if (c == 0) {
-            const u32 *pm = P.perm[g];
-            o.base = vi.p[b * vi.sb + l * vi.sl + (pm ? __ldg(pm + i) : i)];
+            if (!P.no_base0) {
+                const u32 *pm = P.perm[g];
+                o.base = vi.p[b * vi.sb + l * vi.sl + (pm ? __ldg(pm + i) : i)];
+            }
         } else if (P.has_base1) {
             o.base = vi.p[b * vi.sb + vi.sp + l * vi.sl + i];
         }
@@ -501,6 +507,7 @@ __global__ void __launch_bounds__(256) ks_inner_kernel(const KsParams P, const M
                 mac128(h1, l1, d, __ldg(key + (size_t)(2 * j + 1) * kstride));
             }
         }
+        if (P.add_pc0 && i < L) mac128(h0, l0, v.p[b * v.sb + i * v.sl + xs], m.pmont);
         P.acc[((e * 2 + 0) * (L + 1) + i) * n + x] = mont_reduce(h0, l0, m);  // keys are stored as k*2^64 mod m
         P.acc[((e * 2 + 1) * (L + 1) + i) * n + x] = mont_reduce(h1, l1, m);
     }
@@ -623,11 +630,12 @@ __global__ void __launch_bounds__(256) fixup_kernel(const CtView v, u32 B, u32 p
 //   inner[g][b][p][l][x] = sum_{k<n1} baby_k[b][p][l][x] * diag[g*n1+k][l][x]  mod q_l
 // ---------------------------------------------------------------------------------------
 struct BsgsParams {
-    CtView baby[MAXG];  // baby[0] = the input batch
+    CtView baby[MAXB];  // baby[0] = the input batch
     CtView inner;       // batch index = g*B + b
     const u64 *diag;    // [n1*n2][Lcap][N], Montgomery form (d * 2^64 mod q_l)
     size_t diag_si, diag_sl;
     u32 n1, n2, B, L, n;
+    u32 special_limb, K;  // limb index that lives mod the special prime (mods[K-1]); ~0u: none
 };
 
 // block = (32 coefficients) x (BSGS_GT giant steps); grid = (n/32, L, ceil(n2/BSGS_GT)).
@@ -636,7 +644,6 @@ struct BsgsParams {
 // staged in shared memory by cp.async (double buffered) and shared by the BSGS_GT warps, so
 // they are read from HBM exactly once; the diagonals are read exactly once as well.
 constexpr int BSGS_GT = 8;
-constexpr int BSGS_C = 4;
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 {
@@ -650,6 +657,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int N1>
 __global__ void __launch_bounds__(32 * BSGS_GT) bsgs_inner_kernel(const BsgsParams P, const ModConst *__restrict__ mods)
 {
+    constexpr int BSGS_C = N1 > 16 ? 2 : 4;  // staging depth: 2 x C x N1 x 256 B of static shared memory
     __shared__ u64 buf[2][BSGS_C][N1][32];
     __shared__ const u64 *bptr[N1];
     __shared__ size_t bsb[N1], bsp[N1];
@@ -664,7 +672,7 @@ __global__ void __launch_bounds__(32 * BSGS_GT) bsgs_inner_kernel(const BsgsPara
         bsp[tid] = c.sp;
     }
     __syncthreads();
-    const ModConst m = mods[l];
+    const ModConst m = mods[l == P.special_limb ? P.K - 1 : l];
     u64 d[N1];
     if (active) {
         const u64 *dp = P.diag + (size_t)g * N1 * P.diag_si + l * P.diag_sl + x0 + threadIdx.x;
@@ -734,8 +742,9 @@ __global__ void __launch_bounds__(256) sum_terms_kernel(const SumParams P, const
 }
 
 // lazy mod-down over giant steps: accsum[b][c][i] = sum_g acc[g*B+b][c][i] mod m_i  (rows = 2*(L+1))
-__global__ void __launch_bounds__(256) acc_group_sum_kernel(const u64 *__restrict__ acc, u64 *__restrict__ out, u32 groups, u32 B,
-                                                            u32 L, u32 K, u32 n, const ModConst *__restrict__ mods)
+__global__ void __launch_bounds__(256) acc_group_sum_kernel(const u64 *__restrict__ acc, const u64 *__restrict__ init,
+                                                            u64 *__restrict__ out, u32 groups, u32 B, u32 L, u32 K, u32 n,
+                                                            const ModConst *__restrict__ mods)
 {
     const size_t per_b = (size_t)2 * (L + 1) * n;
     const size_t total = (size_t)B * per_b;
@@ -744,7 +753,7 @@ __global__ void __launch_bounds__(256) acc_group_sum_kernel(const u64 *__restric
         const size_t r = idx % per_b;
         const u32 i = (u32)((r / n) % (L + 1));
         const u64 q = mods[i == L ? K - 1 : i].q;
-        u64 s = 0;
+        u64 s = init ? init[idx] : 0;  // init: an unrotated term already in the extended basis
         for (u32 g = 0; g < groups; ++g) s = addmod(s, acc[((size_t)g * B + b) * per_b + r], q);
         out[idx] = s;
     }
@@ -781,14 +790,39 @@ __global__ void __launch_bounds__(256) base_gather_sum_kernel(const BaseSumParam
 // K-1 = special prime; plaintext layout: limb l = modulus l)
 __global__ void __launch_bounds__(256) to_montgomery_kernel(const u64 *__restrict__ src, u64 *__restrict__ dst, size_t rows,
                                                             u32 limbs_per_item, size_t row_stride_src, size_t row_stride_dst, u32 n,
-                                                            const ModConst *__restrict__ mods)
+                                                            const ModConst *__restrict__ mods, u32 special_limb = ~0u, u32 K = 0)
 {
     const size_t total = rows * n;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const size_t r = idx / n;
         const u32 x = (u32)(idx % n);
-        const ModConst m = mods[r % limbs_per_item];
+        const u32 l = (u32)(r % limbs_per_item);
+        const ModConst m = mods[l == special_limb ? K - 1 : l];
         dst[r * row_stride_dst + x] = mul_shoup(src[r * row_stride_src + x], m.rmod, m.rmod_sh, m.q);
+    }
+}
+
+// double-hoisted baby step 0: out[b][c][i] = P * in[b][c][i] mod q_i (i < L), out[b][c][L] = 0;
+// out in the key-switch accumulator layout [B][2][L+1][N]
+__global__ void __launch_bounds__(256) scale_by_p_kernel(const CtView in, u64 *__restrict__ out, u32 B, u32 L, u32 n,
+                                                         const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)2 * (L + 1) * n;
+    const size_t total = (size_t)B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        u32 r = (u32)(idx % per_b);
+        const u32 x = r % n;
+        r /= n;
+        const u32 i = r % (L + 1), c = r / (L + 1);
+        u64 v = 0;
+        if (i < L) {
+            const ModConst m = mods[i];
+            u64 h = 0, lo = 0;
+            mac128(h, lo, in.p[b * in.sb + c * in.sp + i * in.sl + x], m.pmont);
+            v = mont_reduce(h, lo, m);
+        }
+        out[idx] = v;
     }
 }
 

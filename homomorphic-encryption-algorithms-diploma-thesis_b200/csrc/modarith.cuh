@@ -22,7 +22,7 @@ struct ModConst {
     u64 qinv_neg; // -q^-1 mod 2^64 (Montgomery reduction)
     u64 rmod;     // 2^64 mod q, and its Shoup quotient: x -> x*2^64 mod q (Montgomery form)
     u64 rmod_sh;
-    u64 pad2;
+    u64 pmont;    // (special prime P mod q) * 2^64 mod q: x -> x*P mod q through one Montgomery reduction
 };
 
 __device__ __forceinline__ u64 csub(u64 v, u64 c) { return v >= c ? v - c : v; }

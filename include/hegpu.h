@@ -94,6 +94,10 @@ int hegpu_ct_device_view(hegpu_ct *ct, void **dptr, size_t *batch_stride, size_t
 int hegpu_pt_create(hegpu_ctx *ctx, hegpu_pt **pt, uint32_t count, uint32_t L_cap);
 int hegpu_pt_destroy(hegpu_pt *pt);
 int hegpu_pt_upload(hegpu_pt *pt, const uint64_t *host, uint32_t L, double scale); /* [count][L][N] */
+/* extended plaintexts for HEGPU_MATVEC_DH: host [count][L+1][N], limbs 0..L-1 as above and limb L =
+ * the same integer polynomial mod the special prime (NTT form) -- CKKSEncoder::encode at the key
+ * level restricted to the limbs q_0..q_{L-1}, P.  Needs L_cap >= L+1. */
+int hegpu_pt_upload_ext(hegpu_pt *pt, const uint64_t *host, uint32_t L, double scale);
 int hegpu_pt_upload_one(hegpu_pt *pt, uint32_t index, const uint64_t *host);
 int hegpu_pt_download_one(hegpu_pt *pt, uint32_t index, uint64_t *host);
 
@@ -150,7 +154,14 @@ int hegpu_ntt_inverse_host(hegpu_ctx *ctx, uint64_t *host, uint32_t count, uint3
  *                              permutation is applied to the lifted digits);
  *        HEGPU_MATVEC_LAZY     the giant-step key-switches are summed in the extended basis and
  *                              share ONE mod-down.
- * HOIST / LAZY compute the same function up to key-switch noise but different bits than a
+        HEGPU_MATVEC_DH       double-hoisted (Bossuat et al., EUROCRYPT 2021): one digit decomposition
+ *                              for all baby steps, the rotated ciphertexts stay in the extended basis
+ *                              q_0..q_{L-1},P scaled by P (no mod-down per baby step), the inner sums
+ *                              are taken there against plaintexts that carry a limb mod P
+ *                              (hegpu_pt_upload_ext), each rotated giant step costs one mod-down + one
+ *                              key-switch without mod-down, and everything shares ONE final mod-down.
+ *                              n1 <= 32.  Implies HOIST and LAZY.
+ * HOIST / LAZY / DH compute the same function up to key-switch noise but different bits than a
  * chain of rotate_vector calls; with neither flag the composite is exactly the chain of SEAL
  * primitives.  hegpu_matvec_bsgs_range is the diagonal-sharded form: this call
  * owns the n2 giant steps g_first .. g_first+n2-1 (diags holds their n1*n2 diagonals); the
@@ -160,6 +171,7 @@ int hegpu_ntt_inverse_host(hegpu_ctx *ctx, uint64_t *host, uint32_t count, uint3
 #define HEGPU_MATVEC_RESCALE 1
 #define HEGPU_MATVEC_HOIST 2
 #define HEGPU_MATVEC_LAZY 4
+#define HEGPU_MATVEC_DH 8
 int hegpu_matvec_bsgs(hegpu_ctx *ctx, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, uint32_t n1,
                       uint32_t n2, int flags);
 int hegpu_matvec_bsgs_range(hegpu_ctx *ctx, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, uint32_t n1,

@@ -948,3 +948,106 @@ void orc_matvec_bsgs_fast(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1
 {
     orc_matvec_bsgs_ex(c, L, B, cts, n1, n2, 0, pts, baby_keys, giant_keys, 1 | 2 | 4, out, threads);
 }
+
+/* Double-hoisted BSGS matvec = the restatement of hegpu_matvec_bsgs_range with HEGPU_MATVEC_DH
+ * (Bossuat et al., "Efficient bootstrapping for approximate HE with non-sparse keys", EUROCRYPT 2021,
+ * section 5 -- the same composite, built from SEAL's key-switch steps of SURVEY 9.6):
+ *   - the digits of c1 are decomposed once (ks_decompose);
+ *   - baby rotation k stays in the extended basis q_0..q_{L-1}, P, scaled by P:
+ *       b_k = ( ks_inner(pi_k(ext), key_k)[0] + P*pi_k(c0),  ks_inner(...)[1] ),   b_0 = (P*c0, P*c1)
+ *   - inner sums in the extended basis with plaintexts that carry a limb mod P:
+ *       u_g = sum_k ptx[g*n1+k] (.) b_k                                (accumulated lazily, one reduction)
+ *   - rotated giant step g: (v0,v1) = mod_down(u_g); F += ks_inner(decompose(pi_g(v1)), key_g);
+ *     base0 += pi_g(v0);   the unrotated step adds u_g to F directly;
+ *   - ONE final mod-down: res = (base0, 0) + mod_down(F); optional rescale.
+ * Only (n2 - 1) + 1 mod-downs instead of (n1 - 1) + 1.  Same function as the chain of primitives up
+ * to key-switch noise; different bits.  ptsx: [n1*n2][L+1][N], limb L = residues mod the special
+ * prime (NTT form).  flags: 4 = final rescale.  out as orc_matvec_bsgs_ex. */
+void orc_matvec_bsgs_dh(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1, u32 n2, u32 g_first, const u64 *ptsx,
+                        const u64 *const *baby_keys, const u64 *const *giant_keys, int flags, u64 *out, int threads)
+{
+    const u32 n = c->n, K = c->K;
+    const int rescale = flags & 4;
+    const size_t ctw = (size_t)2 * L * n, ptw = (size_t)(L + 1) * n, accw = (size_t)2 * (L + 1) * n;
+    const u64 P = c->q[K - 1];
+    u32 *tabs = (u32 *)malloc(sizeof(u32) * (size_t)(n1 + n2) * n);
+    for (u32 k = 1; k < n1; ++k) orc_galois_table(n, orc_galois_elt_from_step(n, (int)k), tabs + (size_t)k * n);
+    for (u32 g = 0; g < n2; ++g)
+        if (g_first + g) orc_galois_table(n, orc_galois_elt_from_step(n, (int)((g_first + g) * n1)), tabs + (size_t)(n1 + g) * n);
+    (void)threads;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(dynamic, 1)
+#endif
+    for (u32 b = 0; b < B; ++b) {
+        const u64 *ct = cts + (size_t)b * ctw;
+        u64 *ext = (u64 *)malloc(sizeof(u64) * (size_t)L * (L + 1) * n);
+        u64 *baby = (u64 *)malloc(sizeof(u64) * accw * n1); /* b_k, layout [2][L+1][N] */
+        u64 *u = (u64 *)malloc(sizeof(u64) * accw);
+        u64 *acc = (u64 *)malloc(sizeof(u64) * accw);
+        u64 *F = (u64 *)calloc(accw, sizeof(u64));
+        u64 *v = (u64 *)malloc(sizeof(u64) * ctw);
+        u64 *zero = (u64 *)calloc(ctw, sizeof(u64));
+        u64 *base = (u64 *)calloc(ctw, sizeof(u64));
+        u64 *res = (u64 *)malloc(sizeof(u64) * ctw);
+        u64 *tgt = (u64 *)malloc(sizeof(u64) * (size_t)L * n);
+        u128 *lazy = (u128 *)malloc(sizeof(u128) * n);
+        ks_decompose(c, L, ct + (size_t)L * n, ext);
+        for (u32 k = 0; k < n1; ++k) {
+            u64 *bk = baby + (size_t)k * accw;
+            const u32 *tab = k ? tabs + (size_t)k * n : NULL;
+            if (k) ks_inner(c, L, ext, tab, baby_keys[k], bk);
+            else memset(bk, 0, sizeof(u64) * accw);
+            for (u32 comp = 0; comp < (k ? 1u : 2u); ++comp)
+                for (u32 i = 0; i < L; ++i) {
+                    const u64 q = c->q[i], pm = P % q;
+                    const u64 *src = ct + ((size_t)comp * L + i) * n;
+                    u64 *dst = bk + ((size_t)comp * (L + 1) + i) * n;
+                    for (u32 x = 0; x < n; ++x) dst[x] = addmod(dst[x], MULMOD(c, i, src[tab ? tab[x] : x], pm), q);
+                }
+        }
+        int rotated = 0;
+        for (u32 g = 0; g < n2; ++g) {
+            for (u32 comp = 0; comp < 2; ++comp)
+                for (u32 I = 0; I <= L; ++I) {
+                    const u32 ki = (I == L) ? K - 1 : I;
+                    memset(lazy, 0, sizeof(u128) * n);
+                    for (u32 k = 0; k < n1; ++k) {
+                        const u64 *bk = baby + (size_t)k * accw + ((size_t)comp * (L + 1) + I) * n;
+                        const u64 *pt = ptsx + (size_t)(g * n1 + k) * ptw + (size_t)I * n;
+                        for (u32 x = 0; x < n; ++x) lazy[x] += (u128)bk[x] * pt[x];
+                    }
+                    u64 *o = u + ((size_t)comp * (L + 1) + I) * n;
+                    for (u32 x = 0; x < n; ++x) o[x] = barrett128(lazy[x], c->q[ki], c->r0[ki], c->r1[ki]);
+                }
+            const u64 *add = u;
+            if (g_first + g) {
+                rotated = 1;
+                const u32 *tab = tabs + (size_t)(n1 + g) * n;
+                ks_mod_down_add(c, L, u, zero, v); /* destroys u */
+                for (u32 i = 0; i < L; ++i) {
+                    const u64 q = c->q[i];
+                    for (u32 x = 0; x < n; ++x) {
+                        tgt[(size_t)i * n + x] = v[(size_t)(L + i) * n + tab[x]];
+                        base[(size_t)i * n + x] = addmod(base[(size_t)i * n + x], v[(size_t)i * n + tab[x]], q);
+                    }
+                }
+                ks_decompose(c, L, tgt, ext);
+                ks_inner(c, L, ext, NULL, giant_keys[g], acc);
+                add = acc;
+            }
+            for (u32 comp = 0; comp < 2; ++comp)
+                for (u32 I = 0; I <= L; ++I) {
+                    const u64 m = c->q[I == L ? K - 1 : I];
+                    u64 *s = F + ((size_t)comp * (L + 1) + I) * n;
+                    const u64 *a = add + ((size_t)comp * (L + 1) + I) * n;
+                    for (u32 x = 0; x < n; ++x) s[x] = addmod(s[x], a[x], m);
+                }
+        }
+        (void)rotated;
+        ks_mod_down_add(c, L, F, base, res);
+        if (rescale) orc_rescale(c, L, res, 2, out + (size_t)b * 2 * (L - 1) * n);
+        else memcpy(out + (size_t)b * ctw, res, sizeof(u64) * ctw);
+        free(ext); free(baby); free(u); free(acc); free(F); free(v); free(zero); free(base); free(res); free(tgt); free(lazy);
+    }
+    free(tabs);
+}

@@ -112,6 +112,12 @@ void orc_matvec_bsgs_ex(const orc_ctx *ctx, uint32_t L, uint32_t B, const uint64
 void orc_matvec_bsgs_fast(const orc_ctx *ctx, uint32_t L, uint32_t B, const uint64_t *cts, uint32_t n1, uint32_t n2,
                           const uint64_t *pts, const uint64_t *const *baby_keys, const uint64_t *const *giant_keys,
                           uint64_t *out, int threads);
+/* restatement of hegpu_matvec_bsgs_range with HEGPU_MATVEC_DH (double-hoisted BSGS: baby rotations
+ * stay in the extended basis, one mod-down per giant step).  ptsx: [n1*n2][L+1][N], limb L = residues
+ * mod the special prime.  flags: 4 = final rescale. */
+void orc_matvec_bsgs_dh(const orc_ctx *ctx, uint32_t L, uint32_t B, const uint64_t *cts, uint32_t n1, uint32_t n2,
+                        uint32_t g_first, const uint64_t *ptsx, const uint64_t *const *baby_keys,
+                        const uint64_t *const *giant_keys, int flags, uint64_t *out, int threads);
 int orc_max_threads(void);
 
 #ifdef __cplusplus

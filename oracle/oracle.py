@@ -278,20 +278,26 @@ class Oracle:
 
     # ---- composites
     def matvec_bsgs(self, cts, n1: int, n2: int, pts, baby_keys, giant_keys, threads: int = 1, fast: bool = False,
-                    hoist: bool | None = None, lazy: bool | None = None, rescale: bool = True, g_first: int = 0):
+                    hoist: bool | None = None, lazy: bool | None = None, rescale: bool = True, g_first: int = 0,
+                    dh: bool = False):
         """cts [B][2][L][N]; pts [n1*n2][L][N]; baby_keys[k], giant_keys[g'] lists (unused entries may be None).
         fast=True restates HEGPU_MATVEC_HOIST|LAZY; hoist / lazy select them separately; g_first is the first
-        global giant step of a diagonal-sharded call."""
+        global giant step of a diagonal-sharded call.  dh=True restates HEGPU_MATVEC_DH (double-hoisted); pts
+        then carries a limb mod the special prime: [n1*n2][L+1][N]."""
         cts = np.ascontiguousarray(cts)
         pts = np.ascontiguousarray(pts)
         B, _, L, _ = cts.shape
+        assert pts.shape[1] == (L + 1 if dh else L)
         hoist = fast if hoist is None else hoist
         lazy = fast if lazy is None else lazy
         null = C.cast(None, u64p)
         bk = (u64p * n1)(*[null if k is None else _p(k) for k in baby_keys])
         gk = (u64p * n2)(*[null if k is None else _p(k) for k in giant_keys])
         o = self._out(B, 2, L - 1 if rescale else L, self.n)
-        if not hoist and not lazy and rescale and g_first == 0:
+        if dh:
+            lib().orc_matvec_bsgs_dh(self._h, C.c_uint32(L), C.c_uint32(B), _p(cts), C.c_uint32(n1), C.c_uint32(n2),
+                                     C.c_uint32(g_first), _p(pts), bk, gk, C.c_int(4 if rescale else 0), _p(o), C.c_int(threads))
+        elif not hoist and not lazy and rescale and g_first == 0:
             lib().orc_matvec_bsgs(self._h, C.c_uint32(L), C.c_uint32(B), _p(cts), C.c_uint32(n1), C.c_uint32(n2), _p(pts), bk, gk,
                                   _p(o), C.c_int(threads))
         else:

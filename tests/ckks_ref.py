@@ -170,6 +170,99 @@ def rescale_ref(ct, moduli, psis, L):
     return out
 
 
+def galois_table_ntt(n: int, elt: int) -> list[int]:
+    """result[i] = operand[ brev(((elt*(2*brev(i)+1)) >> 1) & (N-1)) ]."""
+    logn = n.bit_length() - 1
+    return [brev(((elt * (2 * brev(i, logn) + 1)) >> 1) & (n - 1), logn) for i in range(n)]
+
+
+def galois_elt_from_step(n: int, step: int) -> int:
+    m = 2 * n
+    if step == 0:
+        return m - 1
+    pos = abs(step)
+    s = (n >> 1) - pos if step < 0 else pos
+    return pow(3, s, m)
+
+
+def _decompose_ref(target, moduli, psis, L):
+    """ext[J][I] = NTT_{m_I}(INTT_{q_J}(target_J) mod m_I); ext[J][J] = target_J."""
+    K = len(moduli)
+    ext = [[None] * (L + 1) for _ in range(L)]
+    for J in range(L):
+        coef = intt_naive(target[J], moduli[J], psis[J])
+        for I in range(L + 1):
+            ki = K - 1 if I == L else I
+            ext[J][I] = list(target[J]) if I == J else ntt_naive([x % moduli[ki] for x in coef], moduli[ki], psis[ki])
+    return ext
+
+
+def _inner_ref(ext, key, moduli, L, tab=None):
+    K = len(moduli)
+    n = len(ext[0][0])
+    acc = [[None] * (L + 1) for _ in range(2)]
+    for I in range(L + 1):
+        ki = K - 1 if I == L else I
+        for c in range(2):
+            acc[c][I] = [sum(ext[J][I][tab[x] if tab else x] * key[J][c][ki][x] for J in range(L)) % moduli[ki] for x in range(n)]
+    return acc
+
+
+def _mod_down_ref(acc, moduli, psis, L):
+    """[2][L+1][N] in the basis q_0..q_{L-1},P -> round(acc / P) as [2][L][N]."""
+    K = len(moduli)
+    P = moduli[K - 1]
+    half = P // 2
+    out = [[None] * L for _ in range(2)]
+    for c in range(2):
+        t = [(x + half) % P for x in intt_naive(acc[c][L], P, psis[K - 1])]
+        for i in range(L):
+            q = moduli[i]
+            d = ntt_naive([(x % q - half % q) % q for x in t], q, psis[i])
+            pinv = pow(P % q, q - 2, q)
+            out[c][i] = [(acc[c][i][x] - d[x]) * pinv % q for x in range(len(t))]
+    return out
+
+
+def matvec_dh_ref(ct, n1, n2, ptsx, baby_keys, giant_keys, moduli, psis, L, rescale=True, g_first=0):
+    """Double-hoisted BSGS matvec (HEGPU_MATVEC_DH) in big integers, written from the description in
+    include/hegpu.h -- not from the C oracle.  ct [2][L][N]; ptsx [n1*n2][L+1][N]; keys as in switch_key_ref."""
+    K = len(moduli)
+    P = moduli[K - 1]
+    n = len(ct[0][0])
+    mods = [moduli[i] for i in range(L)] + [P]
+    ext = _decompose_ref(ct[1], moduli, psis, L)
+    baby = []
+    for k in range(n1):
+        if k == 0:
+            b = [[[ct[c][i][x] * P % mods[i] for x in range(n)] for i in range(L)] + [[0] * n] for c in range(2)]
+        else:
+            tab = galois_table_ntt(n, galois_elt_from_step(n, k))
+            b = _inner_ref(ext, baby_keys[k], moduli, L, tab)
+            for i in range(L):
+                b[0][i] = [(b[0][i][x] + P * ct[0][i][tab[x]]) % mods[i] for x in range(n)]
+        baby.append(b)
+    F = [[[0] * n for _ in range(L + 1)] for _ in range(2)]
+    base0 = [[0] * n for _ in range(L)]
+    for g in range(n2):
+        u = [[[sum(baby[k][c][I][x] * ptsx[g * n1 + k][I][x] for k in range(n1)) % mods[I] for x in range(n)]
+              for I in range(L + 1)] for c in range(2)]
+        if g_first + g:
+            tab = galois_table_ntt(n, galois_elt_from_step(n, (g_first + g) * n1))
+            v = _mod_down_ref(u, moduli, psis, L)
+            tgt = [[v[1][i][tab[x]] for x in range(n)] for i in range(L)]
+            for i in range(L):
+                base0[i] = [(base0[i][x] + v[0][i][tab[x]]) % mods[i] for x in range(n)]
+            u = _inner_ref(_decompose_ref(tgt, moduli, psis, L), giant_keys[g], moduli, L)
+        for c in range(2):
+            for I in range(L + 1):
+                F[c][I] = [(F[c][I][x] + u[c][I][x]) % mods[I] for x in range(n)]
+    res = _mod_down_ref(F, moduli, psis, L)
+    for i in range(L):
+        res[0][i] = [(res[0][i][x] + base0[i][x]) % mods[i] for x in range(n)]
+    return rescale_ref(res, moduli, psis, L) if rescale else res
+
+
 # ---------------------------------------------------------------- CKKS encode / decode (9.8)
 class Encoder:
     """Vector CKKS encoder over ring degree n (slots = n/2). NTTs are delegated to `ntt_fwd(i, a)`
@@ -223,6 +316,18 @@ class Encoder:
             else:
                 r = np.array([x % q for x in c], dtype=np.uint64)
             out[i] = self._fwd(i, r)
+        return out
+
+    def encode_ext(self, values, scale: float, L: int) -> np.ndarray:
+        """[L+1][N]: the L data limbs plus a limb mod the special prime (moduli[-1]) -- the plaintext
+        layout of the double-hoisted matvec (HEGPU_MATVEC_DH), i.e. an encode at the key level
+        restricted to the limbs q_0..q_{L-1}, P."""
+        c = self.coeffs(values, scale)
+        out = np.empty((L + 1, self.n), dtype=np.uint64)
+        out[:L] = self.encode_coeffs(c, L)
+        K = len(self.moduli)
+        P = self.moduli[K - 1]
+        out[L] = self._fwd(K - 1, np.array([x % P for x in c], dtype=np.uint64))
         return out
 
     def encode_scalar(self, value: float, scale: float, L: int) -> np.ndarray:

@@ -243,6 +243,71 @@ def test_matvec_bsgs_bit_exact_and_decrypts(hg, n, dim, n1, n2):
     assert np.array_equal(np.stack([S.o.rescale(part[i]) for i in range(B)]), want)
 
 
+def _diag_plaintexts_ext(S, M, n1, n2, scale, L):
+    dim = M.shape[0]
+    slots = S.n // 2
+    pts = np.empty((dim, L + 1, S.n), dtype=np.uint64)
+    for g in range(n2):
+        for b in range(n1):
+            d = g * n1 + b
+            diag = np.array([M[r, (r + d) % dim] for r in range(dim)])
+            pts[d] = S.enc.encode_ext(np.roll(np.tile(diag, slots // dim), g * n1), scale, L)
+    return pts
+
+
+@pytest.mark.parametrize("n,dim,n1,n2", [(8192, 16, 4, 4), (16384, 32, 8, 4), (8192, 32, 32, 1), (8192, 8, 1, 8), (8192, 48, 24, 2),
+                                         (8192, 64, 32, 2)])
+def test_matvec_bsgs_double_hoisted(hg, n, dim, n1, n2):
+    """HEGPU_MATVEC_DH against its oracle restatement (orc_matvec_bsgs_dh, itself pinned by a big-integer
+    restatement in tests/test_oracle_evaluator.py): bit-exact, decrypts to M @ v, with and without the
+    final rescale, and diagonal-sharded (g_first > 0)."""
+    S = setup(n, (60, 40, 40, 60))
+    ctx = make_ctx(hg, S)
+    rng = np.random.default_rng(22)
+    scale, L, B = 2.0**40, 3, 3
+    M = rng.uniform(-1, 1, (dim, dim))
+    V = rng.uniform(-1, 1, (B, dim))
+    tiles = (S.n // 2) % dim == 0  # otherwise (n1 = 24): random plaintexts, bit-exactness only
+    cts = np.stack([S.encrypt(np.tile(V[i], S.n // 2 // dim) if tiles else V[i], scale, L, seed=i) for i in range(B)])
+    if tiles:
+        ptsx = _diag_plaintexts_ext(S, M, n1, n2, scale, L)
+    else:
+        ptsx = rand_residues(rng, S.moduli[:L] + [S.moduli[-1]], (n1 * n2,), n)
+    bsteps = list(range(1, n1))
+    gsteps = [g * n1 for g in range(1, n2)]
+    gk = S.gk(bsteps + gsteps)
+    ctx.load_galois_keys(gk)
+    bk = [None] + [gk[orc.galois_elt_from_step(n, s)] for s in bsteps]
+    gkeys = [None] + [gk[orc.galois_elt_from_step(n, s)] for s in gsteps]
+    X = ctx.upload_ct(cts, scale)
+    D = ctx.upload_pt_ext(ptsx, scale)
+    out = ctx.ct(B, 2)
+    tol = ckks_tol(dim, n, scale)
+    want = S.o.matvec_bsgs(cts, n1, n2, ptsx, bk, gkeys, threads=4, dh=True)
+    ctx.matvec_bsgs(out, X, D, n1, n2, dh=True)
+    got = out.download()
+    assert np.array_equal(got, want)
+    for i in range(B if tiles else 0):
+        dec = S.decrypt(got[i], out.scale).real[:dim]
+        assert np.max(np.abs(dec - M @ V[i])) < tol
+    ctx.matvec_bsgs(out, X, D, n1, n2, rescale=False, dh=True)
+    assert out.L == L
+    assert np.array_equal(out.download(), S.o.matvec_bsgs(cts, n1, n2, ptsx, bk, gkeys, threads=4, dh=True, rescale=False))
+    if n2 >= 2:  # the giant steps of the second half as their own call (diagonal sharding)
+        g0 = n2 // 2
+        cnt = n2 - g0
+        Dp = ctx.upload_pt_ext(np.ascontiguousarray(ptsx[g0 * n1:]), scale)
+        ctx.matvec_bsgs(out, X, Dp, n1, cnt, rescale=False, dh=True, g_first=g0)
+        wantp = S.o.matvec_bsgs(cts, n1, cnt, ptsx[g0 * n1:], bk, gkeys[g0:], threads=4, dh=True, rescale=False, g_first=g0)
+        assert np.array_equal(out.download(), wantp)
+    # the ordinary plaintext set is rejected in DH mode and vice versa (no silent misuse)
+    Dn = ctx.upload_pt(np.ascontiguousarray(ptsx[:, :L]), scale)
+    with pytest.raises(hg.InvalidArgument):
+        ctx.matvec_bsgs(out, X, Dn, n1, n2, dh=True)
+    with pytest.raises(hg.InvalidArgument):
+        ctx.matvec_bsgs(out, X, D, min(n1, 16), n2, hoist=True)
+
+
 @pytest.mark.parametrize("case_b", [False, True])
 def test_bmatmul_reference_loop_order(hg, case_b):
     """BatchedMatrix::matmul (he_linalg.cpp:943-1006) restated on the oracle in the reference's own

@@ -180,3 +180,67 @@ def test_key_switch_phases_compose_to_switch_key():
     a = o.matvec_bsgs(cts, 1, 2, pts, [None], [None, gk], fast=False)
     b = o.matvec_bsgs(cts, 1, 2, pts, [None], [None, gk], fast=True)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n1,n2,g_split", [(4, 4, None), (8, 2, None), (16, 1, None), (1, 16, None), (4, 4, 2)])
+def test_matvec_bsgs_double_hoisted_decrypts(n1, n2, g_split):
+    """HEGPU_MATVEC_DH restatement (baby rotations kept in the extended basis, plaintexts with a limb
+    mod P, one mod-down per giant step): decrypts to M @ v within the CKKS tolerance, and -- sharded
+    by giant steps without the rescale -- the partial ciphertexts sum to the unsharded one up to the
+    rounding of the separate mod-downs."""
+    n = 8192
+    moduli = orc.coeff_modulus_create(n, [60, 40, 40, 60])
+    o = orc.Oracle(n, moduli)
+    enc = ref.Encoder(n, moduli, o.ntt_fwd, o.ntt_inv)
+    s = o.sample_secret(78)
+    rng = np.random.default_rng(5)
+    dim, L = 16, 3
+    slots = n // 2
+    scale = 2.0**40
+    M = rng.uniform(-1, 1, (dim, dim))
+    v = rng.uniform(-1, 1, dim)
+    ct = o.encrypt_symmetric(9, s, enc.encode(np.tile(v, slots // dim), scale, L))
+    ptsx = np.empty((dim, L + 1, n), dtype=np.uint64)
+    for g in range(n2):
+        for b in range(n1):
+            d = g * n1 + b
+            diag = np.array([M[r, (r + d) % dim] for r in range(dim)])
+            ptsx[d] = enc.encode_ext(np.roll(np.tile(diag, slots // dim), g * n1), scale, L)
+    bk = [None] + [o.gen_galois_key(200 + b, s, orc.galois_elt_from_step(n, b)) for b in range(1, n1)]
+    gkeys = [None] + [o.gen_galois_key(300 + g, s, orc.galois_elt_from_step(n, g * n1)) for g in range(1, n2)]
+    tol = ckks_tol(dim, n, scale)
+    out = o.matvec_bsgs(ct[None], n1, n2, ptsx, bk, gkeys, threads=2, dh=True)
+    got = enc.decode(o.decrypt(out[0], s), scale * scale / moduli[2]).real[:dim]
+    assert np.max(np.abs(got - M @ v)) < tol
+    # the data limbs of the extended plaintexts are the ordinary plaintexts
+    assert np.array_equal(ptsx[0, :L], enc.encode(np.tile(np.array([M[r, r % dim] for r in range(dim)]), slots // dim), scale, L))
+    if g_split:
+        parts = []
+        for g0, cnt in ((0, g_split), (g_split, n2 - g_split)):
+            parts.append(o.matvec_bsgs(ct[None], n1, cnt, ptsx[g0 * n1:(g0 + cnt) * n1], bk, gkeys[g0:g0 + cnt], threads=2,
+                                       dh=True, rescale=False, g_first=g0)[0])
+        summed = o.add(parts[0], parts[1])
+        got2 = enc.decode(o.decrypt(o.rescale(summed), s), scale * scale / moduli[2]).real[:dim]
+        assert np.max(np.abs(got2 - M @ v)) < tol
+
+
+@pytest.mark.parametrize("bits,L,n1,n2,g_first", [([30, 25, 28, 30], 3, 2, 2, 0), ([30, 25, 28, 30], 2, 3, 2, 0),
+                                                    ([20, 30, 25], 2, 2, 3, 1), ([30, 30], 1, 4, 1, 0)])
+def test_matvec_double_hoisted_vs_bigint(bits, L, n1, n2, g_first):
+    """The C restatement of the double-hoisted matvec against an independent big-integer one, bit-exact."""
+    n = 16
+    moduli = orc.coeff_modulus_create(n, bits)
+    K = len(moduli)
+    o = orc.Oracle(n, moduli)
+    psis = [o.psi(i) for i in range(K)]
+    rng = np.random.default_rng(11)
+    ext_mods = moduli[:L] + [moduli[K - 1]]
+    ct = _rand_poly(rng, moduli[:L], (2,), n)
+    ptsx = _rand_poly(rng, ext_mods, (n1 * n2,), n)
+    bk = [None] + [_rand_poly(rng, moduli, (K - 1, 2), n) for _ in range(1, n1)]
+    gkeys = [_rand_poly(rng, moduli, (K - 1, 2), n) for _ in range(n2)]
+    rescale = L >= 2
+    got = o.matvec_bsgs(ct[None], n1, n2, ptsx, bk, gkeys, dh=True, rescale=rescale, g_first=g_first)[0]
+    want = ref.matvec_dh_ref(ct.tolist(), n1, n2, ptsx.tolist(), [None if k is None else k.tolist() for k in bk],
+                             [k.tolist() for k in gkeys], moduli, psis, L, rescale=rescale, g_first=g_first)
+    assert got.tolist() == want
