@@ -114,11 +114,11 @@ struct Arena {  // grow-only device scratch, bump-allocated per API call
 
 enum ProfKind {
     PK_NTT_FWD_PLAIN, PK_NTT_INV_PLAIN, PK_KS_INTT, PK_KS_LIFT_NTT, PK_KS_INNER, PK_HALF_INTT, PK_KS_MODDOWN_NTT,
-    PK_RESCALE_NTT, PK_BSGS_INNER, PK_TENSOR, PK_ELEMENTWISE, PK_COUNT
+    PK_RESCALE_NTT, PK_BSGS_INNER, PK_TENSOR, PK_ELEMENTWISE, PK_DH_INNER, PK_COUNT
 };
 static const char *const kProfNames[PK_COUNT] = { "ntt_fwd_plain", "ntt_inv_plain", "ks_intt", "ks_lift_ntt", "ks_inner",
                                                   "half_intt", "ks_moddown_ntt", "rescale_ntt", "bsgs_inner", "tensor",
-                                                  "elementwise" };
+                                                  "elementwise", "dh_inner" };
 struct ProfRec {
     int kind;
     cudaEvent_t a, b;
@@ -157,6 +157,7 @@ struct hegpu_ctx {
     size_t stage_words = 0;
     u64 launches = 0;
     int sms = 148;
+    int dh_fused = 1;  // double-hoisted matvec: fused baby-step + inner-sum kernel (HEGPU_DH_FUSED=0: unfused kernels)
     int loge = 3;  // NTT register-set size at N = 16384: 3 = radix-8 passes, 256 threads x 80 registers, 3 CTAs per SM (HEGPU_LOGE=4: radix-16, 2 CTAs)
     size_t ws_budget = (size_t)24 << 30;  // scratch budget per composite chunk
 };
@@ -310,6 +311,7 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     c->sms = prop.multiProcessorCount;
     if (const char *e = getenv("HEGPU_LOGE")) c->loge = atoi(e) == 3 ? 3 : 4;
     if (const char *e = getenv("HEGPU_PARK")) c->use_park = atoi(e) != 0;
+    if (const char *e = getenv("HEGPU_DH_FUSED")) c->dh_fused = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_d2h, cudaStreamNonBlocking));
@@ -1500,6 +1502,24 @@ static void launch_bsgs_inner_n1(hegpu_ctx *c, const BsgsParams &P, u32 n1)
     }
 }
 
+static u32 dh_n2_pad(u32 n2) { return n2 <= 1 ? 1 : n2 <= 2 ? 2 : n2 <= 4 ? 4 : 8; }
+template <int LT, int N2>
+static int launch_dh_inner(hegpu_ctx *c, const DhInnerParams &P)
+{
+    const size_t smem = dh_inner_smem(P.n1, N2, LT);
+    auto kern = dh_inner_kernel<LT, N2>;
+    static size_t configured[16] = {};
+    if (configured[c->device] < smem) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[c->device] = smem;
+    }
+    dim3 grid(P.n / DH_TX, LT + 1, (P.B + DH_BCH - 1) / DH_BCH);
+    kern<<<grid, DH_TX * DH_KG, smem, c->stream>>>(P, c->d_mods);
+    c->launches++;
+    CU(cudaGetLastError());
+    return HEGPU_OK;
+}
+
 // hegpu_matvec_bsgs_range with HEGPU_MATVEC_DH (double-hoisted; oracle: orc_matvec_bsgs_dh)
 static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, u32 n1, u32 n2, u32 g_first,
                           bool rescale, const std::vector<u32> &belt, const std::vector<u32> &gelt)
@@ -1508,9 +1528,11 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
     const size_t n = c->n, ctw = (size_t)2 * L * n, accw = (size_t)2 * (L + 1) * n;
     if (nrot > (u32)MAXG) INVALID("double-hoisted matvec supports at most 16 rotated giant steps per call");
     const u32 nr1 = std::max<u32>(nrot, 1);
+    const bool fused = c->dh_fused && L <= 4 && n2 <= 8 && dh_inner_smem(n1, dh_n2_pad(n2), L) <= (size_t)200 * 1024;
+    const size_t nbaby = fused ? 0 : n1;  // the rotated ciphertexts only exist in HBM on the unfused path
     auto need = [&](u32 Bc) {
         return align256((size_t)Bc * L * n) + align256((size_t)Bc * L * (L + 1) * n) + align256(inv_scratch_words(c, (size_t)Bc * std::max<u32>(L, 2))) +
-               align256((size_t)n1 * Bc * accw) + align256((size_t)n2 * Bc * accw) + align256((size_t)nr1 * Bc * ctw) +
+               align256((size_t)nbaby * Bc * accw) + align256((size_t)n2 * Bc * accw) + align256((size_t)nr1 * Bc * ctw) +
                align256((size_t)nr1 * Bc * 2 * n) + align256(inv_scratch_words(c, (size_t)nr1 * Bc * 2)) + align256((size_t)Bc * accw) +
                align256((size_t)Bc * 2 * n) + 2 * align256((size_t)Bc * ctw) + ks_scratch(c, (size_t)nr1 * Bc, L) + rescale_scratch(c, Bc, 2);
     };
@@ -1525,7 +1547,7 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
         u64 *coef = ap.take((size_t)Bc * L * n);
         u64 *ext = ap.take((size_t)Bc * L * (L + 1) * n);
         u64 *scr0 = ap.take(inv_scratch_words(c, (size_t)Bc * std::max<u32>(L, 2)));
-        u64 *babyq = ap.take((size_t)n1 * Bc * accw);
+        u64 *babyq = ap.take((size_t)nbaby * Bc * accw);
         u64 *u = ap.take((size_t)n2 * Bc * accw);
         u64 *v = ap.take((size_t)nr1 * Bc * ctw);
         u64 *tu = ap.take((size_t)nr1 * Bc * 2 * n);
@@ -1553,51 +1575,84 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
         pl0.E = Bn;
         pl0.scr = scr0;
         TRY(ks_decompose(c, pl0));
-        // 2. baby step 0 = P * (c0, c1) in the extended basis
-        {
-            const size_t total = (size_t)Bn * accw;
-            Prof pf(c, PK_ELEMENTWISE, total, (size_t)Bn * ctw * 8 + total * 8);
-            scale_by_p_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(vin, babyq, Bn, L, c->n, c->d_mods);
-            c->launches++;
-            CU(cudaGetLastError());
-        }
-        // 3. baby steps k >= 1: key inner products of the permuted digits, + P * pi_k(c0); no mod-down
-        for (u32 k0 = 1; k0 < n1; k0 += MAXG) {
-            KsPlan pk = pl0;
-            u32 ng = 0;
-            for (u32 k = k0; k < n1 && ng < (u32)MAXG; ++k, ++ng) {
-                const u32 *pm;
-                TRY(get_perm(c, belt[k], &pm));
-                pk.P.in[ng] = vin;
-                pk.P.key[ng] = c->galois_keys[belt[k]];
-                pk.P.perm[ng] = pm;
+        if (fused) {
+            // 2-4 fused: baby-step key inner products and the inner sums of every giant step in one kernel
+            DhInnerParams P{};
+            P.in = vin;
+            P.ext = ext;
+            for (u32 k = 1; k < n1; ++k) {
+                P.key[k] = c->galois_keys[belt[k]];
+                TRY(get_perm(c, belt[k], &P.perm[k]));
             }
-            pk.P.ngroups = ng;
-            pk.P.add_pc0 = 1;
-            pk.P.acc = babyq + (size_t)k0 * Bn * accw;
-            pk.E = (size_t)ng * Bn;
-            TRY(ks_inner(c, pk));
-        }
-        // 4. inner sums of every giant step in the extended basis
-        {
-            BsgsParams P{};
-            for (u32 k = 0; k < n1; ++k) P.baby[k] = qp_view(babyq, (size_t)k * Bn);
-            P.inner = qp_view(u, 0);
             P.diag = dmont;
             P.diag_si = diags->stride();
-            P.diag_sl = n;
+            P.u = u;
             P.n1 = n1;
             P.n2 = n2;
             P.B = Bn;
-            P.L = L + 1;
-            P.n = c->n;
-            P.special_limb = L;
+            P.L = L;
             P.K = c->K;
-            const size_t total = (size_t)Bn * accw;
-            Prof pf(c, PK_BSGS_INNER, total, total * 8 * (n1 + n2) + (u64)n1 * n2 * (L + 1) * n * 8);
-            launch_bsgs_inner_n1(c, P, n1);
-            c->launches++;
-            CU(cudaGetLastError());
+            P.n = c->n;
+            // reads: ciphertexts, lifted digits, keys and diagonals once; writes: the inner sums once
+            const u64 words = (u64)Bn * ctw + (u64)Bn * L * (L + 1) * n + (u64)(n1 - 1) * 2 * L * (L + 1) * n +
+                              (u64)n1 * n2 * (L + 1) * n + (u64)n2 * Bn * accw;
+            Prof pf(c, PK_DH_INNER, (u64)Bn * (L + 1) * n, words * 8);
+#define DH_CASE(LT, N2) case (LT) * 16 + (N2): TRY((launch_dh_inner<LT, N2>(c, P))); break;
+            switch (L * 16 + dh_n2_pad(n2)) {
+                DH_CASE(1, 1) DH_CASE(1, 2) DH_CASE(1, 4) DH_CASE(1, 8)
+                DH_CASE(2, 1) DH_CASE(2, 2) DH_CASE(2, 4) DH_CASE(2, 8)
+                DH_CASE(3, 1) DH_CASE(3, 2) DH_CASE(3, 4) DH_CASE(3, 8)
+                DH_CASE(4, 1) DH_CASE(4, 2) DH_CASE(4, 4) DH_CASE(4, 8)
+            default: LOGIC("unsupported double-hoisted shape");
+            }
+#undef DH_CASE
+        } else {
+            // 2. baby step 0 = P * (c0, c1) in the extended basis
+            {
+                const size_t total = (size_t)Bn * accw;
+                Prof pf(c, PK_ELEMENTWISE, total, (size_t)Bn * ctw * 8 + total * 8);
+                scale_by_p_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(vin, babyq, Bn, L, c->n, c->d_mods);
+                c->launches++;
+                CU(cudaGetLastError());
+            }
+            // 3. baby steps k >= 1: key inner products of the permuted digits, + P * pi_k(c0); no mod-down
+            for (u32 k0 = 1; k0 < n1; k0 += MAXG) {
+                KsPlan pk = pl0;
+                u32 ng = 0;
+                for (u32 k = k0; k < n1 && ng < (u32)MAXG; ++k, ++ng) {
+                    const u32 *pm;
+                    TRY(get_perm(c, belt[k], &pm));
+                    pk.P.in[ng] = vin;
+                    pk.P.key[ng] = c->galois_keys[belt[k]];
+                    pk.P.perm[ng] = pm;
+                }
+                pk.P.ngroups = ng;
+                pk.P.add_pc0 = 1;
+                pk.P.acc = babyq + (size_t)k0 * Bn * accw;
+                pk.E = (size_t)ng * Bn;
+                TRY(ks_inner(c, pk));
+            }
+            // 4. inner sums of every giant step in the extended basis
+            {
+                BsgsParams P{};
+                for (u32 k = 0; k < n1; ++k) P.baby[k] = qp_view(babyq, (size_t)k * Bn);
+                P.inner = qp_view(u, 0);
+                P.diag = dmont;
+                P.diag_si = diags->stride();
+                P.diag_sl = n;
+                P.n1 = n1;
+                P.n2 = n2;
+                P.B = Bn;
+                P.L = L + 1;
+                P.n = c->n;
+                P.special_limb = L;
+                P.K = c->K;
+                const size_t total = (size_t)Bn * accw;
+                Prof pf(c, PK_BSGS_INNER, total, total * 8 * (n1 + n2) + (u64)n1 * n2 * (L + 1) * n * 8);
+                launch_bsgs_inner_n1(c, P, n1);
+                c->launches++;
+                CU(cudaGetLastError());
+            }
         }
         CtView dst = rescale ? view_of(accb, 0) : out->view_at(b0);
         KsPlan pf1;  // the final mod-down

@@ -708,11 +708,138 @@ __global__ void __launch_bounds__(32 * BSGS_GT) bsgs_inner_kernel(const BsgsPara
 #pragma unroll
                     for (int k = 0; k < N1; ++k) mac128(h, lo, buf[s][ci][k][threadIdx.x], d[k]);
                     P.inner.p[((size_t)g * P.B + (it >> 1)) * P.inner.sb + (it & 1) * P.inner.sp + l * P.inner.sl + x0 + threadIdx.x] =
-                        mont_reduce(h, lo, m);  // diag holds d*2^64 mod q
+                        N1 > 16 ? mont_reduce_wide(h, lo, m) : mont_reduce(h, lo, m);  // diag holds d*2^64 mod q
                 }
             }
         }
         __syncthreads();  // the buffer is refilled by the next-but-one issue
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Double-hoisted BSGS, fused: baby-step key inner products + inner sums of every giant step in one
+// pass (replaces scale_by_p + ks_inner(add_pc0) + bsgs_inner of the unfused path; same values):
+//   b_0[c]   = P * ct[c]                                              (limb L: 0)
+//   b_k[c]   = sum_j pi_k(digit_j) * key_k[j][c]  (+ P * pi_k(c0) for c = 0, limbs < L)
+//   u_g[c]   = sum_k b_k[c] * diag[g*n1+k]                            all in the extended basis
+// A CTA owns one extended limb i and a tile of DH_TX = 32 coefficients; it stages the key words
+// (n1 x 2L), the diagonal words (n1*n2) and the gather indices of that tile in shared memory ONCE
+// and sweeps a chunk of the batch, so keys and diagonals leave HBM once per chunk and the rotated
+// ciphertexts b_k never exist in HBM.  Inside the CTA every WARP owns whole ciphertexts (lane =
+// coefficient): it walks the n1 baby steps, builds b_k in registers (the lifted digits are gathered
+// from HBM/L2 -- a Galois permutation maps an aligned 32-word tile to an aligned tile, so a gather
+// is one fully used 256-byte line -- and prefetched two baby steps ahead) and feeds it straight
+// into the 2*n2 independent 128-bit accumulators of the giant steps: no barrier and no
+// shared-memory round trip in the main loop, one Montgomery reduction per output word.
+// grid = (N / 32, L+1, batch chunks), block = 32 * DH_KG.
+// ---------------------------------------------------------------------------------------
+constexpr int DH_TX = 32, DH_KG = 8, DH_BCH = 32;
+struct DhInnerParams {
+    CtView in;             // input batch at level L
+    const u64 *ext;        // [B][L][L+1][N] lifted digits of c1 (hoisted decomposition)
+    const u64 *key[MAXB];  // Galois key of baby step k, Montgomery form; [0] unused
+    const u32 *perm[MAXB]; // gather table of baby step k; [0] unused
+    const u64 *diag;       // [n1*n2][Lcap][N] Montgomery form, limb L = special prime
+    size_t diag_si;
+    u64 *u;                // [n2][B][2][L+1][N]
+    u32 n1, n2, B, L, K, n;
+};
+static inline size_t dh_inner_smem(u32 n1, u32 n2, u32 L)
+{
+    return ((size_t)n1 * 2 * L + (size_t)n1 * n2) * DH_TX * sizeof(u64) + (size_t)n1 * DH_TX * sizeof(u32);
+}
+
+template <int LT, int N2>
+__global__ void __launch_bounds__(DH_TX * DH_KG, 2) dh_inner_kernel(const DhInnerParams P, const ModConst *__restrict__ mods)
+{
+    extern __shared__ __align__(16) u64 dh_smem[];
+    constexpr u32 TX = DH_TX, NT = DH_TX * DH_KG, L = LT;
+    const u32 n = P.n, n1 = P.n1;
+    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const u32 x0 = blockIdx.x * TX, i = blockIdx.y;
+    const u32 b0 = blockIdx.z * DH_BCH, b1 = min(P.B, b0 + DH_BCH);
+    const u32 ki = (i == L) ? P.K - 1 : i;
+    const ModConst m = mods[ki];
+    u64 *skey = dh_smem;                                        // [n1][2L][TX]
+    u64 *sdiag = skey + (size_t)n1 * 2 * L * TX;                 // [n1][N2][TX]
+    u32 *sperm = reinterpret_cast<u32 *>(sdiag + (size_t)n1 * N2 * TX);  // [n1][TX]
+    for (u32 idx = threadIdx.x; idx < n1 * 2 * L * TX; idx += NT) {
+        const u32 x = idx % TX, r = idx / TX, jc = r % (2 * L), k = r / (2 * L);
+        skey[idx] = k ? __ldg(P.key[k] + ((size_t)jc * P.K + ki) * n + x0 + x) : 0;
+    }
+    for (u32 idx = threadIdx.x; idx < n1 * N2 * TX; idx += NT) {
+        const u32 x = idx % TX, r = idx / TX, g = r % N2, k = r / N2;
+        sdiag[idx] = g < P.n2 ? __ldg(P.diag + (size_t)(g * n1 + k) * P.diag_si + (size_t)i * n + x0 + x) : 0;
+    }
+    for (u32 idx = threadIdx.x; idx < n1 * TX; idx += NT) {
+        const u32 x = idx % TX, k = idx / TX;
+        sperm[idx] = k ? __ldg(P.perm[k] + x0 + x) : x0 + x;
+    }
+    __syncthreads();
+    const bool data_limb = i < L;
+    for (u32 b = b0 + w; b < b1; b += DH_KG) {
+        const u64 *cb = P.in.p + b * P.in.sb;
+        const u64 *eb = P.ext + ((size_t)b * L * (L + 1) + i) * n;
+        // operands of baby step k: k = 0 -> {c0, c1} of the CTA's own limb; k >= 1 -> the L permuted
+        // digits (digit i itself is c1's limb i) and, on data limbs, the permuted c0 word
+        auto fetch = [&](u32 k, u64 (&d)[LT + 1]) {
+            const u32 xs = sperm[k * TX + lane];
+            if (k == 0) {
+                d[0] = data_limb ? cb[i * P.in.sl + xs] : 0;
+                d[1] = data_limb ? cb[P.in.sp + i * P.in.sl + xs] : 0;
+#pragma unroll
+                for (int j = 2; j <= LT; ++j) d[j] = 0;
+                return;
+            }
+#pragma unroll
+            for (int j = 0; j < LT; ++j)
+                d[j] = ((u32)j == i) ? cb[P.in.sp + j * P.in.sl + xs] : eb[(size_t)j * (L + 1) * n + xs];
+            d[LT] = data_limb ? cb[i * P.in.sl + xs] : 0;
+        };
+        u64 ah[N2][2], al[N2][2];
+#pragma unroll
+        for (int g = 0; g < N2; ++g) ah[g][0] = al[g][0] = ah[g][1] = al[g][1] = 0;
+        u64 d0[LT + 1], d1[LT + 1], d2[LT + 1];
+        fetch(0, d0);
+        if (n1 > 1) fetch(1, d1);
+        // one baby step: start the gathers of step k+2 into `nxt`, then consume `cur`
+        auto step = [&](u32 k, const u64 (&cur)[LT + 1], u64 (&nxt)[LT + 1]) {
+            if (k + 2 < n1) fetch(k + 2, nxt);
+            u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+            if (k == 0) {
+                mac128(h0, l0, cur[0], m.pmont);  // pmont = 0 for the special prime: b_0[L] = 0
+                mac128(h1, l1, cur[1 % (LT + 1)], m.pmont);
+            } else {
+                const u64 *kp = skey + (size_t)k * 2 * L * TX + lane;
+#pragma unroll
+                for (int j = 0; j < LT; ++j) {
+                    mac128(h0, l0, cur[j], kp[(2 * j) * TX]);
+                    mac128(h1, l1, cur[j], kp[(2 * j + 1) * TX]);
+                }
+                mac128(h0, l0, cur[LT], m.pmont);
+            }
+            const u64 a0 = mont_reduce(h0, l0, m), a1 = mont_reduce(h1, l1, m);
+            const u64 *dp = sdiag + (size_t)k * N2 * TX + lane;
+#pragma unroll
+            for (int g = 0; g < N2; ++g) {
+                const u64 dg = dp[g * TX];
+                mac128(ah[g][0], al[g][0], a0, dg);
+                mac128(ah[g][1], al[g][1], a1, dg);
+            }
+        };
+        for (u32 k = 0; k < n1; k += 3) {  // the three operand sets rotate by name, not by copying
+            step(k, d0, d2);
+            if (k + 1 < n1) step(k + 1, d1, d0);
+            if (k + 2 < n1) step(k + 2, d2, d1);
+        }
+#pragma unroll
+        for (int g = 0; g < N2; ++g) {
+            if ((u32)g < P.n2) {
+                u64 *up = P.u + ((((size_t)g * P.B + b) * 2) * (L + 1) + i) * n + x0 + lane;
+                up[0] = mont_reduce_wide(ah[g][0], al[g][0], m);
+                up[(size_t)(L + 1) * n] = mont_reduce_wide(ah[g][1], al[g][1], m);
+            }
+        }
     }
 }
 

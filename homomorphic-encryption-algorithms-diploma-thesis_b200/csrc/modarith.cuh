@@ -81,6 +81,15 @@ __device__ __forceinline__ u64 mont_reduce(u64 hi, u64 lo, const ModConst &m)
     return csub(r, m.q);
 }
 
+// same for sums of up to 32 products of canonical residues (hi:lo < 2 * q * 2^64): result < 3q before
+// the two conditional subtractions
+__device__ __forceinline__ u64 mont_reduce_wide(u64 hi, u64 lo, const ModConst &m)
+{
+    const u64 t = lo * m.qinv_neg;
+    const u64 r = hi + __umul64hi(t, m.q) + (lo != 0 ? 1ull : 0ull);
+    return csub(csub(r, m.q), m.q);
+}
+
 __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { return csub(a + b, q); }
 __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
 __device__ __forceinline__ u64 negmod(u64 a, u64 q) { return a ? q - a : 0; }
