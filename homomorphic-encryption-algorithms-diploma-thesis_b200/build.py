@@ -8,20 +8,34 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhegpu.so")
-SOURCES = ["hegpu.cu"]
-HEADERS = ["modarith.cuh", "ntt.cuh", "kernels.cuh", os.path.join("..", "..", "include", "hegpu.h")]
+SOURCES = ["hegpu.cu", "ntt_inst_plain_fwd.cu", "ntt_inst_plain_inv.cu", "ntt_inst_ks_intt.cu", "ntt_inst_ks_lift.cu",
+           "ntt_inst_half_intt.cu", "ntt_inst_ks_moddown.cu", "ntt_inst_rescale.cu"]
+HEADERS = ["modarith.cuh", "ntt.cuh", "kernels.cuh", "mac_kernels.cuh", "internal.cuh", "ntt_launch.cuh", os.path.join("..", "..", "include", "hegpu.h")]
+OBJDIR = os.environ.get("HEGPU_OBJDIR", "/tmp/hegpu_obj")  # objects are scratch: only the linked .so lives in-tree
 NVCC_FLAGS = [
-    "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
+    "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
 ]
+
+
+def _obj(src: str) -> str:
+    return os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
+
+
+def _obj_stale(src: str) -> bool:
+    o = _obj(src)
+    if not os.path.exists(o):
+        return True
+    t = os.path.getmtime(o)
+    deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
 def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    return any(_obj_stale(f) or os.path.getmtime(_obj(f)) > t for f in SOURCES)
 
 
 HOST = os.path.join(HERE, "host")
@@ -52,17 +66,33 @@ def build_host(force: bool = False) -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """One object per translation unit (the NTT kernels of each job resolver are their own unit),
+    compiled in parallel, linked into libhegpu.so."""
     if not force and not _stale():
         build_host()
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
+    os.makedirs(OBJDIR, exist_ok=True)
+    todo = [f for f in SOURCES if force or _obj_stale(f)]
+    procs = []
+    for f in todo:
+        cmd = [nvcc, "-c"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", _obj(f), os.path.join(CSRC, f)]
+        procs.append((f, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for f, pr in procs:
+        out, _ = pr.communicate()
+        if verbose:
+            print(out)
+        if pr.returncode != 0:
+            sys.stderr.write(out)
+            failed = True
+    if failed:
+        raise RuntimeError("nvcc failed building libhegpu.so")
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [_obj(f) for f in SOURCES]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if verbose:
-        print(r.stdout)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
-        raise RuntimeError("nvcc failed building libhegpu.so")
+        raise RuntimeError("nvcc failed linking libhegpu.so")
     build_host(force=True)
     return LIB
 

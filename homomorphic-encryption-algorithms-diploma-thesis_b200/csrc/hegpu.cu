@@ -1,44 +1,16 @@
 // hegpu.cu -- host side of libhegpu.so: context/tables, device handles, the C ABI of
 // include/hegpu.h and the composites that stay on the device.  No CPU arithmetic on
 // ciphertext data happens here; the host only builds constant tables and launches kernels.
-#include "../../include/hegpu.h"
-
-#include <algorithm>
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <limits>
-#include <map>
-#include <string>
-#include <vector>
-
-#include "kernels.cuh"
-
-using namespace hegpu;
+#include "ntt_launch.cuh"
+#include "mac_kernels.cuh"
 
 // ------------------------------------------------------------------------- errors
 static thread_local std::string g_err;
-static int fail(int code, const std::string &msg)
+int fail(int code, const std::string &msg)
 {
     g_err = msg;
     return code;
 }
-#define CU(expr)                                                                                  \
-    do {                                                                                          \
-        cudaError_t _e = (expr);                                                                  \
-        if (_e != cudaSuccess) {                                                                  \
-            if (_e == cudaErrorMemoryAllocation) return fail(HEGPU_ERR_OUT_OF_MEMORY, std::string("out of device memory: ") + #expr); \
-            return fail(HEGPU_ERR_CUDA, std::string(cudaGetErrorString(_e)) + " at " + #expr);    \
-        }                                                                                         \
-    } while (0)
-#define TRY(expr)                 \
-    do {                          \
-        int _s = (expr);          \
-        if (_s != HEGPU_OK) return _s; \
-    } while (0)
-#define INVALID(msg) return fail(HEGPU_ERR_INVALID_ARGUMENT, msg)
-#define LOGIC(msg) return fail(HEGPU_ERR_LOGIC, msg)
 
 extern "C" const char *hegpu_last_error(void) { return g_err.c_str(); }
 extern "C" const char *hegpu_version(void) { return "hegpu 0.1 (sm_100a)"; }
@@ -106,126 +78,13 @@ static u64 h_min_root(u64 q, u32 n)
     return best;
 }
 
-// ------------------------------------------------------------------------- objects
-struct Arena {  // grow-only device scratch, bump-allocated per API call
-    char *base = nullptr;
-    size_t cap = 0, off = 0;
-};
-
-enum ProfKind {
-    PK_NTT_FWD_PLAIN, PK_NTT_INV_PLAIN, PK_KS_INTT, PK_KS_LIFT_NTT, PK_KS_INNER, PK_HALF_INTT, PK_KS_MODDOWN_NTT,
-    PK_RESCALE_NTT, PK_BSGS_INNER, PK_TENSOR, PK_ELEMENTWISE, PK_DH_INNER, PK_COUNT
-};
-static const char *const kProfNames[PK_COUNT] = { "ntt_fwd_plain", "ntt_inv_plain", "ks_intt", "ks_lift_ntt", "ks_inner",
-                                                  "half_intt", "ks_moddown_ntt", "rescale_ntt", "bsgs_inner", "tensor",
-                                                  "elementwise", "dh_inner" };
-struct ProfRec {
-    int kind;
-    cudaEvent_t a, b;
-    u64 units, bytes;
-};
-
-struct hegpu_ctx {
-    bool profiling = false;
-    std::vector<ProfRec> prof;
-    std::vector<cudaEvent_t> ev_pool;
-    double prof_ms[PK_COUNT] = {};
-    u64 prof_launches[PK_COUNT] = {}, prof_units[PK_COUNT] = {}, prof_bytes[PK_COUNT] = {};
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t copy_h2d = nullptr, copy_d2h = nullptr;  // async host<->device copies overlap compute
-    cudaEvent_t ev_fence = nullptr;
-    u32 n = 0, logn = 0, K = 0;
-    std::vector<u64> q, psi;
-    std::vector<int> level_bits;  // total_coeff_modulus_bit_count for L = 1..K
-    // device tables
-    ulonglong2 *d_fwd = nullptr, *d_inv = nullptr, *d_inv_last = nullptr;
-    double *d_fwd_d = nullptr, *d_inv_d = nullptr;
-    ModF64 *d_modsd = nullptr;
-    ModConst *d_mods = nullptr;
-    MdConst *d_md = nullptr;  // [K][K]: row d = dropped modulus, column i = target limb
-    NttTables tabs{};
-    // keys
-    u64 *relin_key = nullptr;
-    std::map<u32, u64 *> galois_keys;
-    std::map<u32, u32 *> perms;
-    Arena arena;
-    u64 *park = nullptr;  // [jobs][N/2] scratch of the N = 16384 park kernels (L2-resident in practice)
-    size_t park_words = 0;
-    int use_park = 1;
-    u64 *stage = nullptr;  // host<->device staging
-    size_t stage_words = 0;
-    u64 launches = 0;
-    int sms = 148;
-    int dh_fused = 1;  // double-hoisted matvec: fused baby-step + inner-sum kernel (HEGPU_DH_FUSED=0: unfused kernels)
-    int loge = 3;  // NTT register-set size at N = 16384: 3 = radix-8 passes, 256 threads x 80 registers, 3 CTAs per SM (HEGPU_LOGE=4: radix-16, 2 CTAs)
-    size_t ws_budget = (size_t)24 << 30;  // scratch budget per composite chunk
-};
-
-struct hegpu_ct {
-    hegpu_ctx *ctx;
-    u64 *d;
-    u32 batch, size_cap, L_cap;
-    u32 size, L;
-    double scale;
-    cudaEvent_t ev_copy = nullptr;      // last asynchronous host<->device copy of this batch
-    mutable bool copy_pending = false;  // compute that touches the batch must wait for ev_copy first
-    CtView view() const { return CtView{ d, (size_t)size_cap * L_cap * ctx->n, (size_t)L_cap * ctx->n, (size_t)ctx->n }; }
-    CtView view_at(u32 b0) const
-    {
-        CtView v = view();
-        v.p += b0 * v.sb;
-        return v;
-    }
-};
-
-struct hegpu_pt {
-    hegpu_ctx *ctx;
-    u64 *d;
-    u32 count, L_cap, L;
-    double scale;
-    u64 *d_mont = nullptr;  // lazily built copy in Montgomery form (matvec diagonals)
-    bool mont_valid = false;
-    bool ext = false;       // limb L holds the residues mod the special prime (hegpu_pt_upload_ext)
-    size_t stride() const { return (size_t)L_cap * ctx->n; }
-};
-
-// brackets one launch with events while profiling is enabled
-struct Prof {
-    hegpu_ctx *c;
-    ProfRec r{};
-    bool on;
-    Prof(hegpu_ctx *c_, int kind, u64 units, u64 bytes) : c(c_), on(c_->profiling)
-    {
-        if (!on) return;
-        auto get = [&]() {
-            cudaEvent_t e;
-            if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
-            else cudaEventCreate(&e);
-            return e;
-        };
-        r.kind = kind;
-        r.units = units;
-        r.bytes = bytes;
-        r.a = get();
-        r.b = get();
-        cudaEventRecord(r.a, c->stream);
-    }
-    ~Prof()
-    {
-        if (!on) return;
-        cudaEventRecord(r.b, c->stream);
-        c->prof.push_back(r);
-    }
-};
-
-static int set_device(hegpu_ctx *c)
+int set_device(hegpu_ctx *c)
 {
     CU(cudaSetDevice(c->device));
     return HEGPU_OK;
 }
 
-static int arena_reserve(hegpu_ctx *c, size_t bytes)
+int arena_reserve(hegpu_ctx *c, size_t bytes)
 {
     if (bytes <= c->arena.cap) return HEGPU_OK;
     CU(cudaStreamSynchronize(c->stream));
@@ -237,20 +96,8 @@ static int arena_reserve(hegpu_ctx *c, size_t bytes)
     c->arena.cap = want;
     return HEGPU_OK;
 }
-struct ArenaPlan {  // first pass sizes the scratch, second pass hands out pointers
-    hegpu_ctx *c;
-    size_t off = 0;
-    u64 *take(size_t words)
-    {
-        size_t bytes = (words * sizeof(u64) + 255) & ~(size_t)255;
-        u64 *p = (u64 *)(c->arena.base + off);
-        off += bytes;
-        return p;
-    }
-};
-static inline size_t align256(size_t words) { return ((words * sizeof(u64) + 255) & ~(size_t)255); }
 
-static int park_reserve(hegpu_ctx *c, size_t words)
+int park_reserve(hegpu_ctx *c, size_t words)
 {
     if (words <= c->park_words) return HEGPU_OK;
     CU(cudaStreamSynchronize(c->stream));
@@ -263,7 +110,7 @@ static int park_reserve(hegpu_ctx *c, size_t words)
     return HEGPU_OK;
 }
 
-static int stage_reserve(hegpu_ctx *c, size_t words)
+int stage_reserve(hegpu_ctx *c, size_t words)
 {
     if (words <= c->stage_words) return HEGPU_OK;
     CU(cudaStreamSynchronize(c->stream));
@@ -275,7 +122,7 @@ static int stage_reserve(hegpu_ctx *c, size_t words)
     return HEGPU_OK;
 }
 
-static inline int ew_grid(hegpu_ctx *c, size_t total)
+int ew_grid(hegpu_ctx *c, size_t total)
 {
     size_t blocks = (total + 255) / 256;
     size_t cap = (size_t)c->sms * 16;
@@ -881,110 +728,6 @@ extern "C" int hegpu_pt_download_one(hegpu_pt *t, uint32_t index, uint64_t *host
     return pt_io(t, index, 1, (u64 *)host, false);
 }
 
-// ------------------------------------------------------------------------- NTT launchers
-template <int LOGL, int SPLIT, int LOGE, class Job>
-static int launch_fwd_shape(hegpu_ctx *c, const Job &job, u32 jobs, int kind, u64 words_per_job)
-{
-    Prof pf(c, kind, jobs, (u64)jobs * words_per_job * 8 * c->n);
-    auto kern = ntt_fwd_kernel<LOGL, SPLIT, LOGE, Job>;
-    static bool configured[16] = {};
-    if (!configured[c->device]) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL, LOGE>::SMEM));
-        configured[c->device] = true;
-    }
-    kern<<<jobs << SPLIT, NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::SMEM, c->stream>>>(job, c->tabs);
-    c->launches++;
-    CU(cudaGetLastError());
-    return HEGPU_OK;
-}
-template <int LOGL, int LOGE, class Job>
-static int launch_fwd_park(hegpu_ctx *c, const Job &job, u32 jobs, int kind, u64 words_per_job)
-{
-    TRY(park_reserve(c, (size_t)jobs << LOGL));
-    Prof pf(c, kind, jobs, (u64)jobs * words_per_job * 8 * c->n);
-    auto kern = ntt_fwd_park_kernel<LOGL, LOGE, Job>;
-    static bool configured[16] = {};
-    if (!configured[c->device]) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL, LOGE>::SMEM));
-        configured[c->device] = true;
-    }
-    kern<<<jobs, NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::SMEM, c->stream>>>(job, c->tabs, c->park);
-    c->launches++;
-    CU(cudaGetLastError());
-    return HEGPU_OK;
-}
-template <int LOGL, int LOGE, class Job>
-static int launch_inv_park(hegpu_ctx *c, const Job &job, u32 jobs, int kind)
-{
-    TRY(park_reserve(c, (size_t)jobs << LOGL));
-    Prof pf(c, kind, jobs, (u64)jobs * 16 * c->n);
-    auto kern = ntt_inv_park_kernel<LOGL, LOGE, Job>;
-    static bool configured[16] = {};
-    if (!configured[c->device]) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL, LOGE>::SMEM));
-        configured[c->device] = true;
-    }
-    kern<<<jobs, NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::SMEM, c->stream>>>(job, c->tabs, c->park);
-    c->launches++;
-    CU(cudaGetLastError());
-    return HEGPU_OK;
-}
-
-// words_per_job: algorithmic HBM words per coefficient of one job (2 = read + write)
-template <class Job>
-static int launch_ntt_fwd(hegpu_ctx *c, const Job &job, u32 jobs, int kind, u64 words_per_job)
-{
-    if (jobs == 0) return HEGPU_OK;
-    switch (c->logn) {
-    case 12: return launch_fwd_shape<12, 0, 4>(c, job, jobs, kind, words_per_job);
-    case 13: return launch_fwd_shape<13, 0, 4>(c, job, jobs, kind, words_per_job);
-    case 14:
-        if (c->use_park)
-            return c->loge == 3 ? launch_fwd_park<13, 3>(c, job, jobs, kind, words_per_job)
-                                : launch_fwd_park<13, 4>(c, job, jobs, kind, words_per_job);
-        return launch_fwd_shape<14, 0, 4>(c, job, jobs, kind, words_per_job);
-    case 15: return launch_fwd_shape<14, 1, 4>(c, job, jobs, kind, words_per_job);
-    }
-    LOGIC("unsupported ring degree");
-}
-
-template <int LOGL, int SPLIT, int LOGE, class Job>
-static int launch_inv_shape(hegpu_ctx *c, const Job &job, u32 jobs, u64 *scratch, int kind)
-{
-    Prof pf(c, kind, jobs, (u64)jobs * 16 * c->n);
-    auto kern = ntt_inv_kernel<LOGL, SPLIT, LOGE, Job>;
-    static bool configured[16] = {};
-    if (!configured[c->device]) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL, LOGE>::SMEM));
-        configured[c->device] = true;
-    }
-    kern<<<jobs << SPLIT, NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::SMEM, c->stream>>>(job, c->tabs, scratch);
-    c->launches++;
-    CU(cudaGetLastError());
-    if (SPLIT) {
-        const size_t total = (size_t)jobs << LOGL;
-        ntt_inv_final_kernel<LOGL, Job><<<ew_grid(c, total), 256, 0, c->stream>>>(job, c->tabs, scratch, jobs);
-        c->launches++;
-        CU(cudaGetLastError());
-    }
-    return HEGPU_OK;
-}
-// scratch: [jobs][N] words, only used for N = 32768
-template <class Job>
-static int launch_ntt_inv(hegpu_ctx *c, const Job &job, u32 jobs, u64 *scratch, int kind)
-{
-    if (jobs == 0) return HEGPU_OK;
-    switch (c->logn) {
-    case 12: return launch_inv_shape<12, 0, 4>(c, job, jobs, scratch, kind);
-    case 13: return launch_inv_shape<13, 0, 4>(c, job, jobs, scratch, kind);
-    case 14:
-        if (c->use_park)
-            return c->loge == 3 ? launch_inv_park<13, 3>(c, job, jobs, kind) : launch_inv_park<13, 4>(c, job, jobs, kind);
-        return launch_inv_shape<14, 0, 4>(c, job, jobs, scratch, kind);
-    case 15: return launch_inv_shape<14, 1, 4>(c, job, jobs, scratch, kind);
-    }
-    LOGIC("unsupported ring degree");
-}
 static size_t inv_scratch_words(hegpu_ctx *c, size_t jobs) { return c->logn == 15 ? jobs * c->n : 0; }
 
 static int ntt_device(hegpu_ctx *c, void *d, u32 count, u32 first_mod, u32 n_mods, bool inverse)
@@ -1528,7 +1271,7 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
     const size_t n = c->n, ctw = (size_t)2 * L * n, accw = (size_t)2 * (L + 1) * n;
     if (nrot > (u32)MAXG) INVALID("double-hoisted matvec supports at most 16 rotated giant steps per call");
     const u32 nr1 = std::max<u32>(nrot, 1);
-    const bool fused = c->dh_fused && L <= 4 && n2 <= 8 && dh_inner_smem(n1, dh_n2_pad(n2), L) <= (size_t)200 * 1024;
+    const bool fused = c->dh_fused && L <= 4 && n2 <= 8 && dh_inner_smem(n1, dh_n2_pad(n2), L) <= (size_t)110 * 1024;
     const size_t nbaby = fused ? 0 : n1;  // the rotated ciphertexts only exist in HBM on the unfused path
     auto need = [&](u32 Bc) {
         return align256((size_t)Bc * L * n) + align256((size_t)Bc * L * (L + 1) * n) + align256(inv_scratch_words(c, (size_t)Bc * std::max<u32>(L, 2))) +

@@ -1,0 +1,534 @@
+// mac_kernels.cuh -- the non-NTT kernels: key inner product, element-wise ops, tensor product, BSGS
+// inner sums (unfused and double-hoisted fused), accumulations, repacking.  Included by hegpu.cu only
+// (the NTT kernels and their job resolvers live in kernels.cuh, shared with the ntt_inst_*.cu units).
+#pragma once
+#include "kernels.cuh"
+
+namespace hegpu {
+
+// ---------------------------------------------------------------------------------------
+// K7 step 3: key inner product.  acc[e][c][i] = sum_j ext[e][j][i] (.) key[j][c][ki] mod m_i;
+// digit i == j reads the (permuted) target directly.  128-bit lazy accumulation, one
+// reduction (SEAL: Barrett; here the device copy of every key is kept in Montgomery form
+// k*2^64 mod m, so one Montgomery reduction returns the same canonical residue at a third of
+// the multiplies).  A thread owns one (group, ext limb, coefficient), keeps the
+// 2L key words of that coefficient in registers and sweeps a chunk of the batch, so the keys
+// are read once per chunk instead of once per ciphertext.  grid = (x blocks, ngroups*(L+1),
+// batch chunks).  LT = L when L <= 4 (keys in registers), 0 = generic.
+// ---------------------------------------------------------------------------------------
+constexpr int KS_INNER_BCHUNK = 16;
+
+template <int LT>
+__global__ void __launch_bounds__(256) ks_inner_kernel(const KsParams P, const ModConst *__restrict__ mods)
+{
+    const u32 L = LT ? LT : P.L, n = P.n;
+    const u32 x = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 g = blockIdx.y / (L + 1), i = blockIdx.y % (L + 1);
+    const u32 b0 = blockIdx.z * KS_INNER_BCHUNK;
+    const u32 b1 = min(P.B, b0 + KS_INNER_BCHUNK);
+    if (x >= n) return;
+    const u32 ki = (i == L) ? P.K - 1 : i;
+    const ModConst m = mods[ki];
+    const u64 *key = P.key[g] + (size_t)ki * n + x;
+    const size_t kstride = (size_t)P.K * n;  // between (j,c) slices
+    u64 k0[LT ? LT : 1], k1[LT ? LT : 1];
+    if (LT) {
+#pragma unroll
+        for (int j = 0; j < (LT ? LT : 1); ++j) {
+            k0[j] = __ldg(key + (size_t)(2 * j) * kstride);
+            k1[j] = __ldg(key + (size_t)(2 * j + 1) * kstride);
+        }
+    }
+    const CtView &v = P.in[g];
+    const u32 *pm = P.perm[g];
+    const u32 xs = ((i < L || P.hoisted) && pm) ? __ldg(pm + x) : x;  // gathered column
+    const u32 xe = P.hoisted ? xs : x;                                  // column of the lifted digits
+    for (u32 b = b0; b < b1; ++b) {
+        const size_t e = (size_t)g * P.B + b;
+        const size_t ee = P.hoisted ? b : e;
+        u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+        if (LT) {
+            u64 d[LT ? LT : 1];
+#pragma unroll
+            for (int j = 0; j < (LT ? LT : 1); ++j)
+                d[j] = ((u32)j == i) ? v.p[b * v.sb + P.target_poly * v.sp + j * v.sl + xs]
+                                     : P.ext[((ee * L + j) * (L + 1) + i) * n + xe];
+#pragma unroll
+            for (int j = 0; j < (LT ? LT : 1); ++j) {
+                mac128(h0, l0, d[j], k0[j]);
+                mac128(h1, l1, d[j], k1[j]);
+            }
+        } else {
+            for (u32 j = 0; j < L; ++j) {
+                const u64 d = (j == i) ? v.p[b * v.sb + P.target_poly * v.sp + j * v.sl + xs]
+                                       : P.ext[((ee * L + j) * (L + 1) + i) * n + xe];
+                mac128(h0, l0, d, __ldg(key + (size_t)(2 * j) * kstride));
+                mac128(h1, l1, d, __ldg(key + (size_t)(2 * j + 1) * kstride));
+            }
+        }
+        if (P.add_pc0 && i < L) mac128(h0, l0, v.p[b * v.sb + i * v.sl + xs], m.pmont);
+        P.acc[((e * 2 + 0) * (L + 1) + i) * n + x] = mont_reduce(h0, l0, m);  // keys are stored as k*2^64 mod m
+        P.acc[((e * 2 + 1) * (L + 1) + i) * n + x] = mont_reduce(h1, l1, m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// element-wise kernels over (b, p, l, x).  b's batch stride may be 0 (broadcast).
+// ---------------------------------------------------------------------------------------
+enum EwOp { EW_ADD, EW_SUB, EW_NEG, EW_COPY, EW_MULPLAIN, EW_ADDPLAIN, EW_SUBPLAIN, EW_NEGCOPY_B };
+
+struct EwParams {
+    CtView out, a, b;  // b: second ciphertext, or plaintext (sp = 0)
+    u32 B, polys, L, n;
+};
+
+template <int OP>
+__global__ void __launch_bounds__(256) ew_kernel(const EwParams P, const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)P.polys * P.L * P.n;
+    const size_t total = (size_t)P.B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        u32 r = (u32)(idx % per_b);
+        const u32 x = r % P.n;
+        r /= P.n;
+        const u32 l = r % P.L, p = r / P.L;
+        const size_t oa = b * P.a.sb + p * P.a.sp + l * P.a.sl + x;
+        const size_t ob = b * P.b.sb + p * P.b.sp + l * P.b.sl + x;
+        const size_t oo = b * P.out.sb + p * P.out.sp + l * P.out.sl + x;
+        const u64 q = mods[l].q;
+        u64 v;
+        if (OP == EW_ADD) v = addmod(P.a.p[oa], P.b.p[ob], q);
+        else if (OP == EW_SUB) v = submod(P.a.p[oa], P.b.p[ob], q);
+        else if (OP == EW_NEG) v = negmod(P.a.p[oa], q);
+        else if (OP == EW_COPY) v = P.a.p[oa];
+        else if (OP == EW_NEGCOPY_B) v = negmod(P.b.p[ob], q);
+        else if (OP == EW_MULPLAIN) v = mulmod(P.a.p[oa], P.b.p[ob], mods[l]);
+        else if (OP == EW_ADDPLAIN) v = addmod(P.a.p[oa], P.b.p[ob], q);
+        else v = submod(P.a.p[oa], P.b.p[ob], q);
+        P.out.p[oo] = v;
+    }
+}
+
+// K5: tensor product 2x2 -> 3 (d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1); SQUARE: b = a.
+// out may alias a or b: every thread reads its inputs before it writes.
+template <bool SQUARE>
+__global__ void __launch_bounds__(256) tensor_kernel(const EwParams P, const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)P.L * P.n;
+    const size_t total = (size_t)P.B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        const u32 r = (u32)(idx % per_b);
+        const u32 l = r / P.n, x = r % P.n;
+        const ModConst m = mods[l];
+        const size_t oa = b * P.a.sb + l * P.a.sl + x;
+        const u64 a0 = P.a.p[oa], a1 = P.a.p[oa + P.a.sp];
+        u64 b0, b1;
+        if (SQUARE) {
+            b0 = a0;
+            b1 = a1;
+        } else {
+            const size_t ob = b * P.b.sb + l * P.b.sl + x;
+            b0 = P.b.p[ob];
+            b1 = P.b.p[ob + P.b.sp];
+        }
+        const u64 d0 = mulmod(a0, b0, m), d2 = mulmod(a1, b1, m);
+        u64 h = 0, lo = 0;
+        mac128(h, lo, a0, b1);
+        mac128(h, lo, a1, b0);
+        const u64 d1 = barrett128(h, lo, m);
+        const size_t oo = b * P.out.sb + l * P.out.sl + x;
+        P.out.p[oo] = d0;
+        P.out.p[oo + P.out.sp] = d1;
+        P.out.p[oo + 2 * P.out.sp] = d2;
+    }
+}
+
+// general ciphertext product (sizes sa x sb -> sa+sb-1), used when an operand has size 3.
+// out must not alias.
+__global__ void __launch_bounds__(256) convolve_kernel(const EwParams P, u32 sa, u32 sb, const ModConst *__restrict__ mods)
+{
+    const u32 so = sa + sb - 1;
+    const size_t per_b = (size_t)so * P.L * P.n;
+    const size_t total = (size_t)P.B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        u32 r = (u32)(idx % per_b);
+        const u32 x = r % P.n;
+        r /= P.n;
+        const u32 l = r % P.L, k = r / P.L;
+        const ModConst m = mods[l];
+        u64 h = 0, lo = 0;
+        for (u32 ia = 0; ia < sa; ++ia) {
+            if (k < ia || k - ia >= sb) continue;
+            mac128(h, lo, P.a.p[b * P.a.sb + ia * P.a.sp + l * P.a.sl + x], P.b.p[b * P.b.sb + (k - ia) * P.b.sp + l * P.b.sl + x]);
+        }
+        P.out.p[b * P.out.sb + k * P.out.sp + l * P.out.sl + x] = barrett128(h, lo, m);
+    }
+}
+
+// K6 standalone (only used when a rotation's output aliases its input): out = pi(in)
+__global__ void __launch_bounds__(256) fixup_kernel(const CtView v, u32 B, u32 polys, u32 L, u32 n, const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)polys * L * n;
+    const size_t total = (size_t)B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        u32 r = (u32)(idx % per_b);
+        const u32 x = r % n;
+        r /= n;
+        const u32 l = r % L, p = r / L;
+        u64 *ptr = v.p + b * v.sb + p * v.sp + l * v.sl + x;
+        *ptr = barrett64(*ptr, mods[l]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K10: BSGS inner sums for every giant step in one pass over the baby rotations.
+//   inner[g][b][p][l][x] = sum_{k<n1} baby_k[b][p][l][x] * diag[g*n1+k][l][x]  mod q_l
+// ---------------------------------------------------------------------------------------
+struct BsgsParams {
+    CtView baby[MAXB];  // baby[0] = the input batch
+    CtView inner;       // batch index = g*B + b
+    const u64 *diag;    // [n1*n2][Lcap][N], Montgomery form (d * 2^64 mod q_l)
+    size_t diag_si, diag_sl;
+    u32 n1, n2, B, L, n;
+    u32 special_limb, K;  // limb index that lives mod the special prime (mods[K-1]); ~0u: none
+};
+
+// block = (32 coefficients) x (BSGS_GT giant steps); grid = (n/32, L, ceil(n2/BSGS_GT)).
+// A thread keeps the N1 diagonal words of its (g, l, x) in registers for the whole batch and
+// sweeps the 2B polynomials.  The rotated-ciphertext words of BSGS_C consecutive polynomials are
+// staged in shared memory by cp.async (double buffered) and shared by the BSGS_GT warps, so
+// they are read from HBM exactly once; the diagonals are read exactly once as well.
+constexpr int BSGS_GT = 8;
+
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int N1>
+__global__ void __launch_bounds__(32 * BSGS_GT) bsgs_inner_kernel(const BsgsParams P, const ModConst *__restrict__ mods)
+{
+    constexpr int BSGS_C = N1 > 16 ? 2 : 4;  // staging depth: 2 x C x N1 x 256 B of static shared memory
+    __shared__ u64 buf[2][BSGS_C][N1][32];
+    __shared__ const u64 *bptr[N1];
+    __shared__ size_t bsb[N1], bsp[N1];
+    const u32 tid = threadIdx.y * 32 + threadIdx.x;
+    const u32 x0 = blockIdx.x * 32, l = blockIdx.y;
+    const u32 g = blockIdx.z * BSGS_GT + threadIdx.y;
+    const bool active = g < P.n2;
+    if (tid < N1) {
+        const CtView &c = P.baby[tid];
+        bptr[tid] = c.p + l * c.sl + x0;
+        bsb[tid] = c.sb;
+        bsp[tid] = c.sp;
+    }
+    __syncthreads();
+    const ModConst m = mods[l == P.special_limb ? P.K - 1 : l];
+    u64 d[N1];
+    if (active) {
+        const u64 *dp = P.diag + (size_t)g * N1 * P.diag_si + l * P.diag_sl + x0 + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < N1; ++k) d[k] = __ldg(dp + k * P.diag_si);
+    }
+    const u32 iters = 2 * P.B;
+    const u32 nchunks = (iters + BSGS_C - 1) / BSGS_C;
+    auto issue = [&](u32 chunk, u32 s) {
+        for (u32 v = tid; v < BSGS_C * N1 * 32; v += 32 * BSGS_GT) {
+            const u32 xx = v & 31, k = (v >> 5) % N1, ci = v / (32 * N1);
+            const u32 it = chunk * BSGS_C + ci;
+            if (it < iters) cp_async8(&buf[s][ci][k][xx], bptr[k] + (it >> 1) * bsb[k] + (it & 1) * bsp[k] + xx);
+        }
+        cp_async_commit();
+    };
+    issue(0, 0);
+    for (u32 ch = 0; ch < nchunks; ++ch) {
+        const u32 s = ch & 1;
+        if (ch + 1 < nchunks) {
+            issue(ch + 1, s ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int ci = 0; ci < BSGS_C; ++ci) {
+                const u32 it = ch * BSGS_C + ci;
+                if (it < iters) {
+                    u64 h = 0, lo = 0;
+#pragma unroll
+                    for (int k = 0; k < N1; ++k) mac128(h, lo, buf[s][ci][k][threadIdx.x], d[k]);
+                    P.inner.p[((size_t)g * P.B + (it >> 1)) * P.inner.sb + (it & 1) * P.inner.sp + l * P.inner.sl + x0 + threadIdx.x] =
+                        N1 > 16 ? mont_reduce_wide(h, lo, m) : mont_reduce(h, lo, m);  // diag holds d*2^64 mod q
+                }
+            }
+        }
+        __syncthreads();  // the buffer is refilled by the next-but-one issue
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Double-hoisted BSGS, fused: baby-step key inner products + inner sums of every giant step in one
+// pass (replaces scale_by_p + ks_inner(add_pc0) + bsgs_inner of the unfused path; same values):
+//   b_0[c]   = P * ct[c]                                              (limb L: 0)
+//   b_k[c]   = sum_j pi_k(digit_j) * key_k[j][c]  (+ P * pi_k(c0) for c = 0, limbs < L)
+//   u_g[c]   = sum_k b_k[c] * diag[g*n1+k]                            all in the extended basis
+// A CTA owns one extended limb i and a tile of DH_TX = 32 coefficients; it stages the key words
+// (n1 x 2L), the diagonal words (n1*n2) and the gather indices of that tile in shared memory ONCE
+// and sweeps a chunk of the batch, so keys and diagonals leave HBM once per chunk and the rotated
+// ciphertexts b_k never exist in HBM.  Inside the CTA every WARP owns whole ciphertexts (lane =
+// coefficient): it walks the n1 baby steps, builds b_k in registers (the lifted digits are gathered
+// from HBM/L2 -- a Galois permutation maps an aligned 32-word tile to an aligned tile, so a gather
+// is one fully used 256-byte line -- and prefetched two baby steps ahead) and feeds it straight
+// into the 2*n2 independent 128-bit accumulators of the giant steps: no barrier and no
+// shared-memory round trip in the main loop, one Montgomery reduction per output word.  The kernel
+// is bound by integer-multiply issue (ncu: fmaheavy pipe 80 % busy), not by HBM: keys, diagonals,
+// digits and outputs cross HBM once (a few hundred MB per launch).
+// grid = (N / 32, L+1, batch chunks), block = 32 * DH_KG.
+// ---------------------------------------------------------------------------------------
+constexpr int DH_TX = 32, DH_KG = 8, DH_BCH = 32;
+struct DhInnerParams {
+    CtView in;             // input batch at level L
+    const u64 *ext;        // [B][L][L+1][N] lifted digits of c1 (hoisted decomposition)
+    const u64 *key[MAXB];  // Galois key of baby step k, Montgomery form; [0] unused
+    const u32 *perm[MAXB]; // gather table of baby step k; [0] unused
+    const u64 *diag;       // [n1*n2][Lcap][N] Montgomery form, limb L = special prime
+    size_t diag_si;
+    u64 *u;                // [n2][B][2][L+1][N]
+    u32 n1, n2, B, L, K, n;
+};
+static inline size_t dh_inner_smem(u32 n1, u32 n2, u32 L)
+{
+    return ((size_t)n1 * 2 * L + (size_t)n1 * n2) * DH_TX * sizeof(u64) + (size_t)n1 * DH_TX * sizeof(u32);
+}
+
+template <int LT, int N2>
+__global__ void __launch_bounds__(DH_TX * DH_KG, 2) dh_inner_kernel(const DhInnerParams P, const ModConst *__restrict__ mods)
+{
+    extern __shared__ __align__(16) u64 dh_smem[];
+    constexpr u32 TX = DH_TX, NT = DH_TX * DH_KG, L = LT;
+    const u32 n = P.n, n1 = P.n1;
+    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const u32 x0 = blockIdx.x * TX, i = blockIdx.y;
+    const u32 b0 = blockIdx.z * DH_BCH, b1 = min(P.B, b0 + DH_BCH);
+    const u32 ki = (i == L) ? P.K - 1 : i;
+    const ModConst m = mods[ki];
+    u64 *skey = dh_smem;                                        // [n1][2L][TX]
+    u64 *sdiag = skey + (size_t)n1 * 2 * L * TX;                 // [n1][N2][TX]
+    u32 *sperm = reinterpret_cast<u32 *>(sdiag + (size_t)n1 * N2 * TX);  // [n1][TX]
+    for (u32 idx = threadIdx.x; idx < n1 * 2 * L * TX; idx += NT) {
+        const u32 x = idx % TX, r = idx / TX, jc = r % (2 * L), k = r / (2 * L);
+        skey[idx] = k ? __ldg(P.key[k] + ((size_t)jc * P.K + ki) * n + x0 + x) : 0;
+    }
+    for (u32 idx = threadIdx.x; idx < n1 * N2 * TX; idx += NT) {
+        const u32 x = idx % TX, r = idx / TX, g = r % N2, k = r / N2;
+        sdiag[idx] = g < P.n2 ? __ldg(P.diag + (size_t)(g * n1 + k) * P.diag_si + (size_t)i * n + x0 + x) : 0;
+    }
+    for (u32 idx = threadIdx.x; idx < n1 * TX; idx += NT) {
+        const u32 x = idx % TX, k = idx / TX;
+        sperm[idx] = k ? __ldg(P.perm[k] + x0 + x) : x0 + x;
+    }
+    __syncthreads();
+    const bool data_limb = i < L;
+    for (u32 b = b0 + w; b < b1; b += DH_KG) {
+        // operand streams of this ciphertext, fixed for all baby steps (only the gathered column
+        // changes): src[j] = digit j lifted to limb i (digit i itself is c1's limb i), src[L] = c0's
+        // limb i.  Baby step 0 uses the same words unpermuted: c0 = src[L], c1 = src[i].
+        const u64 *src[LT + 1];
+        {
+            const u64 *cb = P.in.p + b * P.in.sb;
+            const u64 *eb = P.ext + ((size_t)b * L * (L + 1) + i) * n;
+#pragma unroll
+            for (int j = 0; j < LT; ++j) src[j] = ((u32)j == i) ? cb + P.in.sp + j * P.in.sl : eb + (size_t)j * (L + 1) * n;
+            src[LT] = cb + (data_limb ? i : 0) * P.in.sl;
+        }
+        auto fetch = [&](u32 k, u64 (&d)[LT + 1]) {
+            const u32 xs = sperm[k * TX + lane];
+#pragma unroll
+            for (int j = 0; j < LT; ++j) d[j] = src[j][xs];
+            d[LT] = data_limb ? src[LT][xs] : 0;
+        };
+        u64 ah[N2][2], al[N2][2];
+#pragma unroll
+        for (int g = 0; g < N2; ++g) ah[g][0] = al[g][0] = ah[g][1] = al[g][1] = 0;
+        u64 d0[LT + 1], d1[LT + 1], d2[LT + 1];
+        fetch(0, d0);
+        if (n1 > 1) fetch(1, d1);
+        // one baby step: start the gathers of step k+2 into `nxt`, then consume `cur`
+        auto step = [&](u32 k, const u64 (&cur)[LT + 1], u64 (&nxt)[LT + 1]) {
+            if (k + 2 < n1) fetch(k + 2, nxt);
+            u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+            if (k == 0) {  // b_0 = P * (c0, c1); pmont = 0 for the special prime: b_0[L] = 0
+                u64 w1 = cur[0];
+#pragma unroll
+                for (int j = 1; j < LT; ++j) w1 = ((u32)j == i) ? cur[j] : w1;
+                mac128(h0, l0, cur[LT], m.pmont);
+                mac128(h1, l1, w1, m.pmont);
+            } else {
+                const u64 *kp = skey + (size_t)k * 2 * L * TX + lane;
+#pragma unroll
+                for (int j = 0; j < LT; ++j) {
+                    mac128(h0, l0, cur[j], kp[(2 * j) * TX]);
+                    mac128(h1, l1, cur[j], kp[(2 * j + 1) * TX]);
+                }
+                mac128(h0, l0, cur[LT], m.pmont);
+            }
+            const u64 a0 = mont_reduce(h0, l0, m), a1 = mont_reduce(h1, l1, m);
+            const u64 *dp = sdiag + (size_t)k * N2 * TX + lane;
+#pragma unroll
+            for (int g = 0; g < N2; ++g) {
+                const u64 dg = dp[g * TX];
+                mac128(ah[g][0], al[g][0], a0, dg);
+                mac128(ah[g][1], al[g][1], a1, dg);
+            }
+        };
+        for (u32 k = 0; k < n1; k += 3) {  // the three operand sets rotate by name, not by copying
+            step(k, d0, d2);
+            if (k + 1 < n1) step(k + 1, d1, d0);
+            if (k + 2 < n1) step(k + 2, d2, d1);
+        }
+#pragma unroll
+        for (int g = 0; g < N2; ++g) {
+            if ((u32)g < P.n2) {
+                u64 *up = P.u + ((((size_t)g * P.B + b) * 2) * (L + 1) + i) * n + x0 + lane;
+                up[0] = mont_reduce_wide(ah[g][0], al[g][0], m);
+                up[(size_t)(L + 1) * n] = mont_reduce_wide(ah[g][1], al[g][1], m);
+            }
+        }
+    }
+}
+
+// sum of `terms` ciphertext batches laid out at batch offsets g*B: out = sum_g src_g
+struct SumParams {
+    CtView first;  // term 0
+    CtView rest;   // terms 1.., batch index (g-1)*B + b
+    CtView out;
+    u32 terms, B, polys, L, n;
+};
+__global__ void __launch_bounds__(256) sum_terms_kernel(const SumParams P, const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)P.polys * P.L * P.n;
+    const size_t total = (size_t)P.B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        u32 r = (u32)(idx % per_b);
+        const u32 x = r % P.n;
+        r /= P.n;
+        const u32 l = r % P.L, p = r / P.L;
+        const u64 q = mods[l].q;
+        u64 s = P.first.p[b * P.first.sb + p * P.first.sp + l * P.first.sl + x];
+        for (u32 g = 1; g < P.terms; ++g)
+            s = addmod(s, P.rest.p[((size_t)(g - 1) * P.B + b) * P.rest.sb + p * P.rest.sp + l * P.rest.sl + x], q);
+        P.out.p[b * P.out.sb + p * P.out.sp + l * P.out.sl + x] = s;
+    }
+}
+
+// lazy mod-down over giant steps: accsum[b][c][i] = sum_g acc[g*B+b][c][i] mod m_i  (rows = 2*(L+1))
+__global__ void __launch_bounds__(256) acc_group_sum_kernel(const u64 *__restrict__ acc, const u64 *__restrict__ init,
+                                                            u64 *__restrict__ out, u32 groups, u32 B, u32 L, u32 K, u32 n,
+                                                            const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)2 * (L + 1) * n;
+    const size_t total = (size_t)B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        const size_t r = idx % per_b;
+        const u32 i = (u32)((r / n) % (L + 1));
+        const u64 q = mods[i == L ? K - 1 : i].q;
+        u64 s = init ? init[idx] : 0;  // init: an unrotated term already in the extended basis
+        for (u32 g = 0; g < groups; ++g) s = addmod(s, acc[((size_t)g * B + b) * per_b + r], q);
+        out[idx] = s;
+    }
+}
+
+// base[b][0] = first[b][0] + sum_g pi_g(rest[g*B+b][0]);  base[b][1] = first[b][1]
+struct BaseSumParams {
+    CtView first, rest, out;
+    const u32 *perm[MAXG];
+    u32 groups, B, L, n;
+    u32 has_first;  // 0: there is no unrotated term (diagonal-sharded ranks other than the first)
+};
+__global__ void __launch_bounds__(256) base_gather_sum_kernel(const BaseSumParams P, const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)2 * P.L * P.n;
+    const size_t total = (size_t)P.B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        u32 r = (u32)(idx % per_b);
+        const u32 x = r % P.n;
+        r /= P.n;
+        const u32 l = r % P.L, p = r / P.L;
+        const u64 q = mods[l].q;
+        u64 s = P.has_first ? P.first.p[b * P.first.sb + p * P.first.sp + l * P.first.sl + x] : 0;
+        if (p == 0)
+            for (u32 g = 0; g < P.groups; ++g)
+                s = addmod(s, P.rest.p[((size_t)g * P.B + b) * P.rest.sb + l * P.rest.sl + __ldg(P.perm[g] + x)], q);
+        P.out.p[b * P.out.sb + p * P.out.sp + l * P.out.sl + x] = s;
+    }
+}
+
+// x -> x * 2^64 mod q (Montgomery form) for `rows` limb polynomials; row r uses modulus
+// mod_of_row = (r % limbs_per_item) mapped through `last_is_special` (key layout: K limbs, limb
+// K-1 = special prime; plaintext layout: limb l = modulus l)
+__global__ void __launch_bounds__(256) to_montgomery_kernel(const u64 *__restrict__ src, u64 *__restrict__ dst, size_t rows,
+                                                            u32 limbs_per_item, size_t row_stride_src, size_t row_stride_dst, u32 n,
+                                                            const ModConst *__restrict__ mods, u32 special_limb = ~0u, u32 K = 0)
+{
+    const size_t total = rows * n;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = idx / n;
+        const u32 x = (u32)(idx % n);
+        const u32 l = (u32)(r % limbs_per_item);
+        const ModConst m = mods[l == special_limb ? K - 1 : l];
+        dst[r * row_stride_dst + x] = mul_shoup(src[r * row_stride_src + x], m.rmod, m.rmod_sh, m.q);
+    }
+}
+
+// double-hoisted baby step 0: out[b][c][i] = P * in[b][c][i] mod q_i (i < L), out[b][c][L] = 0;
+// out in the key-switch accumulator layout [B][2][L+1][N]
+__global__ void __launch_bounds__(256) scale_by_p_kernel(const CtView in, u64 *__restrict__ out, u32 B, u32 L, u32 n,
+                                                         const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)2 * (L + 1) * n;
+    const size_t total = (size_t)B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        u32 r = (u32)(idx % per_b);
+        const u32 x = r % n;
+        r /= n;
+        const u32 i = r % (L + 1), c = r / (L + 1);
+        u64 v = 0;
+        if (i < L) {
+            const ModConst m = mods[i];
+            u64 h = 0, lo = 0;
+            mac128(h, lo, in.p[b * in.sb + c * in.sp + i * in.sl + x], m.pmont);
+            v = mont_reduce(h, lo, m);
+        }
+        out[idx] = v;
+    }
+}
+
+// strided repack between SEAL's packed host layout (staged in HBM) and the batch layout
+__global__ void __launch_bounds__(256) repack_kernel(const CtView dst, const CtView src, u32 B, u32 polys, u32 L, u32 n)
+{
+    const size_t per_b = (size_t)polys * L * n;
+    const size_t total = (size_t)B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        u32 r = (u32)(idx % per_b);
+        const u32 x = r % n;
+        r /= n;
+        const u32 l = r % L, p = r / L;
+        dst.p[b * dst.sb + p * dst.sp + l * dst.sl + x] = src.p[b * src.sb + p * src.sp + l * src.sl + x];
+    }
+}
+
+}  // namespace hegpu
