@@ -359,8 +359,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default=CFG["mode"], choices=sorted(MODES))
     ap.add_argument("--n1", type=int, default=None, help="baby steps (n1 * n2 = 128)")
+    ap.add_argument("--batch", type=int, default=None, help="ciphertexts per GPU per step")
     args = ap.parse_args()
     CFG["mode"] = args.mode
+    if args.batch:
+        CFG["batch"] = args.batch
     if args.n1:
         assert CFG["dim"] % args.n1 == 0
         CFG["n1"], CFG["n2"] = args.n1, CFG["dim"] // args.n1

@@ -34,6 +34,12 @@ __device__ __forceinline__ u64 mul_shoup_lazy(u64 x, u64 w, u64 wsh, u64 q)
     return x * w - h * q;
 }
 __device__ __forceinline__ u64 mul_shoup(u64 x, u64 w, u64 wsh, u64 q) { return csub(mul_shoup_lazy(x, w, wsh, q), q); }
+// same with nq = 2^64 - q precomputed: x*w + h*nq is one multiply-add chain (no negation of h*q)
+__device__ __forceinline__ u64 mul_shoup_lazy_nq(u64 x, u64 w, u64 wsh, u64 nq)
+{
+    u64 h = __umul64hi(x, wsh);
+    return x * w + h * nq;
+}
 
 // x mod q for any x < 2^64 (SEAL barrett_reduce_64)
 __device__ __forceinline__ u64 barrett64(u64 x, const ModConst &m)

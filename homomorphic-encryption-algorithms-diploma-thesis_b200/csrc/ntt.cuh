@@ -107,13 +107,14 @@ struct ArI64 {
     typedef ulonglong2 TW;
     const ModConst &m;
     const ulonglong2 wlast;
-    __device__ __forceinline__ ArI64(const ModConst &m_, ulonglong2 wl) : m(m_), wlast(wl) {}
+    const u64 nq;  // 2^64 - q
+    __device__ __forceinline__ ArI64(const ModConst &m_, ulonglong2 wl) : m(m_), wlast(wl), nq(0ull - m_.q) {}
     __device__ __forceinline__ V from_load(u64 v) const { return v; }
     // forward: values < 8q at pass start (BIG), +2q per stage, < 16q < 2^64
     __device__ __forceinline__ V fwd_fix(V v) const { return BIG ? csub(v, m.q << 3) : v; }
     __device__ __forceinline__ void fwd_bfly(V &X, V &Y, const TW W) const
     {
-        const u64 T = mul_shoup_lazy(Y, W.x, W.y, m.q);
+        const u64 T = mul_shoup_lazy_nq(Y, W.x, W.y, nq);
         Y = X + (m.q << 1) - T;
         X = X + T;
     }
@@ -143,7 +144,7 @@ struct ArI64 {
             D = X + (m.q << (GBIT + 1)) - Y;
         }
         X = Sm;
-        Y = mul_shoup_lazy(D, W.x, W.y, m.q);
+        Y = mul_shoup_lazy_nq(D, W.x, W.y, nq);
     }
     template <int GBIT>
     __device__ __forceinline__ void inv_bfly_last(V &X, V &Y) const
