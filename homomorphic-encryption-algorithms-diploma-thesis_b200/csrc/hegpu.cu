@@ -110,6 +110,20 @@ int park_reserve(hegpu_ctx *c, size_t words)
     return HEGPU_OK;
 }
 
+void select_slot(hegpu_ctx *c, int slot)
+{
+    c->park_slots[c->cur_slot] = c->park;
+    c->park_words_slots[c->cur_slot] = c->park_words;
+    c->cur_slot = slot;
+    c->park = c->park_slots[slot];
+    c->park_words = c->park_words_slots[slot];
+    c->stream = slot ? c->aux_stream : c->main_stream;
+}
+struct SlotGuard {  // composites return to slot 0 on every exit path
+    hegpu_ctx *c;
+    ~SlotGuard() { select_slot(c, 0); }
+};
+
 int stage_reserve(hegpu_ctx *c, size_t words)
 {
     if (words <= c->stage_words) return HEGPU_OK;
@@ -160,6 +174,11 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     if (const char *e = getenv("HEGPU_PARK")) c->use_park = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_FUSED")) c->dh_fused = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->main_stream = c->stream;
+    CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    if (const char *e = getenv("HEGPU_STREAMS")) c->dual_stream = atoi(e) >= 2;
     CU(cudaStreamCreateWithFlags(&c->copy_h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_d2h, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_fence, cudaEventDisableTiming));
@@ -276,7 +295,13 @@ extern "C" int hegpu_ctx_destroy(hegpu_ctx *c)
     for (auto &kv : c->perms) cudaFree(kv.second);
     cudaFree(c->arena.base);
     cudaFree(c->stage);
+    select_slot(c, 0);
+    cudaStreamSynchronize(c->aux_stream);
     cudaFree(c->park);
+    cudaFree(c->park_slots[1]);
+    cudaStreamDestroy(c->aux_stream);
+    cudaEventDestroy(c->ev_fork);
+    cudaEventDestroy(c->ev_join);
     cudaStreamSynchronize(c->copy_h2d);
     cudaStreamSynchronize(c->copy_d2h);
     cudaStreamDestroy(c->copy_h2d);
@@ -1279,14 +1304,32 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
                align256((size_t)nr1 * Bc * 2 * n) + align256(inv_scratch_words(c, (size_t)nr1 * Bc * 2)) + align256((size_t)Bc * accw) +
                align256((size_t)Bc * 2 * n) + 2 * align256((size_t)Bc * ctw) + ks_scratch(c, (size_t)nr1 * Bc, L) + rescale_scratch(c, Bc, 2);
     };
-    u32 Bc = B;
-    while (Bc > 1 && need(Bc) > c->ws_budget) Bc = (Bc + 1) / 2;
-    TRY(arena_reserve(c, need(Bc)));
+    // two execution slots: alternate batch chunks go to the main and the auxiliary stream (own scratch
+    // each), so the small grids of one chunk (a single wave of NTT CTAs) overlap the other chunk's kernels
+    const int NS = (c->dual_stream && !c->profiling && B >= 32) ? 2 : 1;
+    u32 Bc = NS == 2 ? (B + 1) / 2 : B;
+    while (Bc > 1 && need(Bc) * NS > c->ws_budget) Bc = (Bc + 1) / 2;
+    TRY(arena_reserve(c, need(Bc) * NS));
     const u64 *dmont;
     TRY(pt_montgomery(const_cast<hegpu_pt *>(diags), &dmont));
-    for (u32 b0 = 0; b0 < B; b0 += Bc) {
+    SlotGuard guard{ c };
+    if (NS == 2) {
+        const size_t park_need = (size_t)nr1 * Bc * (L * L + 2 * L) * (n / 2);  // largest NTT launch of a chunk
+        for (int sl = 0; sl < 2; ++sl) {
+            select_slot(c, sl);
+            if (c->logn == 14 && c->use_park) TRY(park_reserve(c, park_need));
+        }
+        select_slot(c, 0);
+        CU(cudaEventRecord(c->ev_fork, c->main_stream));
+        CU(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+    }
+    u32 chunk_no = 0;
+    for (u32 b0 = 0; b0 < B; b0 += Bc, ++chunk_no) {
         const u32 Bn = std::min(Bc, B - b0);
+        const int slot = NS == 2 ? (int)(chunk_no & 1u) : 0;
+        select_slot(c, slot);
         ArenaPlan ap{ c };
+        ap.off = (size_t)slot * need(Bc);
         u64 *coef = ap.take((size_t)Bc * L * n);
         u64 *ext = ap.take((size_t)Bc * L * (L + 1) * n);
         u64 *scr0 = ap.take(inv_scratch_words(c, (size_t)Bc * std::max<u32>(L, 2)));
@@ -1481,6 +1524,10 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
             ar.off = ap.off;
             TRY(rescale_views(c, out->view_at(b0), dst, Bn, 2, L, ar));
         }
+    }
+    if (NS == 2) {
+        CU(cudaEventRecord(c->ev_join, c->aux_stream));
+        CU(cudaStreamWaitEvent(c->main_stream, c->ev_join, 0));
     }
     return HEGPU_OK;
 }
