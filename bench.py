@@ -1,11 +1,13 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark: CKKS matvecs/s, N = 2^14, 128x128 plaintext matrix x
-encrypted vector, BSGS 16x8, batch of 64 ciphertexts per step (BASELINE.json configs[1]).
+encrypted vector, double-hoisted BSGS 32x4, batch of 128 ciphertexts per step (BASELINE.json
+configs[1]).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                  [--mode dh|hoist] [--n1 N1] [--batch B]
 
 One process per GPU (torchrun for N > 1).  A step is one pass of hegpu_matvec_bsgs over a
-batch of 64 encrypted vectors on every rank (batch sharding, no data-path collective ->
+batch of 128 encrypted vectors on every rank (batch sharding, no data-path collective ->
 weak scaling).  Prints ONE JSON line (rank 0).
 
   value     matvecs/s with inputs resident in HBM (CUDA events on the context's stream)
@@ -34,7 +36,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(N=16384, bits=(60, 40, 40, 60), dim=128, n1=16, n2=8, batch=64, scale=2.0**40, L=3, mode="hoist")
+CFG = dict(N=16384, bits=(60, 40, 40, 60), dim=128, n1=32, n2=4, batch=128, scale=2.0**40, L=3, mode="dh")
 MODES = {
     "hoist": "HEGPU_MATVEC_HOIST|LAZY (hoisted baby steps, one mod-down for the giant steps)",
     "dh": "HEGPU_MATVEC_DH (double-hoisted: baby rotations stay in the extended basis, one mod-down per giant step)",
@@ -304,10 +306,25 @@ def run_gpu(args):
                for k, v in prof.items() if v["launches"]}
     ntt_ms = sum(v["ms"] for k, v in prof.items() if "ntt" in k)
     ntt_bytes = sum(v["algo_bytes"] for k, v in prof.items() if "ntt" in k)
+    # DRAM traffic per launch from the committed ncu capture of this configuration (profiles/), if any
+    traffic, ncu_extra = None, {}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            if tj.get("config") == f"{c['mode']}-{c['n1']}x{c['n2']}-b{B}" and dom in tj.get("kernels", {}):
+                ncu_extra = tj["kernels"][dom]
+                traffic = ncu_extra.get("dram_bytes_per_launch")
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src, "traffic": traffic, "ncu": ncu_extra,
                 "avg_launch_ms": d["ms"] / max(d["launches"], 1), "share_of_step": d["ms"] / tot_ms,
-                "all_ntt_kernels": {"achieved": ntt_bytes / (ntt_ms * 1e-3) / 1e9 if ntt_ms else 0.0, "share_of_step": ntt_ms / tot_ms},
+                "note": ("dh_inner is bound by 64-bit integer multiply issue, not by HBM (ncu: fmaheavy pipe ~80 % busy, DRAM < 5 %): "
+                         "fusing the baby-step key inner products with the giant-step sums removed the traffic, so its HBM "
+                         "fraction is small by construction; the HBM-bound family is the NTT (all_ntt_kernels)") if dom == "dh_inner" else None,
+                "all_ntt_kernels": {"achieved": ntt_bytes / (ntt_ms * 1e-3) / 1e9 if ntt_ms else 0.0,
+                                    "frac": (ntt_bytes / (ntt_ms * 1e-3) / 1e9 / peak) if ntt_ms else 0.0, "share_of_step": ntt_ms / tot_ms},
                 "kernels": kernels}
 
     line = {
@@ -316,7 +333,7 @@ def run_gpu(args):
         "data": "synthetic",
         "config": {"workload": workload_name(), "batch_per_gpu_per_step": B, "parallelism": f"batch-sharded x{world}, keys and diagonals replicated",
                    "mode": MODES[c["mode"]] + "; the CPU arm runs the same algorithm",
-                   "l2": "no flush: each step streams ~3.5 GB of key-switch scratch per GPU, far beyond the 126 MB L2",
+                   "l2": "no flush: each step streams > 2 GB of ciphertexts, lifted digits, keys, diagonals and scratch per GPU, far beyond the 126 MB L2",
                    "tolerance": tol, "max_abs_err_vs_numpy": max_err},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "matvecs/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(cts.nbytes),
@@ -336,13 +353,18 @@ def run_gpu(args):
         gkeys = [None] + [gk[ctx.galois_elt_from_step(g * c["n1"])] for g in range(1, c["n2"])]
         sample_n = min(B, max(threads, 1) * 4)
         sub = np.ascontiguousarray(cts[:sample_n])
-        dt = None
-        for _ in range(2):  # best of two passes over the sample (the host is shared and noisy)
+        passes, total, best = 0, 0.0, None
+        while total < 10.0 and passes < 64:  # about 10 s of CPU work on the sample (the host is shared and noisy)
             t0 = time.perf_counter()
             ref_out = o.matvec_bsgs(sub, c["n1"], c["n2"], pts, bk, gkeys, threads=threads, fast=not dh, dh=dh)
-            dt = min(dt, time.perf_counter() - t0) if dt else time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": sample_n / dt, "unit": "matvecs/s", "cores": threads, "kind": "port",
-                                "sample": f"first {sample_n} of the {B} ciphertexts of one step, same keys/diagonals, best of 2 passes, {dt:.2f} s wall each",
+            dt = time.perf_counter() - t0
+            total += dt
+            passes += 1
+            best = dt if best is None else min(best, dt)
+        line["cpu_baseline"] = {"value": sample_n * passes / total, "unit": "matvecs/s", "cores": threads, "kind": "port",
+                                "best_pass_value": sample_n / best,
+                                "sample": f"first {sample_n} of the {B} ciphertexts of one step, same keys/diagonals and algorithm, "
+                                          f"{passes} passes, {total:.1f} s wall in total",
                                 "bit_exact_vs_gpu": bool(np.array_equal(ref_out, got[:sample_n]))}
     if rank == 0:
         print(json.dumps(line))
@@ -353,7 +375,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hegpu", choices=["hegpu", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -364,6 +386,8 @@ def main():
     CFG["mode"] = args.mode
     if args.batch:
         CFG["batch"] = args.batch
+    if args.mode == "hoist" and not args.n1:
+        args.n1 = 16  # the hoisted (single-hoisting) composite takes at most 16 baby steps
     if args.n1:
         assert CFG["dim"] % args.n1 == 0
         CFG["n1"], CFG["n2"] = args.n1, CFG["dim"] // args.n1

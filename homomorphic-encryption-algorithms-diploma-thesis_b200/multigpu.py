@@ -54,14 +54,17 @@ def allreduce_sum(ct, world: int, group=None):
 
 
 def matvec_bsgs_diag_sharded(ctx, out, x, diags_local, n1: int, n2_total: int, rank: int, world: int, hoist: bool = True,
-                             partial=None, group=None):
+                             partial=None, group=None, dh: bool = False):
     """Diagonal-sharded BSGS matvec.  diags_local holds the n1*cnt pre-rotated diagonals of this
-    rank's giant steps (giant_step_range).  Every rank ends with the full result in `out`."""
+    rank's giant steps (giant_step_range).  Every rank ends with the full result in `out`.
+    dh=True: double-hoisted partials (diags_local uploaded with upload_pt_ext); every rank then runs
+    its own final mod-down, so the sum equals the unsharded result up to that rounding (and the
+    oracle's sharded restatement bit for bit)."""
     g_first, cnt = giant_step_range(n2_total, world, rank)
     _, _, L, _ = x.info()
     part = partial if partial is not None else ctx.ct(x.batch, 2, L)
     if cnt:
-        ctx.matvec_bsgs(part, x, diags_local, n1, cnt, rescale=False, hoist=hoist, lazy=False, g_first=g_first)
+        ctx.matvec_bsgs(part, x, diags_local, n1, cnt, rescale=False, hoist=hoist and not dh, lazy=False, g_first=g_first, dh=dh)
     else:  # more ranks than giant steps: contribute zero
         part.upload(np.zeros((x.batch, 2, L, ctx.n), dtype=np.uint64), x.scale * diags_local.scale if diags_local else x.scale)
     if world > 1:

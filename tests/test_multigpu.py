@@ -116,6 +116,42 @@ def test_diag_sharded_emulated_on_one_gpu():
     assert np.array_equal(out.download(), want)
 
 
+@pytest.mark.gpu
+def test_diag_sharded_double_hoisted_emulated_on_one_gpu():
+    """Same with HEGPU_MATVEC_DH partials: every rank's partial is bit-identical to the oracle's
+    sharded restatement, and so is the reduced + rescaled sum."""
+    hg = hegpu_loader.load()
+    from fixtures import rand_residues
+    from hegpu_b200.multigpu import as_torch_i64, giant_step_range
+
+    S, cts, pts, gk, bk, gkeys = _problem()
+    rng = np.random.default_rng(18)
+    ptsx = np.concatenate([pts, rand_residues(rng, [S.moduli[-1]], (N1 * N2,), N)], axis=1)  # + limb mod P
+    ctx = hg.Context(N, S.moduli)
+    ctx.load_galois_keys(gk)
+    X = ctx.upload_ct(cts, SCALE, size_cap=2, L_cap=L)
+    world = 2
+    parts, want_sum = [], None
+    for r in range(world):
+        g0, cnt = giant_step_range(N2, world, r)
+        sl = np.ascontiguousarray(ptsx[g0 * N1:(g0 + cnt) * N1])
+        D = ctx.upload_pt_ext(sl, SCALE)
+        p = ctx.ct(B, 2, L)
+        ctx.matvec_bsgs(p, X, D, N1, cnt, rescale=False, dh=True, g_first=g0)
+        want_part = S.o.matvec_bsgs(cts, N1, cnt, sl, bk, gkeys[g0:g0 + cnt], dh=True, rescale=False, g_first=g0)
+        assert np.array_equal(p.download(), want_part)
+        want_sum = want_part if want_sum is None else np.stack([S.o.add(want_sum[b], want_part[b]) for b in range(B)])
+        parts.append(p)
+    ctx.sync()
+    acc = as_torch_i64(parts[0])
+    acc += as_torch_i64(parts[1])
+    torch.cuda.synchronize()
+    ctx.reduce_fixup(parts[0], world)
+    out = ctx.ct(B, 2, L - 1)
+    ctx.rescale_to_next(out, parts[0])
+    assert np.array_equal(out.download(), np.stack([S.o.rescale(want_sum[b]) for b in range(B)]))
+
+
 def _nccl_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
