@@ -120,6 +120,15 @@ def workload_name():
             f"BSGS {c['n1']}x{c['n2']}")
 
 
+def host_threads():
+    """All the host cores this process may use.  (torchrun exports OMP_NUM_THREADS=1, so
+    omp_get_max_threads() would say 1; the oracle takes the thread count explicitly.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def rotation_steps():
     return list(range(1, CFG["n1"])) + [g * CFG["n1"] for g in range(1, CFG["n2"])]
 
@@ -132,7 +141,7 @@ def run_reference(args):
     from oracle import oracle as orc
 
     c = CFG
-    threads = orc.max_threads()
+    threads = host_threads()
     moduli = orc.coeff_modulus_create(c["N"], c["bits"])
     o = orc.Oracle(c["N"], moduli)
     rng = np.random.default_rng(1)
@@ -347,7 +356,7 @@ def run_gpu(args):
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
 
-        threads = orc.max_threads()
+        threads = host_threads()
         o = orc.Oracle(c["N"], moduli)
         bk = [None] + [gk[ctx.galois_elt_from_step(k)] for k in range(1, c["n1"])]
         gkeys = [None] + [gk[ctx.galois_elt_from_step(g * c["n1"])] for g in range(1, c["n2"])]
