@@ -173,6 +173,7 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     if (const char *e = getenv("HEGPU_LOGE")) c->loge = atoi(e) == 3 ? 3 : 4;
     if (const char *e = getenv("HEGPU_PARK")) c->use_park = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_FUSED")) c->dh_fused = atoi(e) != 0;
+    if (const char *e = getenv("HEGPU_DH_F64")) c->dh_f64 = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->main_stream = c->stream;
     CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
@@ -1270,21 +1271,26 @@ static void launch_bsgs_inner_n1(hegpu_ctx *c, const BsgsParams &P, u32 n1)
     }
 }
 
-static u32 dh_n2_pad(u32 n2) { return n2 <= 1 ? 1 : n2 <= 2 ? 2 : n2 <= 4 ? 4 : 8; }
+static u32 dh_n2_pad(u32 n2) { return n2 <= 1 ? 1 : n2 <= 2 ? 2 : 4; }  // giant steps per launch
 template <int LT, int N2>
 static int launch_dh_inner(hegpu_ctx *c, const DhInnerParams &P)
 {
     const size_t smem = dh_inner_smem(P.n1, N2, LT);
     auto kern = dh_inner_kernel<LT, N2>;
+    DhInnerParams Q = P;
     static size_t configured[16] = {};
     if (configured[c->device] < smem) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[c->device] = smem;
     }
-    dim3 grid(P.n / DH_TX, LT + 1, (P.B + DH_BCH - 1) / DH_BCH);
-    kern<<<grid, DH_TX * DH_KG, smem, c->stream>>>(P, c->d_mods);
-    c->launches++;
-    CU(cudaGetLastError());
+    dim3 grid(P.n / DH_TX * (LT + 1), 1, (P.B + DH_BCH - 1) / DH_BCH);
+    for (u32 g0 = 0; g0 < P.n2; g0 += N2) {
+        Q.g0 = g0;
+        Q.ng = std::min<u32>(N2, P.n2 - g0);
+        kern<<<grid, DH_TX * DH_KG, smem, c->stream>>>(Q, c->d_mods, c->dh_f64);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
     return HEGPU_OK;
 }
 
@@ -1296,7 +1302,7 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
     const size_t n = c->n, ctw = (size_t)2 * L * n, accw = (size_t)2 * (L + 1) * n;
     if (nrot > (u32)MAXG) INVALID("double-hoisted matvec supports at most 16 rotated giant steps per call");
     const u32 nr1 = std::max<u32>(nrot, 1);
-    const bool fused = c->dh_fused && L <= 4 && n2 <= 8 && dh_inner_smem(n1, dh_n2_pad(n2), L) <= (size_t)110 * 1024;
+    const bool fused = c->dh_fused && L <= 4 && dh_inner_smem(n1, dh_n2_pad(n2), L) <= (size_t)110 * 1024;
     const size_t nbaby = fused ? 0 : n1;  // the rotated ciphertexts only exist in HBM on the unfused path
     auto need = [&](u32 Bc) {
         return align256((size_t)Bc * L * n) + align256((size_t)Bc * L * (L + 1) * n) + align256(inv_scratch_words(c, (size_t)Bc * std::max<u32>(L, 2))) +
@@ -1385,10 +1391,10 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
             Prof pf(c, PK_DH_INNER, (u64)Bn * (L + 1) * n, words * 8);
 #define DH_CASE(LT, N2) case (LT) * 16 + (N2): TRY((launch_dh_inner<LT, N2>(c, P))); break;
             switch (L * 16 + dh_n2_pad(n2)) {
-                DH_CASE(1, 1) DH_CASE(1, 2) DH_CASE(1, 4) DH_CASE(1, 8)
-                DH_CASE(2, 1) DH_CASE(2, 2) DH_CASE(2, 4) DH_CASE(2, 8)
-                DH_CASE(3, 1) DH_CASE(3, 2) DH_CASE(3, 4) DH_CASE(3, 8)
-                DH_CASE(4, 1) DH_CASE(4, 2) DH_CASE(4, 4) DH_CASE(4, 8)
+                DH_CASE(1, 1) DH_CASE(1, 2) DH_CASE(1, 4)
+                DH_CASE(2, 1) DH_CASE(2, 2) DH_CASE(2, 4)
+                DH_CASE(3, 1) DH_CASE(3, 2) DH_CASE(3, 4)
+                DH_CASE(4, 1) DH_CASE(4, 2) DH_CASE(4, 4)
             default: LOGIC("unsupported double-hoisted shape");
             }
 #undef DH_CASE

@@ -292,7 +292,8 @@ __global__ void __launch_bounds__(32 * BSGS_GT) bsgs_inner_kernel(const BsgsPara
 // shared-memory round trip in the main loop, one Montgomery reduction per output word.  The kernel
 // is bound by integer-multiply issue (ncu: fmaheavy pipe 80 % busy), not by HBM: keys, diagonals,
 // digits and outputs cross HBM once (a few hundred MB per launch).
-// grid = (N / 32, L+1, batch chunks), block = 32 * DH_KG.
+// More than 4 giant steps run as several launches of at most 4 (registers hold the accumulators; b_k is
+// rebuilt per launch).  grid = ((N / 32) * (L+1), 1, batch chunks), block = 32 * DH_KG.
 // ---------------------------------------------------------------------------------------
 constexpr int DH_TX = 32, DH_KG = 8, DH_BCH = 32;
 struct DhInnerParams {
@@ -304,33 +305,84 @@ struct DhInnerParams {
     size_t diag_si;
     u64 *u;                // [n2][B][2][L+1][N]
     u32 n1, n2, B, L, K, n;
+    u32 g0, ng;            // this launch accumulates giant steps g0 .. g0+ng-1 (ng <= N2)
 };
 static inline size_t dh_inner_smem(u32 n1, u32 n2, u32 L)
 {
     return ((size_t)n1 * 2 * L + (size_t)n1 * n2) * DH_TX * sizeof(u64) + (size_t)n1 * DH_TX * sizeof(u32);
 }
 
-template <int LT, int N2>
-__global__ void __launch_bounds__(DH_TX * DH_KG, 2) dh_inner_kernel(const DhInnerParams P, const ModConst *__restrict__ mods)
+// exact double of a 32-bit unsigned integer without the conversion unit: 2^52 + x has x in its low word
+__device__ __forceinline__ double u32_to_f64(u32 x) { return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0; }
+// exact integer of a double in [0, 2^52)
+__device__ __forceinline__ u64 f64_to_u64(double v) { return (u64)__double_as_longlong(v + 4503599627370496.0) & 0xFFFFFFFFFFFFFull; }
+
+// Arithmetic policies of dh_inner_kernel (uniform per CTA = per extended limb).
+//  DhArI64: any modulus.  Operands are 64-bit words, products accumulate in 128 bits (4 IMAD.WIDE.U32 +
+//           carries on the integer pipes), one Montgomery reduction per sum.  (A PTX carry-chain form of
+//           the accumulate -- mad.lo.cc / madc.hi.cc with the cross products in their own accumulator --
+//           was measured slower: ptxas fills it with IMAD.MOV register shuffles on the multiplier pipe.)
+//  DhArF64: moduli below 2^40 (the 40-bit data primes).  Every word is split into two 20-bit limbs held
+//           as doubles; the four limb products of a multiply-accumulate are < 2^40 and go into three
+//           column sums (weights 1, 2^20, 2^40) with 4 DFMA on the otherwise idle FP64 pipe; up to 64
+//           products stay below 2^47, far inside the 53-bit mantissa, so the sums are EXACT integers.
+//           They are recombined in integers and Montgomery-reduced exactly like the I64 sums: both
+//           policies return the same canonical residues, bit for bit.
+struct DhArI64 {
+    typedef u64 Opnd;
+    struct Acc {
+        u64 h, l;
+    };
+    static __device__ __forceinline__ u64 stage(u64 v) { return v; }
+    static __device__ __forceinline__ Opnd from_word(u64 v) { return v; }
+    static __device__ __forceinline__ Opnd from_staged(u64 v) { return v; }
+    static __device__ __forceinline__ Acc zero() { return Acc{ 0, 0 }; }
+    static __device__ __forceinline__ void mac(Acc &a, Opnd x, Opnd y) { mac128(a.h, a.l, x, y); }
+    static __device__ __forceinline__ u64 reduce(const Acc &a, const ModConst &m) { return mont_reduce(a.h, a.l, m); }
+    static __device__ __forceinline__ u64 reduce_wide(const Acc &a, const ModConst &m) { return mont_reduce_wide(a.h, a.l, m); }
+};
+struct DhArF64 {
+    struct Opnd {
+        double lo, hi;  // 20-bit limbs
+    };
+    struct Acc {
+        double c0, c1, c2;
+    };
+    static __device__ __forceinline__ u64 stage(u64 v) { return (v & 0xFFFFFull) | ((v >> 20) << 32); }
+    static __device__ __forceinline__ Opnd from_word(u64 v) { return Opnd{ u32_to_f64((u32)v & 0xFFFFFu), u32_to_f64((u32)(v >> 20)) }; }
+    static __device__ __forceinline__ Opnd from_staged(u64 p) { return Opnd{ u32_to_f64((u32)p), u32_to_f64((u32)(p >> 32)) }; }
+    static __device__ __forceinline__ Acc zero() { return Acc{ 0.0, 0.0, 0.0 }; }
+    static __device__ __forceinline__ void mac(Acc &a, const Opnd x, const Opnd y)
+    {
+        a.c0 = __fma_rn(x.lo, y.lo, a.c0);
+        a.c1 = __fma_rn(x.lo, y.hi, a.c1);
+        a.c1 = __fma_rn(x.hi, y.lo, a.c1);
+        a.c2 = __fma_rn(x.hi, y.hi, a.c2);
+    }
+    static __device__ __forceinline__ u64 reduce(const Acc &a, const ModConst &m)
+    {
+        const unsigned __int128 t = (unsigned __int128)f64_to_u64(a.c0) + ((unsigned __int128)f64_to_u64(a.c1) << 20) +
+                                    ((unsigned __int128)f64_to_u64(a.c2) << 40);
+        return mont_reduce((u64)(t >> 64), (u64)t, m);  // t < 64 * 2^80 << q * 2^64
+    }
+    static __device__ __forceinline__ u64 reduce_wide(const Acc &a, const ModConst &m) { return reduce(a, m); }
+};
+
+template <int LT, int N2, class Ar>
+__device__ __forceinline__ void dh_inner_body(const DhInnerParams &P, const ModConst &m, u32 i, u32 x0, u32 b0, u32 b1, u64 *skey, u64 *sdiag,
+                                              u32 *sperm)
 {
-    extern __shared__ __align__(16) u64 dh_smem[];
     constexpr u32 TX = DH_TX, NT = DH_TX * DH_KG, L = LT;
     const u32 n = P.n, n1 = P.n1;
     const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const u32 x0 = blockIdx.x * TX, i = blockIdx.y;
-    const u32 b0 = blockIdx.z * DH_BCH, b1 = min(P.B, b0 + DH_BCH);
     const u32 ki = (i == L) ? P.K - 1 : i;
-    const ModConst m = mods[ki];
-    u64 *skey = dh_smem;                                        // [n1][2L][TX]
-    u64 *sdiag = skey + (size_t)n1 * 2 * L * TX;                 // [n1][N2][TX]
-    u32 *sperm = reinterpret_cast<u32 *>(sdiag + (size_t)n1 * N2 * TX);  // [n1][TX]
     for (u32 idx = threadIdx.x; idx < n1 * 2 * L * TX; idx += NT) {
         const u32 x = idx % TX, r = idx / TX, jc = r % (2 * L), k = r / (2 * L);
-        skey[idx] = k ? __ldg(P.key[k] + ((size_t)jc * P.K + ki) * n + x0 + x) : 0;
+        skey[idx] = k ? Ar::stage(__ldg(P.key[k] + ((size_t)jc * P.K + ki) * n + x0 + x)) : 0;
     }
     for (u32 idx = threadIdx.x; idx < n1 * N2 * TX; idx += NT) {
         const u32 x = idx % TX, r = idx / TX, g = r % N2, k = r / N2;
-        sdiag[idx] = g < P.n2 ? __ldg(P.diag + (size_t)(g * n1 + k) * P.diag_si + (size_t)i * n + x0 + x) : 0;
+        sdiag[idx] = g < P.ng ? Ar::stage(__ldg(P.diag + (size_t)((P.g0 + g) * n1 + k) * P.diag_si + (size_t)i * n + x0 + x)) : 0;
     }
     for (u32 idx = threadIdx.x; idx < n1 * TX; idx += NT) {
         const u32 x = idx % TX, k = idx / TX;
@@ -338,6 +390,7 @@ __global__ void __launch_bounds__(DH_TX * DH_KG, 2) dh_inner_kernel(const DhInne
     }
     __syncthreads();
     const bool data_limb = i < L;
+    const typename Ar::Opnd pm = Ar::from_word(m.pmont);  // 0 for the special prime: no c0 term, b_0[L] = 0
     for (u32 b = b0 + w; b < b1; b += DH_KG) {
         // operand streams of this ciphertext, fixed for all baby steps (only the gathered column
         // changes): src[j] = digit j lifted to limb i (digit i itself is c1's limb i), src[L] = c0's
@@ -356,38 +409,39 @@ __global__ void __launch_bounds__(DH_TX * DH_KG, 2) dh_inner_kernel(const DhInne
             for (int j = 0; j < LT; ++j) d[j] = src[j][xs];
             d[LT] = data_limb ? src[LT][xs] : 0;
         };
-        u64 ah[N2][2], al[N2][2];
+        typename Ar::Acc acc[N2][2];
 #pragma unroll
-        for (int g = 0; g < N2; ++g) ah[g][0] = al[g][0] = ah[g][1] = al[g][1] = 0;
+        for (int g = 0; g < N2; ++g) acc[g][0] = acc[g][1] = Ar::zero();
         u64 d0[LT + 1], d1[LT + 1], d2[LT + 1];
         fetch(0, d0);
         if (n1 > 1) fetch(1, d1);
         // one baby step: start the gathers of step k+2 into `nxt`, then consume `cur`
         auto step = [&](u32 k, const u64 (&cur)[LT + 1], u64 (&nxt)[LT + 1]) {
             if (k + 2 < n1) fetch(k + 2, nxt);
-            u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
-            if (k == 0) {  // b_0 = P * (c0, c1); pmont = 0 for the special prime: b_0[L] = 0
+            typename Ar::Acc s0 = Ar::zero(), s1 = Ar::zero();
+            if (k == 0) {  // b_0 = P * (c0, c1)
                 u64 w1 = cur[0];
 #pragma unroll
                 for (int j = 1; j < LT; ++j) w1 = ((u32)j == i) ? cur[j] : w1;
-                mac128(h0, l0, cur[LT], m.pmont);
-                mac128(h1, l1, w1, m.pmont);
+                Ar::mac(s0, Ar::from_word(cur[LT]), pm);
+                Ar::mac(s1, Ar::from_word(w1), pm);
             } else {
                 const u64 *kp = skey + (size_t)k * 2 * L * TX + lane;
 #pragma unroll
                 for (int j = 0; j < LT; ++j) {
-                    mac128(h0, l0, cur[j], kp[(2 * j) * TX]);
-                    mac128(h1, l1, cur[j], kp[(2 * j + 1) * TX]);
+                    const typename Ar::Opnd dj = Ar::from_word(cur[j]);
+                    Ar::mac(s0, dj, Ar::from_staged(kp[(2 * j) * TX]));
+                    Ar::mac(s1, dj, Ar::from_staged(kp[(2 * j + 1) * TX]));
                 }
-                mac128(h0, l0, cur[LT], m.pmont);
+                Ar::mac(s0, Ar::from_word(cur[LT]), pm);
             }
-            const u64 a0 = mont_reduce(h0, l0, m), a1 = mont_reduce(h1, l1, m);
+            const typename Ar::Opnd a0 = Ar::from_word(Ar::reduce(s0, m)), a1 = Ar::from_word(Ar::reduce(s1, m));
             const u64 *dp = sdiag + (size_t)k * N2 * TX + lane;
 #pragma unroll
             for (int g = 0; g < N2; ++g) {
-                const u64 dg = dp[g * TX];
-                mac128(ah[g][0], al[g][0], a0, dg);
-                mac128(ah[g][1], al[g][1], a1, dg);
+                const typename Ar::Opnd dg = Ar::from_staged(dp[g * TX]);
+                Ar::mac(acc[g][0], a0, dg);
+                Ar::mac(acc[g][1], a1, dg);
             }
         };
         for (u32 k = 0; k < n1; k += 3) {  // the three operand sets rotate by name, not by copying
@@ -397,13 +451,32 @@ __global__ void __launch_bounds__(DH_TX * DH_KG, 2) dh_inner_kernel(const DhInne
         }
 #pragma unroll
         for (int g = 0; g < N2; ++g) {
-            if ((u32)g < P.n2) {
-                u64 *up = P.u + ((((size_t)g * P.B + b) * 2) * (L + 1) + i) * n + x0 + lane;
-                up[0] = mont_reduce_wide(ah[g][0], al[g][0], m);
-                up[(size_t)(L + 1) * n] = mont_reduce_wide(ah[g][1], al[g][1], m);
+            if ((u32)g < P.ng) {
+                u64 *up = P.u + ((((size_t)(P.g0 + g) * P.B + b) * 2) * (L + 1) + i) * n + x0 + lane;
+                up[0] = Ar::reduce_wide(acc[g][0], m);
+                up[(size_t)(L + 1) * n] = Ar::reduce_wide(acc[g][1], m);
             }
         }
     }
+}
+
+template <int LT, int N2>
+__global__ void __launch_bounds__(DH_TX * DH_KG, 2) dh_inner_kernel(const DhInnerParams P, const ModConst *__restrict__ mods, int use_f64)
+{
+    extern __shared__ __align__(16) u64 dh_smem[];
+    constexpr u32 TX = DH_TX, L = LT;
+    // neighbouring CTAs take different limbs of the same tile: the CTAs that share an SM then mix the
+    // integer-pipe policy (60-bit limbs) with the FP64-pipe policy (40-bit limbs)
+    const u32 x0 = (blockIdx.x / (L + 1)) * TX, i = blockIdx.x % (L + 1);
+    const u32 b0 = blockIdx.z * DH_BCH, b1 = min(P.B, b0 + DH_BCH);
+    const ModConst m = mods[(i == L) ? P.K - 1 : i];
+    u64 *skey = dh_smem;                                                // [n1][2L][TX]
+    u64 *sdiag = skey + (size_t)P.n1 * 2 * L * TX;                       // [n1][N2][TX]
+    u32 *sperm = reinterpret_cast<u32 *>(sdiag + (size_t)P.n1 * N2 * TX);  // [n1][TX]
+    if (use_f64 && (m.q >> 40) == 0)
+        dh_inner_body<LT, N2, DhArF64>(P, m, i, x0, b0, b1, skey, sdiag, sperm);
+    else
+        dh_inner_body<LT, N2, DhArI64>(P, m, i, x0, b0, b1, skey, sdiag, sperm);
 }
 
 // sum of `terms` ciphertext batches laid out at batch offsets g*B: out = sum_g src_g
