@@ -39,7 +39,7 @@ def _stale() -> bool:
 
 
 HOST = os.path.join(HERE, "host")
-HOST_SRC = ["ckks_encoder.cpp", "he_operators.cpp", "he_linalg.cpp", "he_fft.cpp"]
+HOST_SRC = ["ckks_encoder.cpp", "he_operators.cpp", "he_linalg.cpp", "he_fft.cpp", "he_math.cpp"]
 HOST_LIB = os.path.join(HERE, "libhe_host.so")
 HOST_TEST = os.path.join(HERE, "he_host_test")
 

@@ -12,6 +12,7 @@
 
 #include "he_fft.h"
 #include "he_linalg.h"
+#include "he_math.h"
 #include "he_util.h"
 
 using namespace he::gpu;
@@ -66,6 +67,7 @@ int main(int argc, char **argv)
         std::ifstream f(argv[1], std::ios::binary);
         const std::string cmd = argv[2];
         auto arg = [&](int i) { return i < argc ? std::atoi(argv[i]) : 0; };
+        auto argd = [&](int i) { return i < argc ? std::atof(argv[i]) : 0.0; };
         const std::uint32_t n = rd<std::uint32_t>(f), K = rd<std::uint32_t>(f);
         const auto moduli = rdv(f, K);
         SEALContext ctx(n, moduli);
@@ -175,6 +177,14 @@ int main(int argc, char **argv)
             he::util::reach_chain_level(ctx, cencd, eval, u, t);
             out.push_back(u);
             wr<std::uint32_t>(*new std::ofstream("/dev/null"), (std::uint32_t)he::util::get_chain_index(ctx, t));
+        } else if (cmd == "math") {  // args: which(0 signed_inv, 1 inv_sqrt_twice, 2 sqrt, 3 abs) a iter_num
+            const int which = arg(4);
+            const double a = argd(5);
+            const std::size_t iters = (std::size_t)arg(6);
+            if (which == 0) out.push_back(he::math::signed_inv(cencd, eval, rk, cts[0], a, iters));
+            else if (which == 1) out.push_back(he::math::inv_sqrt_twice(cencd, eval, rk, cts[0], a, iters));
+            else if (which == 2) out.push_back(he::math::sqrt(ctx, cencd, eval, rk, cts[0], a, iters));
+            else out.push_back(he::math::abs(ctx, cencd, eval, rk, cts[0], a, iters));
         } else if (cmd == "errors") {
             // exception types and messages must be SEAL's
             int ok = 0;

@@ -265,3 +265,108 @@ def test_drop_chain_levels(tmp_path):
     # SEAL's real-scalar encode: round(1 * scale) in every slot of every limb
     for i, q in enumerate(S.moduli[:3]):
         assert np.all(pts[-1][0][i] == np.uint64(2**40 % q))
+
+
+class _Replay:
+    """The reference's he_math.cpp statement by statement on the CPU oracle (an independent restatement:
+    written from src/core/he_math.cpp:22-269, not from host/he_math.cpp).  A value is (ct, scale)."""
+
+    def __init__(self, S):
+        self.S, self.o, self.q = S, S.o, S.moduli
+
+    def const(self, value, v):
+        ct, sc = v
+        return self.S.enc.encode_scalar(value, sc, ct.shape[1])
+
+    def mul_const_rescale(self, v, value):
+        ct, sc = v
+        out = self.o.rescale(self.o.multiply_plain(ct, self.const(value, v)))
+        return out, sc * sc / self.q[ct.shape[1] - 1]
+
+    def add_const(self, v, value):
+        return self.o.add_plain(v[0], self.const(value, v)), v[1]
+
+    def sub_const(self, v, value):
+        return self.o.sub_plain(v[0], self.const(value, v)), v[1]
+
+    def mul_relin_rescale(self, a, b):
+        ct = self.o.rescale(self.o.relinearize(self.o.multiply(a[0], b[0]), self.S.rk))
+        return ct, a[1] * b[1] / self.q[a[0].shape[1] - 1]
+
+    def square_relin_rescale(self, a):
+        ct = self.o.rescale(self.o.relinearize(self.o.square(a[0]), self.S.rk))
+        return ct, a[1] * a[1] / self.q[a[0].shape[1] - 1]
+
+    def signed_inv(self, x, a, iters):  # he_math.cpp:22-90
+        y = self.add_const(self.mul_const_rescale(x, -a * a), 2 * a)
+        if iters == 1:
+            return y
+        t = self.mul_const_rescale(x, a)
+        one = self.const(1, t)
+        t = (self.o.sub_plain(t[0], one), t[1])
+        y = (self.o.rescale(self.o.multiply_plain(y[0], one)), y[1] * t[1] / self.q[y[0].shape[1] - 1])
+        for _ in range(1, iters):
+            t = self.square_relin_rescale(t)
+            y = self.mul_relin_rescale(y, self.add_const(t, 1))
+        return y
+
+    def inv_sqrt_twice(self, x, a, iters):  # he_math.cpp:95-160 (the compiled "#if 1" branch)
+        y = self.add_const(self.mul_const_rescale(x, -a * a * a), 1.5 * a)
+        for i in range(1, iters):
+            yp = y
+            y = self.mul_const_rescale(self.mul_const_rescale(y, 1.5), 1)
+            for _ in range(2 if i > 1 else 1):
+                x = self.mul_const_rescale(x, 1)
+            xy = self.mul_relin_rescale(x, yp)
+            yp = self.mul_relin_rescale(self.square_relin_rescale(yp), xy)
+            y = (self.o.sub(y[0], yp[0]), y[1])
+        return y
+
+    def sqrt(self, x, a, iters):  # he_math.cpp:210-232
+        y = self.inv_sqrt_twice(x, 1 / a / np.sqrt(2), iters)
+        sx = self.mul_const_rescale(x, np.sqrt(2))
+        while sx[0].shape[1] > y[0].shape[1]:
+            sx = self.mul_const_rescale(sx, 1)
+        return self.mul_relin_rescale(y, sx)
+
+    def abs(self, x, a, iters):  # he_math.cpp:237-269
+        x2 = self.square_relin_rescale(x)
+        y = self.inv_sqrt_twice(x2, 1 / a / np.sqrt(2), iters)
+        x2 = self.mul_const_rescale(x2, np.sqrt(2))
+        while x2[0].shape[1] > y[0].shape[1]:
+            x2 = self.mul_const_rescale(x2, 1)
+        return self.mul_relin_rescale(y, x2)
+
+
+@pytest.mark.parametrize("which,name,iters", [(0, "signed_inv", 4), (0, "signed_inv", 1), (1, "inv_sqrt_twice", 3), (2, "sqrt", 3), (3, "abs", 3)])
+def test_he_math(tmp_path, which, name, iters):
+    """he::math (SURVEY 8f N3) through the C++ host mirror: bit-identical to the reference's statement
+    sequence replayed on the oracle, and close to the real function after decryption."""
+    n = 8192
+    S = setup(n, (60,) + (40,) * 7 + (60,))
+    sc, L, a = 2.0**40, 8, 1.0
+    rng = np.random.default_rng(70 + which)
+    slots = n // 2
+    if name == "signed_inv":
+        x = rng.uniform(0.6, 1.4, slots)
+        ref = 1 / x
+    elif name == "inv_sqrt_twice":
+        x = rng.uniform(0.4, 0.6, slots)
+        ref = 1 / np.sqrt(2 * x)
+    elif name == "sqrt":
+        x = rng.uniform(0.8, 1.2, slots)
+        ref = np.sqrt(x)
+    else:
+        x = rng.uniform(0.8, 1.2, slots) * rng.choice([-1.0, 1.0], slots)
+        ref = np.abs(x)
+    ct = S.encrypt(x, sc, L, seed=which)
+    outs, _, _, _ = run(tmp_path, S, "math", [which, a, iters], cts=[(ct, sc)], rk=True)
+    want, want_scale = getattr(_Replay(S), name)((ct, sc), a, iters)
+    got, got_scale = outs[0]
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+    assert abs(got_scale / want_scale - 1) < 1e-12
+    dec = S.decrypt(got, got_scale).real
+    # truncation error of the iteration itself dominates: 0.4^(2^iters) for the product form, quadratic Newton otherwise
+    tol = {("signed_inv", 4): 1e-5, ("signed_inv", 1): 0.3, ("inv_sqrt_twice", 3): 2e-3, ("sqrt", 3): 2e-3, ("abs", 3): 5e-3}[(name, iters)]
+    assert np.max(np.abs(dec - ref)) < tol
