@@ -1104,6 +1104,34 @@ static int ks_inner(hegpu_ctx *c, KsPlan &pl)
     CU(cudaGetLastError());
     return HEGPU_OK;
 }
+// step 3 for lazy giant steps: out = init + sum over the plan's groups of the key inner products
+static int ks_inner_sum(hegpu_ctx *c, KsPlan &pl, const u64 *init, u64 *out)
+{
+    const KsParams &P = pl.P;
+    const u32 L = P.L, B = P.B, ngroups = P.ngroups;
+    if (L > 4 || P.hoisted) {  // generic shapes: one accumulator per group, then the group sum
+        TRY(ks_inner(c, pl));
+        const size_t total = (size_t)B * 2 * (L + 1) * c->n;
+        Prof pf(c, PK_ELEMENTWISE, total, total * 8 * (ngroups + 1 + (init ? 1 : 0)));
+        acc_group_sum_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(P.acc, init, out, ngroups, B, L, c->K, c->n, c->d_mods);
+        c->launches++;
+        CU(cudaGetLastError());
+        return HEGPU_OK;
+    }
+    const size_t total = (size_t)B * (L + 1) * c->n;
+    // per (b,i,x): L digits per group read, 2 written (+2 init); keys read once per batch chunk
+    Prof pf(c, PK_KS_INNER, total * ngroups, total * 8 * ((u64)ngroups * L + 2 + (init ? 2 : 0)) + (u64)ngroups * (L + 1) * c->n * 16 * L);
+    dim3 grid((c->n + 255) / 256, L + 1, (B + KS_INNER_BCHUNK - 1) / KS_INNER_BCHUNK);
+    switch (L) {
+    case 1: ks_inner_sum_kernel<1><<<grid, 256, 0, c->stream>>>(P, init, out, c->d_mods); break;
+    case 2: ks_inner_sum_kernel<2><<<grid, 256, 0, c->stream>>>(P, init, out, c->d_mods); break;
+    case 3: ks_inner_sum_kernel<3><<<grid, 256, 0, c->stream>>>(P, init, out, c->d_mods); break;
+    default: ks_inner_sum_kernel<4><<<grid, 256, 0, c->stream>>>(P, init, out, c->d_mods); break;
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    return HEGPU_OK;
+}
 // steps 4-5: mod-down by P with rounding, add the base ciphertext, write out
 static int ks_moddown(hegpu_ctx *c, KsPlan &pl)
 {
@@ -1496,15 +1524,7 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
             KsPlan pl;
             TRY(ks_setup(c, pl, gs, nrot, Bn, L, 1, false, false, ap));
             TRY(ks_decompose(c, pl));
-            TRY(ks_inner(c, pl));
-            {
-                const size_t total = (size_t)Bn * accw;
-                Prof pf(c, PK_ELEMENTWISE, total, total * 8 * (nrot + 1 + first_rot));
-                acc_group_sum_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(pl.P.acc, first_rot ? u : nullptr, accsum, nrot, Bn, L, c->K,
-                                                                               c->n, c->d_mods);
-                c->launches++;
-                CU(cudaGetLastError());
-            }
+            TRY(ks_inner_sum(c, pl, first_rot ? u : nullptr, accsum));
             {   // base = (sum_r pi_r(v0_r), 0)
                 BS.first = view_of(v, 0);
                 BS.has_first = 0;
@@ -1684,14 +1704,7 @@ extern "C" int hegpu_matvec_bsgs_range(hegpu_ctx *c, hegpu_ct *out, const hegpu_
             KsPlan pl;
             TRY(ks_setup(c, pl, gs, nrot, Bn, L, 1, false, false, ap));
             TRY(ks_decompose(c, pl));
-            TRY(ks_inner(c, pl));
-            {
-                const size_t total = (size_t)Bn * 2 * (L + 1) * n;
-                Prof pf(c, PK_ELEMENTWISE, total, total * 8 * (nrot + 1));
-                acc_group_sum_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(pl.P.acc, nullptr, accsum, nrot, Bn, L, c->K, c->n, c->d_mods);
-                c->launches++;
-                CU(cudaGetLastError());
-            }
+            TRY(ks_inner_sum(c, pl, nullptr, accsum));
             {   // base = [inner_0 if unrotated] + sum_r pi_r(inner_r.c0)
                 BS.first = view_of(inner, 0);
                 BS.has_first = first_rot;

@@ -72,6 +72,49 @@ __global__ void __launch_bounds__(256) ks_inner_kernel(const KsParams P, const M
     }
 }
 
+// K7 step 3 for lazy giant steps: the key inner products of `ngroups` rotations of the SAME batch are
+// summed in the extended basis right here, out[b][c][i] = init[b][c][i] + sum_g <digits_g, key_g>[c][i],
+// instead of writing one accumulator per rotation and summing them in a second pass (saves
+// 2 * ngroups accumulator-sized HBM passes).  Each group's sum is reduced before it is added, exactly as
+// the two-kernel form did, so the result is bit-identical.  Not for hoisted plans.
+template <int LT>
+__global__ void __launch_bounds__(256) ks_inner_sum_kernel(const KsParams P, const u64 *__restrict__ init, u64 *__restrict__ out,
+                                                           const ModConst *__restrict__ mods)
+{
+    const u32 L = LT, n = P.n;
+    const u32 x = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 i = blockIdx.y;
+    const u32 b0 = blockIdx.z * KS_INNER_BCHUNK;
+    const u32 b1 = min(P.B, b0 + KS_INNER_BCHUNK);
+    if (x >= n) return;
+    const u32 ki = (i == L) ? P.K - 1 : i;
+    const ModConst m = mods[ki];
+    const size_t kstride = (size_t)P.K * n;
+    for (u32 b = b0; b < b1; ++b) {
+        const size_t o0 = (((size_t)b * 2 + 0) * (L + 1) + i) * n + x, o1 = o0 + (size_t)(L + 1) * n;
+        u64 s0 = init ? init[o0] : 0, s1 = init ? init[o1] : 0;
+        for (u32 g = 0; g < P.ngroups; ++g) {
+            const CtView &v = P.in[g];
+            const u32 *pm = P.perm[g];
+            const u32 xs = (i < L && pm) ? __ldg(pm + x) : x;
+            const u64 *key = P.key[g] + (size_t)ki * n + x;
+            const size_t e = (size_t)g * P.B + b;
+            u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+#pragma unroll
+            for (int j = 0; j < LT; ++j) {
+                const u64 d = ((u32)j == i) ? v.p[b * v.sb + P.target_poly * v.sp + j * v.sl + xs]
+                                            : P.ext[((e * L + j) * (L + 1) + i) * n + x];
+                mac128(h0, l0, d, __ldg(key + (size_t)(2 * j) * kstride));      // L1-resident across the batch chunk
+                mac128(h1, l1, d, __ldg(key + (size_t)(2 * j + 1) * kstride));
+            }
+            s0 = addmod(s0, mont_reduce(h0, l0, m), m.q);
+            s1 = addmod(s1, mont_reduce(h1, l1, m), m.q);
+        }
+        out[o0] = s0;
+        out[o1] = s1;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // element-wise kernels over (b, p, l, x).  b's batch stride may be 0 (broadcast).
 // ---------------------------------------------------------------------------------------
