@@ -117,7 +117,7 @@ void select_slot(hegpu_ctx *c, int slot)
     c->cur_slot = slot;
     c->park = c->park_slots[slot];
     c->park_words = c->park_words_slots[slot];
-    c->stream = slot ? c->aux_stream : c->main_stream;
+    c->stream = slot ? c->aux_stream[slot] : c->main_stream;
 }
 struct SlotGuard {  // composites return to slot 0 on every exit path
     hegpu_ctx *c;
@@ -176,10 +176,12 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     if (const char *e = getenv("HEGPU_DH_F64")) c->dh_f64 = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->main_stream = c->stream;
-    CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    if (const char *e = getenv("HEGPU_STREAMS")) c->dual_stream = atoi(e) >= 2;
+    for (int sl = 1; sl < hegpu_ctx::MAX_SLOTS; ++sl) {
+        CU(cudaStreamCreateWithFlags(&c->aux_stream[sl], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_join[sl], cudaEventDisableTiming));
+    }
+    if (const char *e = getenv("HEGPU_STREAMS")) c->n_slots = std::min(std::max(atoi(e), 1), (int)hegpu_ctx::MAX_SLOTS);
     CU(cudaStreamCreateWithFlags(&c->copy_h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_d2h, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_fence, cudaEventDisableTiming));
@@ -297,12 +299,14 @@ extern "C" int hegpu_ctx_destroy(hegpu_ctx *c)
     cudaFree(c->arena.base);
     cudaFree(c->stage);
     select_slot(c, 0);
-    cudaStreamSynchronize(c->aux_stream);
     cudaFree(c->park);
-    cudaFree(c->park_slots[1]);
-    cudaStreamDestroy(c->aux_stream);
     cudaEventDestroy(c->ev_fork);
-    cudaEventDestroy(c->ev_join);
+    for (int sl = 1; sl < hegpu_ctx::MAX_SLOTS; ++sl) {
+        cudaStreamSynchronize(c->aux_stream[sl]);
+        cudaFree(c->park_slots[sl]);
+        cudaStreamDestroy(c->aux_stream[sl]);
+        cudaEventDestroy(c->ev_join[sl]);
+    }
     cudaStreamSynchronize(c->copy_h2d);
     cudaStreamSynchronize(c->copy_d2h);
     cudaStreamDestroy(c->copy_h2d);
@@ -1340,27 +1344,27 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
     };
     // two execution slots: alternate batch chunks go to the main and the auxiliary stream (own scratch
     // each), so the small grids of one chunk (a single wave of NTT CTAs) overlap the other chunk's kernels
-    const int NS = (c->dual_stream && !c->profiling && B >= 32) ? 2 : 1;
-    u32 Bc = NS == 2 ? (B + 1) / 2 : B;
+    const int NS = (!c->profiling && B >= 16u * (u32)c->n_slots) ? c->n_slots : 1;
+    u32 Bc = (B + NS - 1) / NS;
     while (Bc > 1 && need(Bc) * NS > c->ws_budget) Bc = (Bc + 1) / 2;
     TRY(arena_reserve(c, need(Bc) * NS));
     const u64 *dmont;
     TRY(pt_montgomery(const_cast<hegpu_pt *>(diags), &dmont));
     SlotGuard guard{ c };
-    if (NS == 2) {
+    if (NS > 1) {
         const size_t park_need = (size_t)nr1 * Bc * (L * L + 2 * L) * (n / 2);  // largest NTT launch of a chunk
-        for (int sl = 0; sl < 2; ++sl) {
+        for (int sl = 0; sl < NS; ++sl) {
             select_slot(c, sl);
             if (c->logn == 14 && c->use_park) TRY(park_reserve(c, park_need));
         }
         select_slot(c, 0);
         CU(cudaEventRecord(c->ev_fork, c->main_stream));
-        CU(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        for (int sl = 1; sl < NS; ++sl) CU(cudaStreamWaitEvent(c->aux_stream[sl], c->ev_fork, 0));
     }
     u32 chunk_no = 0;
     for (u32 b0 = 0; b0 < B; b0 += Bc, ++chunk_no) {
         const u32 Bn = std::min(Bc, B - b0);
-        const int slot = NS == 2 ? (int)(chunk_no & 1u) : 0;
+        const int slot = (int)(chunk_no % (u32)NS);
         select_slot(c, slot);
         ArenaPlan ap{ c };
         ap.off = (size_t)slot * need(Bc);
@@ -1551,9 +1555,9 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
             TRY(rescale_views(c, out->view_at(b0), dst, Bn, 2, L, ar));
         }
     }
-    if (NS == 2) {
-        CU(cudaEventRecord(c->ev_join, c->aux_stream));
-        CU(cudaStreamWaitEvent(c->main_stream, c->ev_join, 0));
+    for (int sl = 1; sl < NS; ++sl) {
+        CU(cudaEventRecord(c->ev_join[sl], c->aux_stream[sl]));
+        CU(cudaStreamWaitEvent(c->main_stream, c->ev_join[sl], 0));
     }
     return HEGPU_OK;
 }

@@ -85,12 +85,13 @@ struct hegpu_ctx {
     size_t park_words = 0;
     // second execution slot: composites run alternate batch chunks on `stream` and `aux_stream` so that
     // small grids of one chunk overlap the kernels of the other; each slot has its own park scratch
-    cudaStream_t main_stream = nullptr, aux_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    u64 *park_slots[2] = { nullptr, nullptr };
-    size_t park_words_slots[2] = { 0, 0 };
+    static constexpr int MAX_SLOTS = 4;
+    cudaStream_t main_stream = nullptr, aux_stream[MAX_SLOTS] = {};  // aux_stream[0] unused (slot 0 = main)
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_SLOTS] = {};
+    u64 *park_slots[MAX_SLOTS] = {};
+    size_t park_words_slots[MAX_SLOTS] = {};
     int cur_slot = 0;
-    int dual_stream = 1;  // HEGPU_STREAMS=1 disables
+    int n_slots = 2;  // HEGPU_STREAMS=k (1..4); 1 disables
     int use_park = 1;
     u64 *stage = nullptr;  // host<->device staging
     size_t stage_words = 0;
@@ -165,7 +166,7 @@ int arena_reserve(hegpu_ctx *c, size_t bytes);
 int park_reserve(hegpu_ctx *c, size_t words);
 int stage_reserve(hegpu_ctx *c, size_t words);
 int ew_grid(hegpu_ctx *c, size_t total);
-void select_slot(hegpu_ctx *c, int slot);  // make `slot` (0 = main stream, 1 = aux stream) the one launches go to
+void select_slot(hegpu_ctx *c, int slot);  // make `slot` (0 = main stream, k = aux stream k) the one launches go to
 
 struct ArenaPlan {  // first pass sizes the scratch, second pass hands out pointers
     hegpu_ctx *c;
