@@ -28,7 +28,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -50,39 +49,45 @@ def tolerance(n_terms, N, scale):
     return n_terms * 3.2 * N**1.5 / (8.0 * scale)
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md): one
+    `nvidia-smi -lms 50` child that streams CSV rows while the steps run."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        super().__init__(daemon=True)
-        self.device, self.rows, self.stop_flag = device, [], threading.Event()
+        self.device, self.proc = device, None
 
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def summary(self):
-        self.stop_flag.set()
-        self.join(timeout=6)
-        if not self.rows:
+        rows = []
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+                rows = [[x.strip() for x in ln.split(",")] for ln in out.splitlines() if ln.count(",") >= 6]
+            except Exception:
+                rows = []
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        power = [float(r[2]) if r[2].replace(".", "").isdigit() else 0.0 for r in rows]
+        pmax = max(power) if power else 0.0
+        loaded = [r for r, p in zip(rows, power) if p >= 0.6 * pmax] or rows  # samples taken while the steps ran
+        sm = sorted(float(r[0]) for r in loaded if r[0].replace(".", "").isdigit())
         reasons = []
         for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
-            if any(r[col].lower() == "active" for r in self.rows if len(r) > col):
+            if any(r[col].lower() == "active" for r in rows if len(r) > col):
                 reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "samples": len(rows), "samples_under_load": len(loaded), "power_w_max": pmax or None,
+                "window": "resident + end-to-end timed regions, 50 ms period; sm_mhz = median of the samples under load"}
 
 
 def measured_peak_gbs():
@@ -258,7 +263,6 @@ def run_gpu(args):
     l0 = ctx.launches
     ms = timed(step, args.steps)
     launches = ctx.launches - l0
-    clocks = sampler.summary()
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- e2e: pinned host buffers, H2D + matvec + D2H every step, through the C ABI's asynchronous
@@ -293,6 +297,7 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
     barrier()
+    clocks = sampler.summary()
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
     for ho in h_out:
         assert np.array_equal(ho.numpy().view(np.uint64), got), "e2e path result differs from the resident path"
