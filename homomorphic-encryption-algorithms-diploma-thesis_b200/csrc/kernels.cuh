@@ -32,6 +32,14 @@ struct MdConst {
 // the load / store functions of that limb polynomial.
 // ---------------------------------------------------------------------------------------
 
+// v mod m for a canonical residue v of the modulus `from`: nothing when from <= m, one conditional
+// subtraction when from < 2m (both 60-bit primes of a chain), Barrett otherwise.  Uniform per CTA.
+__device__ __forceinline__ u64 rebase(u64 v, u64 from, const ModConst &m)
+{
+    if (from <= m.q) return v;
+    return (from >> 1) < m.q ? csub(v, m.q) : barrett64(v, m);
+}
+
 // plain transform of `count` limb polynomials [count][N] (measurement API, host tooling)
 struct PlainJob {
     static constexpr bool PIPE = true;  // software-pipelined first-pass loads (no epilogue operands -> no spills)
@@ -115,7 +123,7 @@ struct KsLiftJob {
     {
         u32 e, dj, di;
         split(j, e, dj, di);
-        return (mods[dj].q > m.q) ? barrett64(v, m) : v;
+        return rebase(v, mods[dj].q, m);
     }
     __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &) const
     {
@@ -161,8 +169,7 @@ struct KsModDownJob {
     __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const { return P.t[(size_t)(j / P.L) * P.n + i]; }
     __device__ __forceinline__ u64 load_fix(u32 j, u64 v, const ModConst &m) const
     {
-        if (mods[P.K - 1].q > m.q) v = barrett64(v, m);
-        return submod(v, md[j % P.L].halfmod, m.q);
+        return submod(rebase(v, mods[P.K - 1].q, m), md[j % P.L].halfmod, m.q);
     }
     struct Ops {
         u64 acc, base;
@@ -209,8 +216,7 @@ struct RescaleJob {
     __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const { return t[(size_t)(j / Lm1) * n + i]; }
     __device__ __forceinline__ u64 load_fix(u32 j, u64 v, const ModConst &m) const
     {
-        if (mods[drop_mod].q > m.q) v = barrett64(v, m);
-        return submod(v, md[j % Lm1].halfmod, m.q);
+        return submod(rebase(v, mods[drop_mod].q, m), md[j % Lm1].halfmod, m.q);
     }
     struct Ops {
         u64 av;

@@ -381,8 +381,13 @@ struct DhArI64 {
     static __device__ __forceinline__ Opnd from_staged(u64 v) { return v; }
     static __device__ __forceinline__ Acc zero() { return Acc{ 0, 0 }; }
     static __device__ __forceinline__ void mac(Acc &a, Opnd x, Opnd y) { mac128(a.h, a.l, x, y); }
-    static __device__ __forceinline__ u64 reduce(const Acc &a, const ModConst &m) { return mont_reduce(a.h, a.l, m); }
-    static __device__ __forceinline__ u64 reduce_wide(const Acc &a, const ModConst &m) { return mont_reduce_wide(a.h, a.l, m); }
+    // b_k only feeds further products: below 2q is enough (n1 <= 32 products of a value < 2q < 2^61 and a
+    // canonical diagonal word stay below 2^126)
+    static __device__ __forceinline__ u64 reduce(const Acc &a, const ModConst &m) { return mont_reduce_lazy(a.h, a.l, m); }
+    static __device__ __forceinline__ u64 reduce_wide(const Acc &a, const ModConst &m)
+    {
+        return csub(mont_reduce_wide(a.h, a.l, m), m.q);  // sum < 4 * q * 2^64: one more subtraction than the canonical-operand bound
+    }
 };
 struct DhArF64 {
     struct Opnd {
@@ -406,9 +411,9 @@ struct DhArF64 {
     {
         const unsigned __int128 t = (unsigned __int128)f64_to_u64(a.c0) + ((unsigned __int128)f64_to_u64(a.c1) << 20) +
                                     ((unsigned __int128)f64_to_u64(a.c2) << 40);
-        return mont_reduce((u64)(t >> 64), (u64)t, m);  // t < 64 * 2^80 << q * 2^64
+        return mont_reduce_lazy((u64)(t >> 64), (u64)t, m);  // t < 64 * 2^82 << q * 2^64; result < 2q < 2^41
     }
-    static __device__ __forceinline__ u64 reduce_wide(const Acc &a, const ModConst &m) { return reduce(a, m); }
+    static __device__ __forceinline__ u64 reduce_wide(const Acc &a, const ModConst &m) { return csub(reduce(a, m), m.q); }
 };
 
 template <int LT, int N2, class Ar>

@@ -87,6 +87,14 @@ __device__ __forceinline__ u64 mont_reduce(u64 hi, u64 lo, const ModConst &m)
     return csub(r, m.q);
 }
 
+// Montgomery reduction without the final conditional subtraction: congruent to (hi:lo) * 2^-64 and
+// below 2q for hi:lo < q * 2^64 -- enough when the result is only an operand of further products
+__device__ __forceinline__ u64 mont_reduce_lazy(u64 hi, u64 lo, const ModConst &m)
+{
+    const u64 t = lo * m.qinv_neg;
+    return hi + __umul64hi(t, m.q) + (lo != 0 ? 1ull : 0ull);
+}
+
 // same for sums of up to 32 products of canonical residues (hi:lo < 2 * q * 2^64): result < 3q before
 // the two conditional subtractions
 __device__ __forceinline__ u64 mont_reduce_wide(u64 hi, u64 lo, const ModConst &m)
