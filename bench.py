@@ -134,6 +134,21 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def bind_to_gpu_numa_node(device):
+    """Pin this rank's host threads to the CPU cores next to its GPU (NVML's ideal affinity), so that the
+    pinned staging buffers it allocates afterwards are first-touched on that NUMA node: with 8 ranks the
+    host<->device copies of the end-to-end path otherwise cross the socket interconnect."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def rotation_steps():
     return list(range(1, CFG["n1"])) + [g * CFG["n1"] for g in range(1, CFG["n2"])]
 
@@ -200,6 +215,7 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None  # N = 1 keeps every host core for the CPU baseline
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -352,7 +368,8 @@ def run_gpu(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "matvecs/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(cts.nbytes),
                 "d2h_bytes_per_step": int(h_out_numel * 8),
-                "pipeline": "double-buffered hegpu_ct_upload_async / download_async, host-clock timed"},
+                "pipeline": "double-buffered hegpu_ct_upload_async / download_async, host-clock timed",
+                "host_cores_bound_per_rank": numa},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
