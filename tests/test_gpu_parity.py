@@ -308,6 +308,32 @@ def test_matvec_bsgs_double_hoisted(hg, n, dim, n1, n2):
         ctx.matvec_bsgs(out, X, D, min(n1, 16), n2, hoist=True)
 
 
+def test_matvec_double_hoisted_two_execution_slots(hg):
+    """Batches of 32 or more ciphertexts are split into chunks that run on two streams with separate
+    scratch (and an uneven last chunk): every ciphertext must still match the oracle bit for bit, also
+    when the same context is used again right away (scratch reuse across calls)."""
+    n, n1, n2, L, B = 4096, 4, 3, 2, 41
+    S = setup(n, (36, 36, 37))
+    ctx = make_ctx(hg, S)
+    rng = np.random.default_rng(23)
+    scale = 2.0**15
+    cts = rand_residues(rng, S.moduli[:L], (B, 2), n)
+    ptsx = rand_residues(rng, S.moduli[:L] + [S.moduli[-1]], (n1 * n2,), n)
+    bsteps, gsteps = list(range(1, n1)), [g * n1 for g in range(1, n2)]
+    gk = S.gk(bsteps + gsteps)
+    ctx.load_galois_keys(gk)
+    bk = [None] + [gk[orc.galois_elt_from_step(n, s)] for s in bsteps]
+    gkeys = [None] + [gk[orc.galois_elt_from_step(n, s)] for s in gsteps]
+    X = ctx.upload_ct(cts, scale, size_cap=2, L_cap=L)
+    D = ctx.upload_pt_ext(ptsx, scale)
+    out, out2 = ctx.ct(B, 2, L), ctx.ct(B, 2, L)
+    want = S.o.matvec_bsgs(cts, n1, n2, ptsx, bk, gkeys, threads=4, dh=True)
+    ctx.matvec_bsgs(out, X, D, n1, n2, dh=True)
+    ctx.matvec_bsgs(out2, X, D, n1, n2, dh=True)  # enqueued while the first call may still be running
+    assert np.array_equal(out.download(), want)
+    assert np.array_equal(out2.download(), want)
+
+
 @pytest.mark.parametrize("case_b", [False, True])
 def test_bmatmul_reference_loop_order(hg, case_b):
     """BatchedMatrix::matmul (he_linalg.cpp:943-1006) restated on the oracle in the reference's own
