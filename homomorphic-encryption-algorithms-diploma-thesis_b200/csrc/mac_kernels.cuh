@@ -362,9 +362,7 @@ __device__ __forceinline__ u64 f64_to_u64(double v) { return (u64)__double_as_lo
 
 // Arithmetic policies of dh_inner_kernel (uniform per CTA = per extended limb).
 //  DhArI64: any modulus.  Operands are 64-bit words, products accumulate in 128 bits (4 IMAD.WIDE.U32 +
-//           carries on the integer pipes), one Montgomery reduction per sum.  (A PTX carry-chain form of
-//           the accumulate -- mad.lo.cc / madc.hi.cc with the cross products in their own accumulator --
-//           was measured slower: ptxas fills it with IMAD.MOV register shuffles on the multiplier pipe.)
+//           three IADD3, see mac128), one Montgomery reduction per sum.
 //  DhArF64: moduli below 2^40 (the 40-bit data primes).  Every word is split into two 20-bit limbs held
 //           as doubles; the four limb products of a multiply-accumulate are < 2^40 and go into three
 //           column sums (weights 1, 2^20, 2^40) with 4 DFMA on the otherwise idle FP64 pipe; up to 64

@@ -69,13 +69,36 @@ __device__ __forceinline__ u64 mulmod(u64 a, u64 b, const ModConst &m)
     return barrett128(__umul64hi(a, b), a * b, m);
 }
 
-// 128-bit accumulate acc += a*b (one 4-IMAD.WIDE product with carry chains)
-__device__ __forceinline__ void mac128(u64 &hi, u64 &lo, u64 a, u64 b)
+// 128-bit accumulate (hi:lo) += x*y, written as PTX carry chains over the 32-bit halves: ptxas turns each
+// mad.lo.cc / madc.hi.cc pair into ONE IMAD.WIDE.U32 with accumulate and carry, so a product costs the four
+// multiplies + three IADD3 on the ALU pipe.  (The plain `unsigned __int128` form compiles to the same four
+// multiplies plus ~7 add / move instructions, a third of them IMAD.X / IMAD.MOV on the multiplier pipe
+// that bounds the multiply-accumulate kernels: measured 9 % slower in dh_inner_kernel.)
+__device__ __forceinline__ void mac128(u64 &hi, u64 &lo, u64 x, u64 y)
 {
-    unsigned __int128 acc = ((unsigned __int128)hi << 64) | lo;
-    acc += (unsigned __int128)a * b;
-    lo = (u64)acc;
-    hi = (u64)(acc >> 64);
+    asm("{\n\t"
+        ".reg .u32 x0, x1, y0, y1, a0, a1, a2, a3, t0, t1, c;\n\t"
+        "mov.b64 {x0, x1}, %2;\n\t"
+        "mov.b64 {y0, y1}, %3;\n\t"
+        "mov.b64 {a0, a1}, %0;\n\t"
+        "mov.b64 {a2, a3}, %1;\n\t"
+        "mad.lo.cc.u32  a0, x0, y0, a0;\n\t"
+        "madc.hi.cc.u32 a1, x0, y0, a1;\n\t"
+        "madc.lo.cc.u32 a2, x1, y1, a2;\n\t"
+        "madc.hi.u32    a3, x1, y1, a3;\n\t"
+        "mul.lo.u32     t0, x0, y1;\n\t"
+        "mul.hi.u32     t1, x0, y1;\n\t"
+        "mad.lo.cc.u32  t0, x1, y0, t0;\n\t"
+        "madc.hi.cc.u32 t1, x1, y0, t1;\n\t"
+        "addc.u32       c, 0, 0;\n\t"
+        "add.cc.u32     a1, a1, t0;\n\t"
+        "addc.cc.u32    a2, a2, t1;\n\t"
+        "addc.u32       a3, a3, c;\n\t"
+        "mov.b64 %0, {a0, a1};\n\t"
+        "mov.b64 %1, {a2, a3};\n\t"
+        "}"
+        : "+l"(lo), "+l"(hi)
+        : "l"(x), "l"(y));
 }
 
 // Montgomery reduction: (hi:lo) * 2^-64 mod q, canonical; needs hi:lo < q * 2^64.
