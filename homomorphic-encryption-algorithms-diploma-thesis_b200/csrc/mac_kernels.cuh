@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(32 * BSGS_GT) bsgs_inner_kernel(const BsgsPara
 // More than 4 giant steps run as several launches of at most 4 (registers hold the accumulators; b_k is
 // rebuilt per launch).  grid = ((N / 32) * (L+1), 1, batch chunks), block = 32 * DH_KG.
 // ---------------------------------------------------------------------------------------
-constexpr int DH_TX = 32, DH_KG = 8, DH_BCH = 32;
+constexpr int DH_TX = 32, DH_KG = 8, DH_BCH = 64;
 struct DhInnerParams {
     CtView in;             // input batch at level L
     const u64 *ext;        // [B][L][L+1][N] lifted digits of c1 (hoisted decomposition)
