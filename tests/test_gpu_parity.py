@@ -308,6 +308,40 @@ def test_matvec_bsgs_double_hoisted(hg, n, dim, n1, n2):
         ctx.matvec_bsgs(out, X, D, min(n1, 16), n2, hoist=True)
 
 
+@pytest.mark.parametrize("bits,L", [((60, 40, 40, 60), 2), ((60, 40, 40, 40, 60), 4), ((60, 40, 40, 40, 60), 3), ((50, 50, 60), 2), ((40, 60), 1)])
+def test_matvec_double_hoisted_levels(hg, bits, L):
+    """Double-hoisted matvec below the top level (the special prime is then NOT the limb after the
+    ciphertext's last one), with four digits, with 50-bit primes only (integer policy everywhere) and with
+    a single digit: bit-exact against the oracle, decrypts to M @ v."""
+    n, dim, n1, n2, B = 8192, 16, 4, 4, 2
+    S = setup(n, bits)
+    ctx = make_ctx(hg, S)
+    rng = np.random.default_rng(24)
+    scale = 2.0**40 if L > 1 else 2.0**15
+    M = rng.uniform(-1, 1, (dim, dim))
+    V = rng.uniform(-1, 1, (B, dim))
+    cts = np.stack([S.encrypt(np.tile(V[i], n // 2 // dim), scale, L, seed=i) for i in range(B)])
+    ptsx = _diag_plaintexts_ext(S, M, n1, n2, scale, L)
+    bsteps, gsteps = list(range(1, n1)), [g * n1 for g in range(1, n2)]
+    gk = S.gk(bsteps + gsteps)
+    ctx.load_galois_keys(gk)
+    bk = [None] + [gk[orc.galois_elt_from_step(n, s)] for s in bsteps]
+    gkeys = [None] + [gk[orc.galois_elt_from_step(n, s)] for s in gsteps]
+    X = ctx.upload_ct(cts, scale)
+    D = ctx.upload_pt_ext(ptsx, scale)
+    out = ctx.ct(B, 2)
+    rescale = L > 1
+    want = S.o.matvec_bsgs(cts, n1, n2, ptsx, bk, gkeys, threads=4, dh=True, rescale=rescale)
+    ctx.matvec_bsgs(out, X, D, n1, n2, dh=True, rescale=rescale)
+    got = out.download()
+    assert out.L == (L - 1 if rescale else L)
+    assert np.array_equal(got, want)
+    if rescale:
+        tol = ckks_tol(dim, n, scale)
+        for i in range(B):
+            assert np.max(np.abs(S.decrypt(got[i], out.scale).real[:dim] - M @ V[i])) < tol
+
+
 def test_matvec_double_hoisted_two_execution_slots(hg):
     """Batches of 32 or more ciphertexts are split into chunks that run on two streams with separate
     scratch (and an uneven last chunk): every ciphertext must still match the oracle bit for bit, also
