@@ -101,30 +101,44 @@ __device__ __forceinline__ void mac128(u64 &hi, u64 &lo, u64 x, u64 y)
         : "l"(x), "l"(y));
 }
 
-// Montgomery reduction: (hi:lo) * 2^-64 mod q, canonical; needs hi:lo < q * 2^64.
-// One low product + one high product instead of Barrett's five.
-__device__ __forceinline__ u64 mont_reduce(u64 hi, u64 lo, const ModConst &m)
-{
-    const u64 t = lo * m.qinv_neg;
-    const u64 r = hi + __umul64hi(t, m.q) + (lo != 0 ? 1ull : 0ull);
-    return csub(r, m.q);
-}
-
-// Montgomery reduction without the final conditional subtraction: congruent to (hi:lo) * 2^-64 and
-// below 2q for hi:lo < q * 2^64 -- enough when the result is only an operand of further products
+// Montgomery reduction core: ((hi:lo) + t*q) >> 64 with t = lo * (-q^-1) mod 2^64, congruent to
+// (hi:lo) * 2^-64 mod q.  The low 64 bits of the sum cancel; the carry chains below produce the high
+// half directly (12 instructions; the mulhi + carry-fix-up form compiles to 17).  For hi:lo < k*q*2^64
+// the result is below (k+1)*q.
 __device__ __forceinline__ u64 mont_reduce_lazy(u64 hi, u64 lo, const ModConst &m)
 {
     const u64 t = lo * m.qinv_neg;
-    return hi + __umul64hi(t, m.q) + (lo != 0 ? 1ull : 0ull);
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 t0, t1, q0, q1, a0, a1, a2, a3, u0, u1, c;\n\t"
+        "mov.b64 {t0, t1}, %1;\n\t"
+        "mov.b64 {q0, q1}, %2;\n\t"
+        "mov.b64 {a0, a1}, %3;\n\t"
+        "mov.b64 {a2, a3}, %4;\n\t"
+        "mad.lo.cc.u32  a0, t0, q0, a0;\n\t"
+        "madc.hi.cc.u32 a1, t0, q0, a1;\n\t"
+        "madc.lo.cc.u32 a2, t1, q1, a2;\n\t"
+        "madc.hi.u32    a3, t1, q1, a3;\n\t"
+        "mul.lo.u32     u0, t0, q1;\n\t"
+        "mul.hi.u32     u1, t0, q1;\n\t"
+        "mad.lo.cc.u32  u0, t1, q0, u0;\n\t"
+        "madc.hi.cc.u32 u1, t1, q0, u1;\n\t"
+        "addc.u32       c, 0, 0;\n\t"
+        "add.cc.u32     a1, a1, u0;\n\t"
+        "addc.cc.u32    a2, a2, u1;\n\t"
+        "addc.u32       a3, a3, c;\n\t"
+        "mov.b64 %0, {a2, a3};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(t), "l"(m.q), "l"(lo), "l"(hi));
+    return r;
 }
-
-// same for sums of up to 32 products of canonical residues (hi:lo < 2 * q * 2^64): result < 3q before
-// the two conditional subtractions
+// canonical; needs hi:lo < q * 2^64
+__device__ __forceinline__ u64 mont_reduce(u64 hi, u64 lo, const ModConst &m) { return csub(mont_reduce_lazy(hi, lo, m), m.q); }
+// canonical for sums of up to 32 products of canonical residues (hi:lo < 2 * q * 2^64)
 __device__ __forceinline__ u64 mont_reduce_wide(u64 hi, u64 lo, const ModConst &m)
 {
-    const u64 t = lo * m.qinv_neg;
-    const u64 r = hi + __umul64hi(t, m.q) + (lo != 0 ? 1ull : 0ull);
-    return csub(csub(r, m.q), m.q);
+    return csub(csub(mont_reduce_lazy(hi, lo, m), m.q), m.q);
 }
 
 // ---- 30-bit limb form: x = lo + hi * 2^30 for x < 2^60.  Limb products are < 2^60, so up to 16 of
