@@ -1,13 +1,13 @@
-// kernels.cuh -- the CUDA kernels of the CKKS evaluator (sm_100a).
+// kernels.cuh -- NTT job resolvers and NTT kernels of the CKKS evaluator (sm_100a); shared by hegpu.cu and
+// the ntt_inst_*.cu translation units.  The multiply-accumulate / element-wise kernels are in mac_kernels.cuh.
 //
-//  K1/K2  ntt_fwd_kernel / ntt_inv_kernel (+ ntt_inv_final_kernel for N = 32768)
-//  K3-K5  element-wise: add / sub / negate / multiply_plain / tensor product / square
+//  K1/K2  ntt_fwd_kernel / ntt_inv_kernel (+ ntt_inv_final_kernel for N = 32768), park kernels (N = 16384)
 //  K6     Galois permutation: fused as a gather into the key-switch INTT load, the key
 //         inner product (digit i == j) and the mod-down epilogue -- never a separate pass
 //  K7     key-switch: ks INTT -> lift+NTT -> key inner product -> INTT(+half) -> mod-down NTT
 //  K8     rescale: INTT(+half) -> mod-down NTT (same two kernels as the end of K7)
-//  K10    bsgs_inner_kernel: sum_k baby_k (.) diag_{g,k} for all giant steps at once
-//  K11    fixup_kernel: reduce NCCL uint64 sums back to [0,q)
+//  (mac_kernels.cuh: K3-K5 element-wise / tensor, K7 step 3 ks_inner[_sum], K10 bsgs_inner / dh_inner,
+//   K11 fixup)
 #pragma once
 #include "ntt.cuh"
 
