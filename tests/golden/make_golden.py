@@ -72,7 +72,13 @@ def outputs(n, bits):
     for hoist in (0, 1):
         for lazy in (0, 1):
             res[f"matvec_2x2_hoist{hoist}_lazy{lazy}"] = digest(o.matvec_bsgs(cts, 2, 2, pts, bk, gkeys, hoist=bool(hoist), lazy=bool(lazy)))
+    # double-hoisted mode: plaintexts with a limb mod the special prime (pseudo-random residues over all K limbs)
+    res["matvec_2x2_dh"] = digest(o.matvec_bsgs(cts, 2, 2, dh_plaintexts(o, s, L, n), bk, gkeys, dh=True))
     return res
+
+
+def dh_plaintexts(o, s, L, n):
+    return np.stack([o.encrypt_symmetric(50 + i, s, np.zeros((L + 1, n), dtype=np.uint64))[0] for i in range(4)])
 
 
 def small_vectors():

@@ -95,3 +95,6 @@ def test_gpu_matches_golden_digests(name):
         for lazy in (0, 1):
             ctx.matvec_bsgs(mv, X, D, 2, 2, hoist=bool(hoist), lazy=bool(lazy))
             assert digest(mv.download()) == g[f"matvec_2x2_hoist{hoist}_lazy{lazy}"]
+    Dx = ctx.upload_pt_ext(make_golden.dh_plaintexts(o, s, L, n), sc)
+    ctx.matvec_bsgs(mv, X, Dx, 2, 2, dh=True)
+    assert digest(mv.download()) == g["matvec_2x2_dh"]
