@@ -174,6 +174,7 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     if (const char *e = getenv("HEGPU_PARK")) c->use_park = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_FUSED")) c->dh_fused = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_F64")) c->dh_f64 = atoi(e) != 0;
+    if (const char *e = getenv("HEGPU_FUSE_FINAL")) c->fuse_final = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->main_stream = c->stream;
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -1147,6 +1148,36 @@ static int ks_moddown(hegpu_ctx *c, KsPlan &pl)
     TRY(launch_ntt_fwd(c, j5, (u32)(pl.E * 2 * L), PK_KS_MODDOWN_NTT, P.has_base1 ? 4 : 3));
     return HEGPU_OK;
 }
+// steps 4-5 and the rescale that follows, fused (FinalInttJob / FinalNttJob): out (level L-1) =
+// rescale(base + mod_down(acc)), bit-identical to ks_moddown + rescale_views with 8 transforms per
+// ciphertext instead of 14 (L = 3).  pl: ngroups = 1, acc, t, in[0] = base (has_base1 / no_base0), scr.
+static int ks_moddown_rescale(hegpu_ctx *c, KsPlan &pl, CtView out, u64 *t2)
+{
+    const KsParams &P = pl.P;
+    const u32 L = P.L, B = P.B;
+    HalfInttJob j4{ P.acc + (size_t)L * c->n, P.t, (size_t)(L + 1) * c->n, 0, 1, c->K - 1, c->n };
+    TRY(launch_ntt_inv(c, j4, B * 2, pl.scr, PK_HALF_INTT));
+    FinalParams F{};
+    F.acc = P.acc;
+    F.base = P.in[0];
+    F.out = out;
+    F.t = P.t;
+    F.t2 = t2;
+    F.mdP = c->d_md + (size_t)(c->K - 1) * c->K;
+    F.mdQ = c->d_md + (size_t)(L - 1) * c->K;
+    F.mods = c->d_mods;
+    F.B = B;
+    F.L = L;
+    F.K = c->K;
+    F.n = c->n;
+    F.has_base0 = P.no_base0 ? 0u : 1u;
+    F.has_base1 = P.has_base1;
+    FinalInttJob ji{ F };
+    TRY(launch_ntt_inv(c, ji, B * 2, pl.scr, PK_HALF_INTT));
+    FinalNttJob jn{ F };
+    TRY(launch_ntt_fwd(c, jn, B * 2 * (L - 1), PK_RESCALE_NTT, 5));
+    return HEGPU_OK;
+}
 // out must not alias in when perm != null.
 static int keyswitch(hegpu_ctx *c, const KsGroupDesc *groups, u32 ngroups, u32 B, u32 L, u32 target_poly, bool has_base1,
                      ArenaPlan &ap, bool hoisted = false)
@@ -1548,11 +1579,18 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
             pf1.P.has_base1 = 1;
             pf1.P.in[0] = view_of(basebuf, 0);
         }
-        TRY(ks_moddown(c, pf1));
-        if (rescale) {
+        if (rescale && c->fuse_final) {
             ArenaPlan ar{ c };
             ar.off = ap.off;
-            TRY(rescale_views(c, out->view_at(b0), dst, Bn, 2, L, ar));
+            u64 *t2 = ar.take((size_t)Bn * 2 * n);  // inside the region sized for the unfused rescale
+            TRY(ks_moddown_rescale(c, pf1, out->view_at(b0), t2));
+        } else {
+            TRY(ks_moddown(c, pf1));
+            if (rescale) {
+                ArenaPlan ar{ c };
+                ar.off = ap.off;
+                TRY(rescale_views(c, out->view_at(b0), dst, Bn, 2, L, ar));
+            }
         }
     }
     for (int sl = 1; sl < NS; ++sl) {

@@ -234,6 +234,85 @@ struct RescaleJob {
 };
 
 // ---------------------------------------------------------------------------------------
+// Mod-down by P followed by rescale by q_last, as ONE pass (bit-identical to the two steps: every
+// operation is exact mod q_i and the NTT is linear, so transforms that the two-step form runs back
+// to back are merged or cancelled).  With F = accumulator in the basis q_0..q_{L-1},P (NTT form),
+// base = ciphertext added after the mod-down, t = INTT_P(F_P) + floor(P/2) (HalfInttJob):
+//   limb L-1:  res_last = base + (F - NTT(d)) P^-1, d = (t mod q_last) - (floor(P/2) mod q_last); the rescale needs
+//              INTT(res_last) + floor(q_last/2) = INTT(base + F P^-1) - d P^-1 + floor(q_last/2) =: t2
+//              -> one INTT with fused loader/epilogue instead of NTT(d) + INTT(res_last)   (FinalInttJob)
+//   limb i<L-1: out = (res_i - NTT(d2)) q_last^-1 with d2 = (t2 mod q_i) - (floor(q_last/2) mod q_i)
+//              = (base + F P^-1 - NTT(d P^-1 + d2)) q_last^-1
+//              -> one NTT instead of two                                                    (FinalNttJob)
+// 4 transforms per polynomial instead of 7 at L = 3.
+// ---------------------------------------------------------------------------------------
+struct FinalParams {
+    const u64 *acc;     // [B][2][L+1][N]
+    CtView base;        // level-L ciphertext batch added after the mod-down
+    CtView out;         // level L-1 result
+    const u64 *t;       // [B*2][N]  INTT_P(F_P) + floor(P/2)
+    u64 *t2;            // [B*2][N]  INTT_{q_last}(res_last) + floor(q_last/2)
+    const MdConst *mdP; // constants of the special prime per target limb
+    const MdConst *mdQ; // constants of q_last per target limb
+    const ModConst *mods;
+    u32 B, L, K, n;
+    u32 has_base0, has_base1;
+};
+struct FinalInttJob {
+    static constexpr bool PIPE = false;
+    FinalParams P;
+    __device__ __forceinline__ u32 mod(u32) const { return P.L - 1; }
+    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const  // (base + F P^-1)[limb L-1], NTT form
+    {
+        const u32 b = j >> 1, c = j & 1u, l = P.L - 1;
+        const u64 q = P.mods[l].q;
+        const u64 f = P.acc[((size_t)j * (P.L + 1) + l) * P.n + i];
+        u64 g = mul_shoup(f, P.mdP[l].inv, P.mdP[l].inv_sh, q);
+        if (c ? P.has_base1 : P.has_base0) g = addmod(g, P.base.p[b * P.base.sb + c * P.base.sp + l * P.base.sl + i], q);
+        return g;
+    }
+    __device__ __forceinline__ u64 load_fix(u32, u64 v, const ModConst &) const { return v; }
+    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m) const
+    {
+        const u32 l = P.L - 1;
+        const u64 d = submod(rebase(P.t[(size_t)j * P.n + i], P.mods[P.K - 1].q, m), P.mdP[l].halfmod, m.q);
+        const u64 r = submod(x, mul_shoup(d, P.mdP[l].inv, P.mdP[l].inv_sh, m.q), m.q);
+        P.t2[(size_t)j * P.n + i] = addmod(r, m.q >> 1, m.q);
+    }
+};
+struct FinalNttJob {
+    static constexpr bool PIPE = false;
+    FinalParams P;
+    __device__ __forceinline__ u32 mod(u32 j) const { return j % (P.L - 1); }
+    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const  // d P^-1 + d2, coefficient form
+    {
+        const u32 l = j % (P.L - 1), bc = j / (P.L - 1);
+        const ModConst &m = P.mods[l];
+        const u64 d = submod(rebase(P.t[(size_t)bc * P.n + i], P.mods[P.K - 1].q, m), P.mdP[l].halfmod, m.q);
+        const u64 d2 = submod(rebase(P.t2[(size_t)bc * P.n + i], P.mods[P.L - 1].q, m), P.mdQ[l].halfmod, m.q);
+        return addmod(mul_shoup(d, P.mdP[l].inv, P.mdP[l].inv_sh, m.q), d2, m.q);
+    }
+    __device__ __forceinline__ u64 load_fix(u32, u64 v, const ModConst &) const { return v; }
+    struct Ops {
+        u64 f, base;
+    };
+    __device__ __forceinline__ Ops fetch(u32 j, u32 i, const ModConst &) const
+    {
+        const u32 l = j % (P.L - 1), bc = j / (P.L - 1), b = bc >> 1, c = bc & 1u;
+        Ops o;
+        o.f = P.acc[((size_t)bc * (P.L + 1) + l) * P.n + i];
+        o.base = (c ? P.has_base1 : P.has_base0) ? P.base.p[b * P.base.sb + c * P.base.sp + l * P.base.sl + i] : 0;
+        return o;
+    }
+    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m, const Ops &o) const
+    {
+        const u32 l = j % (P.L - 1), bc = j / (P.L - 1), b = bc >> 1, c = bc & 1u;
+        const u64 r = addmod(o.base, mul_shoup(o.f, P.mdP[l].inv, P.mdP[l].inv_sh, m.q), m.q);
+        P.out.p[b * P.out.sb + c * P.out.sp + l * P.out.sl + i] = mul_shoup(submod(r, x, m.q), P.mdQ[l].inv, P.mdQ[l].inv_sh, m.q);
+    }
+};
+
+// ---------------------------------------------------------------------------------------
 // Loaders (protocol in ntt.cuh): raw() = memory only, fix() = arithmetic only.
 // ---------------------------------------------------------------------------------------
 template <class Job>

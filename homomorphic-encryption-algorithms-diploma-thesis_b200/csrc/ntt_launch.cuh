@@ -116,4 +116,6 @@ extern template int launch_ntt_fwd<KsLiftJob>(hegpu_ctx *, const KsLiftJob &, u3
 extern template int launch_ntt_inv<HalfInttJob>(hegpu_ctx *, const HalfInttJob &, u32, u64 *, int);
 extern template int launch_ntt_fwd<KsModDownJob>(hegpu_ctx *, const KsModDownJob &, u32, int, u64);
 extern template int launch_ntt_fwd<RescaleJob>(hegpu_ctx *, const RescaleJob &, u32, int, u64);
+extern template int launch_ntt_inv<FinalInttJob>(hegpu_ctx *, const FinalInttJob &, u32, u64 *, int);
+extern template int launch_ntt_fwd<FinalNttJob>(hegpu_ctx *, const FinalNttJob &, u32, int, u64);
 #endif

@@ -256,7 +256,7 @@ def _diag_plaintexts_ext(S, M, n1, n2, scale, L):
 
 
 @pytest.mark.parametrize("n,dim,n1,n2", [(8192, 16, 4, 4), (16384, 32, 8, 4), (8192, 32, 32, 1), (8192, 8, 1, 8), (8192, 48, 24, 2),
-                                         (8192, 64, 32, 2)])
+                                         (8192, 64, 32, 2), (32768, 16, 4, 4), (4096, 8, 4, 2)])
 def test_matvec_bsgs_double_hoisted(hg, n, dim, n1, n2):
     """HEGPU_MATVEC_DH against its oracle restatement (orc_matvec_bsgs_dh, itself pinned by a big-integer
     restatement in tests/test_oracle_evaluator.py): bit-exact, decrypts to M @ v, with and without the
