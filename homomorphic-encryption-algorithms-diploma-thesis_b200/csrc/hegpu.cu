@@ -1118,7 +1118,10 @@ static int ks_inner_sum(hegpu_ctx *c, KsPlan &pl, const u64 *init, u64 *out)
         TRY(ks_inner(c, pl));
         const size_t total = (size_t)B * 2 * (L + 1) * c->n;
         Prof pf(c, PK_ELEMENTWISE, total, total * 8 * (ngroups + 1 + (init ? 1 : 0)));
-        acc_group_sum_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(P.acc, init, out, ngroups, B, L, c->K, c->n, c->d_mods);
+        GatherU0 G{};
+        G.u0 = P.u0;
+        for (u32 g = 0; g < ngroups; ++g) G.perm[g] = P.perm[g];
+        acc_group_sum_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(P.acc, init, out, ngroups, B, L, c->K, c->n, c->d_mods, G);
         c->launches++;
         CU(cudaGetLastError());
         return HEGPU_OK;
@@ -1142,6 +1145,13 @@ static int ks_moddown(hegpu_ctx *c, KsPlan &pl)
 {
     const KsParams &P = pl.P;
     const u32 L = P.L;
+    if (P.only_c1) {  // component 1 of every element: t is [E][N]
+        HalfInttJob j4{ P.acc + (size_t)(2 * L + 1) * c->n, P.t, (size_t)2 * (L + 1) * c->n, 0, 1, c->K - 1, c->n };
+        TRY(launch_ntt_inv(c, j4, (u32)pl.E, pl.scr, PK_HALF_INTT));
+        KsModDownJob j5{ P, c->d_md + (size_t)(c->K - 1) * c->K, c->d_mods };
+        TRY(launch_ntt_fwd(c, j5, (u32)(pl.E * L), PK_KS_MODDOWN_NTT, 3));
+        return HEGPU_OK;
+    }
     HalfInttJob j4{ P.acc + (size_t)L * c->n, P.t, (size_t)(L + 1) * c->n, 0, 1, c->K - 1, c->n };
     TRY(launch_ntt_inv(c, j4, (u32)(pl.E * 2), pl.scr, PK_HALF_INTT));
     KsModDownJob j5{ P, c->d_md + (size_t)(c->K - 1) * c->K, c->d_mods };
@@ -1409,7 +1419,6 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
         u64 *scr1 = ap.take(inv_scratch_words(c, (size_t)nr1 * Bc * 2));
         u64 *accsum = ap.take((size_t)Bc * accw);
         u64 *tsum = ap.take((size_t)Bc * 2 * n);
-        u64 *basebuf = ap.take((size_t)Bc * ctw);
         u64 *accb = ap.take((size_t)Bc * ctw);
         auto view_of = [&](u64 *p, size_t batch_off) { return CtView{ p + batch_off * ctw, ctw, (size_t)L * n, n }; };
         auto qp_view = [&](u64 *p, size_t batch_off) { return CtView{ p + batch_off * accw, accw, (size_t)(L + 1) * n, n }; };
@@ -1527,7 +1536,8 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
             pf1.P.no_base0 = 1;
             pf1.P.in[0] = dst;
         } else {
-            // 5. (v0, v1)_g = mod_down(u_g) for the rotated giant steps
+            // 5. v1_g = mod_down(u_g[1]) for the rotated giant steps: only the component that is key-switched
+            //    leaves the extended basis
             KsPlan pm;
             pm.P = KsParams{};
             pm.P.ngroups = nrot;
@@ -1537,6 +1547,7 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
             pm.P.n = c->n;
             pm.P.target_poly = 1;
             pm.P.no_base0 = 1;
+            pm.P.only_c1 = 1;
             for (u32 r = 0; r < nrot; ++r) {
                 pm.P.in[r] = view_of(v, (size_t)r * Bn);
                 pm.P.out[r] = view_of(v, (size_t)r * Bn);
@@ -1546,38 +1557,22 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
             pm.E = (size_t)nrot * Bn;
             pm.scr = scr1;
             TRY(ks_moddown(c, pm));
-            // 6. giant rotations: key-switch pi_g(v1_g) without mod-down, summed over g (+ u_0)
+            // 6. giant rotations: key-switch pi_g(v1_g) without mod-down, summed over g, + pi_g(u_g[0]) (+ u_0)
             KsGroupDesc gs[MAXG];
-            BaseSumParams BS{};
             for (u32 r = 0; r < nrot; ++r) {
                 const u32 g = first_rot + r;
                 const u32 *pmr;
                 TRY(get_perm(c, gelt[g], &pmr));
                 gs[r] = KsGroupDesc{ view_of(v, (size_t)r * Bn), view_of(v, (size_t)r * Bn), c->galois_keys[gelt[g]], pmr };
-                BS.perm[r] = pmr;
             }
             KsPlan pl;
             TRY(ks_setup(c, pl, gs, nrot, Bn, L, 1, false, false, ap));
             TRY(ks_decompose(c, pl));
+            pl.P.u0 = u + (size_t)first_rot * Bn * accw;
             TRY(ks_inner_sum(c, pl, first_rot ? u : nullptr, accsum));
-            {   // base = (sum_r pi_r(v0_r), 0)
-                BS.first = view_of(v, 0);
-                BS.has_first = 0;
-                BS.rest = view_of(v, 0);
-                BS.out = view_of(basebuf, 0);
-                BS.groups = nrot;
-                BS.B = Bn;
-                BS.L = L;
-                BS.n = c->n;
-                const size_t total = (size_t)Bn * ctw;
-                Prof pf(c, PK_ELEMENTWISE, total, total * 8 + (size_t)Bn * L * n * 8 * nrot);
-                base_gather_sum_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(BS, c->d_mods);
-                c->launches++;
-                CU(cudaGetLastError());
-            }
             pf1.P.acc = accsum;
-            pf1.P.has_base1 = 1;
-            pf1.P.in[0] = view_of(basebuf, 0);
+            pf1.P.no_base0 = 1;
+            pf1.P.in[0] = dst;
         }
         if (rescale && c->fuse_final) {
             ArenaPlan ar{ c };

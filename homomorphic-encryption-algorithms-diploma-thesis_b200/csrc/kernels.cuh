@@ -66,6 +66,9 @@ struct KsParams {
     u32 add_pc0;      // double-hoisted baby steps: acc[0][i] += P * pi(c0)[i] (i < L), the rotated
                       // ciphertext stays in the extended basis scaled by P
     u32 no_base0;     // mod-down without a base ciphertext for component 0 (double-hoisted inner sums)
+    u32 only_c1;      // mod-down of component 1 only (double-hoisted giant steps): job = (e, limb), t is [E][N]
+    const u64 *u0;    // ks_inner_sum: accumulators [ngroups*B][2][L+1][N] whose component 0 is gathered through
+                      // perm[g] (every limb, also the one mod P) and added to the sum; null: nothing
     CtView in[MAXG];
     CtView out[MAXG];
     const u64 *key[MAXG];   // [Lmax][2][K][N]
@@ -162,8 +165,8 @@ struct KsModDownJob {
     __device__ __forceinline__ void split(u32 j, u32 &e, u32 &c, u32 &l) const
     {
         l = j % P.L;
-        c = (j / P.L) & 1u;
-        e = j / (2 * P.L);
+        c = P.only_c1 ? 1u : (j / P.L) & 1u;
+        e = P.only_c1 ? j / P.L : j / (2 * P.L);
     }
     __device__ __forceinline__ u32 mod(u32 j) const { return j % P.L; }
     __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const { return P.t[(size_t)(j / P.L) * P.n + i]; }

@@ -96,7 +96,9 @@ __global__ void __launch_bounds__(256) ks_inner_sum_kernel(const KsParams P, con
         for (u32 g = 0; g < P.ngroups; ++g) {
             const CtView &v = P.in[g];
             const u32 *pm = P.perm[g];
-            const u32 xs = (i < L && pm) ? __ldg(pm + x) : x;
+            const u32 xp = pm ? __ldg(pm + x) : x;
+            const u32 xs = i < L ? xp : x;
+            if (P.u0) s0 = addmod(s0, P.u0[((((size_t)g * P.B + b) * 2) * (L + 1) + i) * n + xp], m.q);
             const u64 *key = P.key[g] + (size_t)ki * n + x;
             const size_t e = (size_t)g * P.B + b;
             u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
@@ -551,9 +553,13 @@ __global__ void __launch_bounds__(256) sum_terms_kernel(const SumParams P, const
 }
 
 // lazy mod-down over giant steps: accsum[b][c][i] = sum_g acc[g*B+b][c][i] mod m_i  (rows = 2*(L+1))
+struct GatherU0 {  // optional: + sum_g pi_g(u0[g][b][0]) on component 0 (every limb)
+    const u64 *u0;
+    const u32 *perm[MAXG];
+};
 __global__ void __launch_bounds__(256) acc_group_sum_kernel(const u64 *__restrict__ acc, const u64 *__restrict__ init,
                                                             u64 *__restrict__ out, u32 groups, u32 B, u32 L, u32 K, u32 n,
-                                                            const ModConst *__restrict__ mods)
+                                                            const ModConst *__restrict__ mods, const GatherU0 G)
 {
     const size_t per_b = (size_t)2 * (L + 1) * n;
     const size_t total = (size_t)B * per_b;
@@ -564,6 +570,10 @@ __global__ void __launch_bounds__(256) acc_group_sum_kernel(const u64 *__restric
         const u64 q = mods[i == L ? K - 1 : i].q;
         u64 s = init ? init[idx] : 0;  // init: an unrotated term already in the extended basis
         for (u32 g = 0; g < groups; ++g) s = addmod(s, acc[((size_t)g * B + b) * per_b + r], q);
+        if (G.u0 && r < (size_t)(L + 1) * n) {  // component 0
+            const u32 x = (u32)(r % n);
+            for (u32 g = 0; g < groups; ++g) s = addmod(s, G.u0[((size_t)g * B + b) * per_b + (r - x) + __ldg(G.perm[g] + x)], q);
+        }
         out[idx] = s;
     }
 }

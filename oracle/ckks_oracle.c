@@ -949,6 +949,28 @@ void orc_matvec_bsgs_fast(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1
     orc_matvec_bsgs_ex(c, L, B, cts, n1, n2, 0, pts, baby_keys, giant_keys, 1 | 2 | 4, out, threads);
 }
 
+/* mod-down by P with rounding of ONE component: out[i] = (acc[i] - NTT_{q_i}((t mod q_i) - (floor(P/2) mod q_i))) * P^-1,
+ * t = INTT_P(acc[L]) + floor(P/2).  acc [L+1][N] is destroyed; out [L][N]. */
+static void mod_down_one(const orc_ctx *c, u32 L, u64 *acc, u64 *out)
+{
+    const u32 n = c->n, K = c->K;
+    const u64 P = c->q[K - 1], halfP = P >> 1;
+    u64 *tmp = (u64 *)malloc(sizeof(u64) * n);
+    u64 *t = acc + (size_t)L * n;
+    orc_ntt_inv(c, K - 1, t);
+    for (u32 x = 0; x < n; ++x) t[x] = addmod(t[x], halfP, P);
+    for (u32 i = 0; i < L; ++i) {
+        const u64 q = c->q[i];
+        const u64 hq = halfP % q, pinv = invmod(P % q, q);
+        for (u32 x = 0; x < n; ++x) tmp[x] = submod(REDUCE64(c, i, t[x]), hq, q);
+        orc_ntt_fwd(c, i, tmp);
+        const u64 *a = acc + (size_t)i * n;
+        u64 *o = out + (size_t)i * n;
+        for (u32 x = 0; x < n; ++x) o[x] = MULMOD(c, i, submod(a[x], tmp[x], q), pinv);
+    }
+    free(tmp);
+}
+
 /* Double-hoisted BSGS matvec = the restatement of hegpu_matvec_bsgs_range with HEGPU_MATVEC_DH
  * (Bossuat et al., "Efficient bootstrapping for approximate HE with non-sparse keys", EUROCRYPT 2021,
  * section 5 -- the same composite, built from SEAL's key-switch steps of SURVEY 9.6):
@@ -957,12 +979,13 @@ void orc_matvec_bsgs_fast(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1
  *       b_k = ( ks_inner(pi_k(ext), key_k)[0] + P*pi_k(c0),  ks_inner(...)[1] ),   b_0 = (P*c0, P*c1)
  *   - inner sums in the extended basis with plaintexts that carry a limb mod P:
  *       u_g = sum_k ptx[g*n1+k] (.) b_k                                (accumulated lazily, one reduction)
- *   - rotated giant step g: (v0,v1) = mod_down(u_g); F += ks_inner(decompose(pi_g(v1)), key_g);
- *     base0 += pi_g(v0);   the unrotated step adds u_g to F directly;
- *   - ONE final mod-down: res = (base0, 0) + mod_down(F); optional rescale.
- * Only (n2 - 1) + 1 mod-downs instead of (n1 - 1) + 1.  Same function as the chain of primitives up
- * to key-switch noise; different bits.  ptsx: [n1*n2][L+1][N], limb L = residues mod the special
- * prime (NTT form).  flags: 4 = final rescale.  out as orc_matvec_bsgs_ex. */
+ *   - rotated giant step g: only the component that has to be key-switched leaves the extended basis,
+ *       v1 = mod_down(u_g[1]);  F += ks_inner(decompose(pi_g(v1)), key_g);  F[0] += pi_g(u_g[0])
+ *     (the Galois permutation acts limb-wise, also on the limb mod P); the unrotated step adds u_g to F;
+ *   - ONE final mod-down of both components: res = mod_down(F); optional rescale.
+ * (n2 - 1) single-component mod-downs + 1 instead of (n1 - 1) + 1 two-component ones.  Same function as the
+ * chain of primitives up to key-switch noise; different bits.  ptsx: [n1*n2][L+1][N], limb L = residues mod
+ * the special prime (NTT form).  flags: 4 = final rescale.  out as orc_matvec_bsgs_ex. */
 void orc_matvec_bsgs_dh(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1, u32 n2, u32 g_first, const u64 *ptsx,
                         const u64 *const *baby_keys, const u64 *const *giant_keys, int flags, u64 *out, int threads)
 {
@@ -985,9 +1008,8 @@ void orc_matvec_bsgs_dh(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1, 
         u64 *u = (u64 *)malloc(sizeof(u64) * accw);
         u64 *acc = (u64 *)malloc(sizeof(u64) * accw);
         u64 *F = (u64 *)calloc(accw, sizeof(u64));
-        u64 *v = (u64 *)malloc(sizeof(u64) * ctw);
+        u64 *v1 = (u64 *)malloc(sizeof(u64) * (size_t)L * n);
         u64 *zero = (u64 *)calloc(ctw, sizeof(u64));
-        u64 *base = (u64 *)calloc(ctw, sizeof(u64));
         u64 *res = (u64 *)malloc(sizeof(u64) * ctw);
         u64 *tgt = (u64 *)malloc(sizeof(u64) * (size_t)L * n);
         u128 *lazy = (u128 *)malloc(sizeof(u128) * n);
@@ -1005,7 +1027,6 @@ void orc_matvec_bsgs_dh(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1, 
                     for (u32 x = 0; x < n; ++x) dst[x] = addmod(dst[x], MULMOD(c, i, src[tab ? tab[x] : x], pm), q);
                 }
         }
-        int rotated = 0;
         for (u32 g = 0; g < n2; ++g) {
             for (u32 comp = 0; comp < 2; ++comp)
                 for (u32 I = 0; I <= L; ++I) {
@@ -1019,35 +1040,31 @@ void orc_matvec_bsgs_dh(const orc_ctx *c, u32 L, u32 B, const u64 *cts, u32 n1, 
                     u64 *o = u + ((size_t)comp * (L + 1) + I) * n;
                     for (u32 x = 0; x < n; ++x) o[x] = barrett128(lazy[x], c->q[ki], c->r0[ki], c->r1[ki]);
                 }
-            const u64 *add = u;
-            if (g_first + g) {
-                rotated = 1;
-                const u32 *tab = tabs + (size_t)(n1 + g) * n;
-                ks_mod_down_add(c, L, u, zero, v); /* destroys u */
-                for (u32 i = 0; i < L; ++i) {
-                    const u64 q = c->q[i];
-                    for (u32 x = 0; x < n; ++x) {
-                        tgt[(size_t)i * n + x] = v[(size_t)(L + i) * n + tab[x]];
-                        base[(size_t)i * n + x] = addmod(base[(size_t)i * n + x], v[(size_t)i * n + tab[x]], q);
-                    }
-                }
+            const u32 *tab = (g_first + g) ? tabs + (size_t)(n1 + g) * n : NULL;
+            const u64 *add1 = u + (size_t)(L + 1) * n; /* what is added to F[1] */
+            if (tab) {
+                mod_down_one(c, L, u + (size_t)(L + 1) * n, v1); /* destroys u[1] */
+                for (u32 i = 0; i < L; ++i)
+                    for (u32 x = 0; x < n; ++x) tgt[(size_t)i * n + x] = v1[(size_t)i * n + tab[x]];
                 ks_decompose(c, L, tgt, ext);
                 ks_inner(c, L, ext, NULL, giant_keys[g], acc);
-                add = acc;
+                add1 = acc + (size_t)(L + 1) * n;
             }
-            for (u32 comp = 0; comp < 2; ++comp)
-                for (u32 I = 0; I <= L; ++I) {
-                    const u64 m = c->q[I == L ? K - 1 : I];
-                    u64 *s = F + ((size_t)comp * (L + 1) + I) * n;
-                    const u64 *a = add + ((size_t)comp * (L + 1) + I) * n;
-                    for (u32 x = 0; x < n; ++x) s[x] = addmod(s[x], a[x], m);
+            for (u32 I = 0; I <= L; ++I) {
+                const u64 m = c->q[I == L ? K - 1 : I];
+                u64 *s0 = F + (size_t)I * n, *s1 = F + ((size_t)(L + 1) + I) * n;
+                const u64 *u0 = u + (size_t)I * n, *a1 = add1 + (size_t)I * n;
+                for (u32 x = 0; x < n; ++x) {
+                    s0[x] = addmod(s0[x], u0[tab ? tab[x] : x], m); /* pi_g(u_g[0]) stays in the extended basis */
+                    if (tab) s0[x] = addmod(s0[x], acc[(size_t)I * n + x], m);
+                    s1[x] = addmod(s1[x], a1[x], m);
                 }
+            }
         }
-        (void)rotated;
-        ks_mod_down_add(c, L, F, base, res);
+        ks_mod_down_add(c, L, F, zero, res);
         if (rescale) orc_rescale(c, L, res, 2, out + (size_t)b * 2 * (L - 1) * n);
         else memcpy(out + (size_t)b * ctw, res, sizeof(u64) * ctw);
-        free(ext); free(baby); free(u); free(acc); free(F); free(v); free(zero); free(base); free(res); free(tgt); free(lazy);
+        free(ext); free(baby); free(u); free(acc); free(F); free(v1); free(zero); free(res); free(tgt); free(lazy);
     }
     free(tabs);
 }

@@ -224,6 +224,21 @@ def _mod_down_ref(acc, moduli, psis, L):
     return out
 
 
+def _mod_down_one_ref(acc1, moduli, psis, L):
+    """One component [L+1][N] in the basis q_0..q_{L-1},P -> round(acc / P) as [L][N]."""
+    K = len(moduli)
+    P = moduli[K - 1]
+    half = P // 2
+    t = [(x + half) % P for x in intt_naive(acc1[L], P, psis[K - 1])]
+    out = []
+    for i in range(L):
+        q = moduli[i]
+        d = ntt_naive([(x % q - half % q) % q for x in t], q, psis[i])
+        pinv = pow(P % q, q - 2, q)
+        out.append([(acc1[i][x] - d[x]) * pinv % q for x in range(len(t))])
+    return out
+
+
 def matvec_dh_ref(ct, n1, n2, ptsx, baby_keys, giant_keys, moduli, psis, L, rescale=True, g_first=0):
     """Double-hoisted BSGS matvec (HEGPU_MATVEC_DH) in big integers, written from the description in
     include/hegpu.h -- not from the C oracle.  ct [2][L][N]; ptsx [n1*n2][L+1][N]; keys as in switch_key_ref."""
@@ -243,23 +258,22 @@ def matvec_dh_ref(ct, n1, n2, ptsx, baby_keys, giant_keys, moduli, psis, L, resc
                 b[0][i] = [(b[0][i][x] + P * ct[0][i][tab[x]]) % mods[i] for x in range(n)]
         baby.append(b)
     F = [[[0] * n for _ in range(L + 1)] for _ in range(2)]
-    base0 = [[0] * n for _ in range(L)]
     for g in range(n2):
         u = [[[sum(baby[k][c][I][x] * ptsx[g * n1 + k][I][x] for k in range(n1)) % mods[I] for x in range(n)]
               for I in range(L + 1)] for c in range(2)]
         if g_first + g:
+            # only the component that is key-switched leaves the extended basis; c0 is permuted limb-wise and stays
             tab = galois_table_ntt(n, galois_elt_from_step(n, (g_first + g) * n1))
-            v = _mod_down_ref(u, moduli, psis, L)
-            tgt = [[v[1][i][tab[x]] for x in range(n)] for i in range(L)]
-            for i in range(L):
-                base0[i] = [(base0[i][x] + v[0][i][tab[x]]) % mods[i] for x in range(n)]
-            u = _inner_ref(_decompose_ref(tgt, moduli, psis, L), giant_keys[g], moduli, L)
+            v1 = _mod_down_one_ref(u[1], moduli, psis, L)
+            tgt = [[v1[i][tab[x]] for x in range(n)] for i in range(L)]
+            ks = _inner_ref(_decompose_ref(tgt, moduli, psis, L), giant_keys[g], moduli, L)
+            add = [[[(u[0][I][tab[x]] + ks[0][I][x]) % mods[I] for x in range(n)] for I in range(L + 1)], ks[1]]
+        else:
+            add = u
         for c in range(2):
             for I in range(L + 1):
-                F[c][I] = [(F[c][I][x] + u[c][I][x]) % mods[I] for x in range(n)]
+                F[c][I] = [(F[c][I][x] + add[c][I][x]) % mods[I] for x in range(n)]
     res = _mod_down_ref(F, moduli, psis, L)
-    for i in range(L):
-        res[0][i] = [(res[0][i][x] + base0[i][x]) % mods[i] for x in range(n)]
     return rescale_ref(res, moduli, psis, L) if rescale else res
 
 
