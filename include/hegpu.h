@@ -158,8 +158,10 @@ int hegpu_ntt_inverse_host(hegpu_ctx *ctx, uint64_t *host, uint32_t count, uint3
  *                              for all baby steps, the rotated ciphertexts stay in the extended basis
  *                              q_0..q_{L-1},P scaled by P (no mod-down per baby step), the inner sums
  *                              are taken there against plaintexts that carry a limb mod P
- *                              (hegpu_pt_upload_ext), each rotated giant step costs one mod-down + one
- *                              key-switch without mod-down, and everything shares ONE final mod-down.
+ *                              (hegpu_pt_upload_ext); of a rotated giant step only component 1 (the one that
+ *                              is key-switched) is divided by P, component 0 is permuted in the extended
+ *                              basis (the Galois map acts limb-wise, also mod P) and added to the sum of the
+ *                              key inner products, and everything shares ONE final mod-down.
  *                              n1 <= 32.  Implies HOIST and LAZY.
  * HOIST / LAZY / DH compute the same function up to key-switch noise but different bits than a
  * chain of rotate_vector calls; with neither flag the composite is exactly the chain of SEAL
