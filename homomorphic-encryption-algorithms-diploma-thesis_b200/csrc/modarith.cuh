@@ -141,40 +141,6 @@ __device__ __forceinline__ u64 mont_reduce_wide(u64 hi, u64 lo, const ModConst &
     return csub(csub(mont_reduce_lazy(hi, lo, m), m.q), m.q);
 }
 
-// ---- 30-bit limb form: x = lo + hi * 2^30 for x < 2^60.  Limb products are < 2^60, so up to 16 of
-// them add up in a 64-bit accumulator without carry handling: a 60x60-bit multiply-accumulate is four
-// IMAD.WIDE.U32 and nothing else (the 128-bit form needs the same four multiplies plus ~7 carry /
-// move instructions, several of which ptxas also places on the multiplier pipe).
-struct Limbs30 {
-    u32 lo, hi;
-};
-__device__ __forceinline__ Limbs30 split30(u64 x) { return Limbs30{ (u32)x & 0x3FFFFFFFu, (u32)(x >> 30) }; }
-// both limbs in one 64-bit word (shared-memory staging): low word = lo, high word = hi
-__device__ __forceinline__ u64 pack30(u64 x) { return (x & 0x3FFFFFFFull) | ((x >> 30) << 32); }
-__device__ __forceinline__ Limbs30 unpack30(u64 p) { return Limbs30{ (u32)p, (u32)(p >> 32) }; }
-__device__ __forceinline__ u64 mad_wide(u32 a, u32 b, u64 c)
-{
-    u64 r;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
-    return r;
-}
-struct Acc30 {  // value = c0 + c1 * 2^30 + c2 * 2^60; at most 8 products between two folds (c1 takes two terms each)
-    u64 c0, c1, c2;
-};
-__device__ __forceinline__ void mac30(Acc30 &a, const Limbs30 x, const Limbs30 y)
-{
-    a.c0 = mad_wide(x.lo, y.lo, a.c0);
-    a.c1 = mad_wide(x.lo, y.hi, a.c1);
-    a.c1 = mad_wide(x.hi, y.lo, a.c1);
-    a.c2 = mad_wide(x.hi, y.hi, a.c2);
-}
-__device__ __forceinline__ void fold30(const Acc30 &a, u64 &hi, u64 &lo)
-{
-    const unsigned __int128 t = (unsigned __int128)a.c0 + ((unsigned __int128)a.c1 << 30) + ((unsigned __int128)a.c2 << 60);
-    lo = (u64)t;
-    hi = (u64)(t >> 64);
-}
-
 __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { return csub(a + b, q); }
 __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
 __device__ __forceinline__ u64 negmod(u64 a, u64 q) { return a ? q - a : 0; }
