@@ -74,10 +74,12 @@ __device__ __forceinline__ u64 mulmod(u64 a, u64 b, const ModConst &m)
 // multiplies + three IADD3 on the ALU pipe.  (The plain `unsigned __int128` form compiles to the same four
 // multiplies plus ~7 add / move instructions, a third of them IMAD.X / IMAD.MOV on the multiplier pipe
 // that bounds the multiply-accumulate kernels: measured 9 % slower in dh_inner_kernel.)
+// PRECONDITION x, y < 2^63 (residues and lazy values of moduli up to 61 bits are below 2^62): the two cross
+// products x0*y1 + x1*y0 then stay below 2^64 and their sum needs no carry of its own.
 __device__ __forceinline__ void mac128(u64 &hi, u64 &lo, u64 x, u64 y)
 {
     asm("{\n\t"
-        ".reg .u32 x0, x1, y0, y1, a0, a1, a2, a3, t0, t1, c;\n\t"
+        ".reg .u32 x0, x1, y0, y1, a0, a1, a2, a3, t0, t1;\n\t"
         "mov.b64 {x0, x1}, %2;\n\t"
         "mov.b64 {y0, y1}, %3;\n\t"
         "mov.b64 {a0, a1}, %0;\n\t"
@@ -89,11 +91,10 @@ __device__ __forceinline__ void mac128(u64 &hi, u64 &lo, u64 x, u64 y)
         "mul.lo.u32     t0, x0, y1;\n\t"
         "mul.hi.u32     t1, x0, y1;\n\t"
         "mad.lo.cc.u32  t0, x1, y0, t0;\n\t"
-        "madc.hi.cc.u32 t1, x1, y0, t1;\n\t"
-        "addc.u32       c, 0, 0;\n\t"
+        "madc.hi.u32    t1, x1, y0, t1;\n\t"
         "add.cc.u32     a1, a1, t0;\n\t"
         "addc.cc.u32    a2, a2, t1;\n\t"
-        "addc.u32       a3, a3, c;\n\t"
+        "addc.u32       a3, a3, 0;\n\t"
         "mov.b64 %0, {a0, a1};\n\t"
         "mov.b64 %1, {a2, a3};\n\t"
         "}"
