@@ -1,9 +1,10 @@
 """Multi-GPU plumbing: one process per GPU, torch.distributed over NCCL/NVLink.
 
-The path shards by independent units.  Two shardings are provided:
+The path shards by independent units.  Three shardings are provided:
 
 * batch sharding -- every rank runs the whole matvec on its own slice of the ciphertext batch;
   keys and diagonals are replicated, there is no data-path collective (bench.py, "weak");
+* hybrid -- grid_2d: batch groups of diag_ranks ranks each, diagonal sharding inside a group;
 * diagonal sharding -- rank r owns a contiguous range of giant steps (its n1*cnt diagonals and
   the Galois keys of those giant steps), recomputes the shared baby-step rotations locally and
   produces a partial ciphertext at level L *before* rescale.  The partials are summed with ONE
@@ -22,6 +23,38 @@ def giant_step_range(n2: int, world: int, rank: int) -> tuple[int, int]:
     base, extra = divmod(n2, world)
     first = rank * base + min(rank, extra)
     return first, base + (1 if rank < extra else 0)
+
+
+def grid_2d(world: int, rank: int, diag_ranks: int) -> tuple[int, int, int]:
+    """Hybrid sharding: the ranks form (world / diag_ranks) batch groups of diag_ranks consecutive
+    ranks.  A batch group owns a slice of the ciphertext batch; inside it the giant steps are split
+    (giant_step_range(n2, diag_ranks, diag_rank)) and the partials are summed over the group only.
+    diag_ranks = world is pure diagonal sharding, diag_ranks = 1 pure batch sharding: the baby-step
+    work that diagonal sharding repeats on every rank shrinks with the group size.
+    Returns (batch_group, diag_rank, n_batch_groups)."""
+    if diag_ranks < 1 or world % diag_ranks:
+        raise ValueError("diag_ranks must divide the number of ranks")
+    return rank // diag_ranks, rank % diag_ranks, world // diag_ranks
+
+
+def batch_slice(batch: int, groups: int, group: int) -> tuple[int, int]:
+    """Contiguous split of the ciphertext batch over the batch groups: (first, count)."""
+    return giant_step_range(batch, groups, group)
+
+
+def diag_group(world: int, rank: int, diag_ranks: int):
+    """The torch.distributed group of this rank's batch group (None when it is the whole world or a
+    single rank).  Collective: every rank must call it."""
+    import torch.distributed as dist
+
+    if diag_ranks == world or diag_ranks == 1:
+        return None
+    mine = None
+    for g in range(world // diag_ranks):
+        grp = dist.new_group(ranks=list(range(g * diag_ranks, (g + 1) * diag_ranks)))
+        if rank // diag_ranks == g:
+            mine = grp
+    return mine
 
 
 class _CudaArray:

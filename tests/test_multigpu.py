@@ -84,6 +84,55 @@ def test_diag_sharded_sum_equals_single_process_gloo():
     assert np.array_equal(got, want)
 
 
+def _gloo_worker_2d(rank, world, diag_ranks, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    hegpu_loader.load()
+    from hegpu_b200.multigpu import batch_slice, diag_group, giant_step_range, grid_2d
+
+    S, cts, pts, gk, bk, gkeys = _problem()
+    bg, dr, nbg = grid_2d(world, rank, diag_ranks)
+    group = diag_group(world, rank, diag_ranks)
+    g0, cnt = giant_step_range(N2, diag_ranks, dr)
+    b0, bn = batch_slice(B, nbg, bg)
+    part = S.o.matvec_bsgs(cts[b0:b0 + bn], N1, cnt, pts[g0 * N1:(g0 + cnt) * N1], bk, gkeys[g0:g0 + cnt], hoist=True, lazy=False,
+                           rescale=False, g_first=g0)
+    t = torch.from_numpy(part.view(np.int64))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)  # over the batch group only
+    summed = t.numpy().view(np.uint64)
+    for i, qi in enumerate(S.moduli[:L]):
+        summed[:, :, i, :] %= np.uint64(qi)
+    res = np.stack([S.o.rescale(summed[b]) for b in range(bn)])
+    if dr == 0:
+        q.put((b0, res))
+    dist.destroy_process_group()
+
+
+def test_hybrid_batch_by_diagonal_grid_gloo():
+    """2 batch groups x 2 diagonal ranks (world 4): every batch group sums its own partials; together the
+    groups produce the single-process result bit for bit."""
+    hegpu_loader.load()
+    from hegpu_b200.multigpu import batch_slice, grid_2d
+
+    assert [grid_2d(8, r, 2) for r in (0, 1, 2, 7)] == [(0, 0, 4), (0, 1, 4), (1, 0, 4), (3, 1, 4)]
+    assert [batch_slice(64, 4, g) for g in range(4)] == [(0, 16), (16, 16), (32, 16), (48, 16)]
+    with pytest.raises(ValueError):
+        grid_2d(8, 0, 3)
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = _free_port()
+    procs = [ctxm.Process(target=_gloo_worker_2d, args=(r, 4, 2, port, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    S, cts, pts, gk, bk, gkeys = _problem()
+    want = S.o.matvec_bsgs(cts, N1, N2, pts, bk, gkeys, hoist=True, lazy=False)
+    assert np.array_equal(np.concatenate([got[0], got[1]]), want)
+
+
 @pytest.mark.gpu
 def test_diag_sharded_emulated_on_one_gpu():
     hg = hegpu_loader.load()
