@@ -120,6 +120,7 @@ def lib() -> C.CDLL:
             "hegpu_bfft_stage": [vp, vp, vp, i32, i32],
             "hegpu_fft_butterflies": [vp, vp, vp, vp, vp, vp],
             "hegpu_reduce_fixup": [vp, vp, u32],
+            "hegpu_ct_transparent": [vp, vp, C.POINTER(u32)],
             "hegpu_profile_enable": [vp, i32],
             "hegpu_profile_reset": [vp],
             "hegpu_profile_read": [vp, i32, C.POINTER(dbl), u64p, u64p, u64p],
@@ -338,6 +339,12 @@ class Context:
 
     def reduce_fixup(self, ct, terms: int):
         _ck(lib().hegpu_reduce_fixup(self._h, ct._h, terms))
+
+    def transparent_count(self, ct) -> int:
+        """Number of transparent ciphertexts of the batch (Ciphertext::is_transparent); blocking."""
+        n = C.c_uint32(0)
+        _ck(lib().hegpu_ct_transparent(self._h, ct._h, C.byref(n)))
+        return int(n.value)
 
 
 class CtBatch:

@@ -1313,6 +1313,32 @@ extern "C" int hegpu_reduce_fixup(hegpu_ctx *c, hegpu_ct *t, uint32_t terms)
     return HEGPU_OK;
 }
 
+// ------------------------------------------------------------------------- transparency query
+extern "C" int hegpu_ct_transparent(hegpu_ctx *c, const hegpu_ct *a, uint32_t *count)
+{
+    if (!c || !count) INVALID("null argument");
+    TRY(check_ct(a));
+    TRY(set_device(c));
+    *count = 0;
+    if (a->batch == 0) return HEGPU_OK;
+    TRY(arena_reserve(c, align256((a->batch + 1) / 2)));
+    ArenaPlan ap{ c };
+    u32 *flags = reinterpret_cast<u32 *>(ap.take((a->batch + 1) / 2));
+    CU(cudaMemsetAsync(flags, 0, sizeof(u32) * a->batch, c->stream));
+    const size_t total = (size_t)a->batch * (a->size - 1) * a->L * c->n;
+    {
+        Prof pf(c, PK_ELEMENTWISE, total, total * 8);
+        nonzero_tail_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(a->view(), a->batch, a->size, a->L, c->n, flags);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    std::vector<u32> h(a->batch);
+    CU(cudaMemcpyAsync(h.data(), flags, sizeof(u32) * a->batch, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (u32 f : h) *count += f ? 0u : 1u;
+    return HEGPU_OK;
+}
+
 // ------------------------------------------------------------------------- composites
 template <int N1>
 static void launch_bsgs_inner(hegpu_ctx *c, const BsgsParams &P)

@@ -229,6 +229,23 @@ __global__ void __launch_bounds__(256) fixup_kernel(const CtView v, u32 B, u32 p
     }
 }
 
+// Ciphertext::is_transparent: flags[b] = 1 when some word of the polynomials 1..size-1 of ciphertext b is non-zero
+// (a ciphertext whose polynomials beyond c0 are all zero decrypts without the secret key).
+__global__ void __launch_bounds__(256) nonzero_tail_kernel(const CtView v, u32 B, u32 polys, u32 L, u32 n, u32 *__restrict__ flags)
+{
+    const size_t per_b = (size_t)(polys - 1) * L * n;
+    const size_t total = (size_t)B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        u32 r = (u32)(idx % per_b);
+        const u32 x = r % n;
+        r /= n;
+        const u32 l = r % L, p = 1 + r / L;
+        const bool nz = v.p[b * v.sb + p * v.sp + l * v.sl + x] != 0;
+        if (__any_sync(__activemask(), nz) && nz && flags[b] == 0) flags[b] = 1;  // benign race: every writer stores 1
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // K10: BSGS inner sums for every giant step in one pass over the baby rotations.
 //   inner[g][b][p][l][x] = sum_{k<n1} baby_k[b][p][l][x] * diag[g*n1+k][l][x]  mod q_l

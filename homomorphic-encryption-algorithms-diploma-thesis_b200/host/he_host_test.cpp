@@ -191,6 +191,15 @@ int main(int argc, char **argv)
             try { Ciphertext t = cts[0]; t.set_scale(t.scale() * 2); t += eval % cts[1]; } catch (const std::invalid_argument &e) { ok += std::string(e.what()) == "scale mismatch"; }
             try { Ciphertext t = cts[0]; t <<= eval % gk % 1; } catch (const std::invalid_argument &e) { ok += std::string(e.what()) == "Galois key not present"; }
             try { Ciphertext t = cts[0]; for (int i = 0; i < 10; ++i) t ^= eval; } catch (const std::invalid_argument &e) { ok += std::string(e.what()) == "end of modulus switching chain reached"; }
+            // SEAL_THROW_ON_TRANSPARENT_CIPHERTEXT: a - a has no polynomial beyond c0 that is non-zero
+            {
+                Evaluator strict(ctx);
+                strict.throw_on_transparent = true;
+                try { Ciphertext t = cts[0]; t -= strict % cts[0]; } catch (const std::logic_error &e) { ok += std::string(e.what()) == "result ciphertext is transparent"; }
+                Ciphertext t = cts[0];
+                t += strict % cts[1];  // an ordinary result passes the check
+                ok += 1;
+            }
             std::printf("errors_ok=%d\n", ok);
         } else {
             std::fprintf(stderr, "unknown command %s\n", cmd.c_str());

@@ -11,6 +11,7 @@
 #pragma once
 
 #include <complex>
+#include <cstdlib>
 #include <cstdint>
 #include <memory>
 #include <stdexcept>
@@ -199,39 +200,54 @@ public:
 // seal::Evaluator stand-in: the 17 methods of SURVEY 8b, same names and argument order
 class Evaluator {
 public:
-    explicit Evaluator(const SEALContext &ctx) : ctx_(ctx) {}
+    explicit Evaluator(const SEALContext &ctx) : ctx_(ctx)
+    {
+        if (const char *e = std::getenv("HEGPU_THROW_ON_TRANSPARENT")) throw_on_transparent = std::atoi(e) != 0;
+    }
     const SEALContext &context() const { return ctx_; }
+    // SEAL_THROW_ON_TRANSPARENT_CIPHERTEXT (SEAL's default build): every operation ends with
+    // `if (result.is_transparent()) throw std::logic_error("result ciphertext is transparent")`.  Here the check is
+    // a device reduction plus a blocking read, so it is opt-in (this flag or HEGPU_THROW_ON_TRANSPARENT=1).
+    bool throw_on_transparent = false;
 
-    void negate_inplace(Ciphertext &a) const { check(hegpu_negate(c(), a.handle(), a.handle())); }
-    void negate(const Ciphertext &a, Ciphertext &d) const { check(hegpu_negate(c(), d.prepare(ctx_), a.handle())); }
-    void add_inplace(Ciphertext &a, const Ciphertext &b) const { check(hegpu_add(c(), a.handle(), a.handle(), b.handle())); }
-    void add(const Ciphertext &a, const Ciphertext &b, Ciphertext &d) const { check(hegpu_add(c(), d.prepare(ctx_), a.handle(), b.handle())); }
-    void sub_inplace(Ciphertext &a, const Ciphertext &b) const { check(hegpu_sub(c(), a.handle(), a.handle(), b.handle())); }
-    void sub(const Ciphertext &a, const Ciphertext &b, Ciphertext &d) const { check(hegpu_sub(c(), d.prepare(ctx_), a.handle(), b.handle())); }
-    void add_plain_inplace(Ciphertext &a, const Plaintext &p) const { check(hegpu_add_plain(c(), a.handle(), a.handle(), p.handle(), 0)); }
-    void add_plain(const Ciphertext &a, const Plaintext &p, Ciphertext &d) const { check(hegpu_add_plain(c(), d.prepare(ctx_), a.handle(), p.handle(), 0)); }
-    void sub_plain_inplace(Ciphertext &a, const Plaintext &p) const { check(hegpu_sub_plain(c(), a.handle(), a.handle(), p.handle(), 0)); }
-    void sub_plain(const Ciphertext &a, const Plaintext &p, Ciphertext &d) const { check(hegpu_sub_plain(c(), d.prepare(ctx_), a.handle(), p.handle(), 0)); }
-    void multiply_inplace(Ciphertext &a, const Ciphertext &b) const { check(hegpu_multiply(c(), a.handle(), a.handle(), b.handle())); }
-    void multiply(const Ciphertext &a, const Ciphertext &b, Ciphertext &d) const { check(hegpu_multiply(c(), d.prepare(ctx_), a.handle(), b.handle())); }
-    void square_inplace(Ciphertext &a) const { check(hegpu_square(c(), a.handle(), a.handle())); }
-    void square(const Ciphertext &a, Ciphertext &d) const { check(hegpu_square(c(), d.prepare(ctx_), a.handle())); }
-    void multiply_plain_inplace(Ciphertext &a, const Plaintext &p) const { check(hegpu_multiply_plain(c(), a.handle(), a.handle(), p.handle(), 0)); }
-    void multiply_plain(const Ciphertext &a, const Plaintext &p, Ciphertext &d) const { check(hegpu_multiply_plain(c(), d.prepare(ctx_), a.handle(), p.handle(), 0)); }
-    void relinearize_inplace(Ciphertext &a, const RelinKeys &) const { check(hegpu_relinearize(c(), a.handle(), a.handle())); }
-    void relinearize(const Ciphertext &a, const RelinKeys &, Ciphertext &d) const { check(hegpu_relinearize(c(), d.prepare(ctx_), a.handle())); }
-    void rescale_to_next_inplace(Ciphertext &a) const { check(hegpu_rescale_to_next(c(), a.handle(), a.handle())); }
-    void rescale_to_next(const Ciphertext &a, Ciphertext &d) const { check(hegpu_rescale_to_next(c(), d.prepare(ctx_), a.handle())); }
-    void mod_switch_to_next_inplace(Ciphertext &a) const { check(hegpu_mod_switch_to_next(c(), a.handle(), a.handle())); }
-    void mod_switch_to_next(const Ciphertext &a, Ciphertext &d) const { check(hegpu_mod_switch_to_next(c(), d.prepare(ctx_), a.handle())); }
-    void rotate_vector_inplace(Ciphertext &a, int steps, const GaloisKeys &) const { check(hegpu_rotate_vector(c(), a.handle(), a.handle(), steps)); }
+    void negate_inplace(Ciphertext &a) const { check(hegpu_negate(c(), a.handle(), a.handle())); post(a); }
+    void negate(const Ciphertext &a, Ciphertext &d) const { check(hegpu_negate(c(), d.prepare(ctx_), a.handle())); post(d); }
+    void add_inplace(Ciphertext &a, const Ciphertext &b) const { check(hegpu_add(c(), a.handle(), a.handle(), b.handle())); post(a); }
+    void add(const Ciphertext &a, const Ciphertext &b, Ciphertext &d) const { check(hegpu_add(c(), d.prepare(ctx_), a.handle(), b.handle())); post(d); }
+    void sub_inplace(Ciphertext &a, const Ciphertext &b) const { check(hegpu_sub(c(), a.handle(), a.handle(), b.handle())); post(a); }
+    void sub(const Ciphertext &a, const Ciphertext &b, Ciphertext &d) const { check(hegpu_sub(c(), d.prepare(ctx_), a.handle(), b.handle())); post(d); }
+    void add_plain_inplace(Ciphertext &a, const Plaintext &p) const { check(hegpu_add_plain(c(), a.handle(), a.handle(), p.handle(), 0)); post(a); }
+    void add_plain(const Ciphertext &a, const Plaintext &p, Ciphertext &d) const { check(hegpu_add_plain(c(), d.prepare(ctx_), a.handle(), p.handle(), 0)); post(d); }
+    void sub_plain_inplace(Ciphertext &a, const Plaintext &p) const { check(hegpu_sub_plain(c(), a.handle(), a.handle(), p.handle(), 0)); post(a); }
+    void sub_plain(const Ciphertext &a, const Plaintext &p, Ciphertext &d) const { check(hegpu_sub_plain(c(), d.prepare(ctx_), a.handle(), p.handle(), 0)); post(d); }
+    void multiply_inplace(Ciphertext &a, const Ciphertext &b) const { check(hegpu_multiply(c(), a.handle(), a.handle(), b.handle())); post(a); }
+    void multiply(const Ciphertext &a, const Ciphertext &b, Ciphertext &d) const { check(hegpu_multiply(c(), d.prepare(ctx_), a.handle(), b.handle())); post(d); }
+    void square_inplace(Ciphertext &a) const { check(hegpu_square(c(), a.handle(), a.handle())); post(a); }
+    void square(const Ciphertext &a, Ciphertext &d) const { check(hegpu_square(c(), d.prepare(ctx_), a.handle())); post(d); }
+    void multiply_plain_inplace(Ciphertext &a, const Plaintext &p) const { check(hegpu_multiply_plain(c(), a.handle(), a.handle(), p.handle(), 0)); post(a); }
+    void multiply_plain(const Ciphertext &a, const Plaintext &p, Ciphertext &d) const { check(hegpu_multiply_plain(c(), d.prepare(ctx_), a.handle(), p.handle(), 0)); post(d); }
+    void relinearize_inplace(Ciphertext &a, const RelinKeys &) const { check(hegpu_relinearize(c(), a.handle(), a.handle())); post(a); }
+    void relinearize(const Ciphertext &a, const RelinKeys &, Ciphertext &d) const { check(hegpu_relinearize(c(), d.prepare(ctx_), a.handle())); post(d); }
+    void rescale_to_next_inplace(Ciphertext &a) const { check(hegpu_rescale_to_next(c(), a.handle(), a.handle())); post(a); }
+    void rescale_to_next(const Ciphertext &a, Ciphertext &d) const { check(hegpu_rescale_to_next(c(), d.prepare(ctx_), a.handle())); post(d); }
+    void mod_switch_to_next_inplace(Ciphertext &a) const { check(hegpu_mod_switch_to_next(c(), a.handle(), a.handle())); post(a); }
+    void mod_switch_to_next(const Ciphertext &a, Ciphertext &d) const { check(hegpu_mod_switch_to_next(c(), d.prepare(ctx_), a.handle())); post(d); }
+    void rotate_vector_inplace(Ciphertext &a, int steps, const GaloisKeys &) const { check(hegpu_rotate_vector(c(), a.handle(), a.handle(), steps)); post(a); }
     void rotate_vector(const Ciphertext &a, int steps, const GaloisKeys &, Ciphertext &d) const
     {
         check(hegpu_rotate_vector(c(), d.prepare(ctx_), a.handle(), steps));
+        post(d);
     }
 
 private:
     hegpu_ctx *c() const { return ctx_.raw(); }
+    void post(const Ciphertext &r) const
+    {
+        if (!throw_on_transparent) return;
+        std::uint32_t cnt = 0;
+        check(hegpu_ct_transparent(c(), r.handle(), &cnt));
+        if (cnt) throw std::logic_error("result ciphertext is transparent");
+    }
     const SEALContext &ctx_;
 };
 

@@ -218,6 +218,13 @@ const char *hegpu_profile_kind_name(int kind);
 int hegpu_profile_read(hegpu_ctx *ctx, int kind, double *ms_total, uint64_t *launches, uint64_t *units,
                        uint64_t *algo_bytes);
 
+/* ---- Ciphertext::is_transparent (SEAL 4.1 ciphertext.h; checked after every Evaluator operation when SEAL is
+ * built with SEAL_THROW_ON_TRANSPARENT_CIPHERTEXT, its default: std::logic_error("result ciphertext is
+ * transparent")).  *count = number of ciphertexts of the batch whose polynomials 1..size-1 are all zero.
+ * Blocking (one reduction kernel + a device-to-host read): the adapter calls it after an operation only when
+ * the check is switched on (host/hegpu_seal_like.hpp: Evaluator::throw_on_transparent). */
+int hegpu_ct_transparent(hegpu_ctx *ctx, const hegpu_ct *ct, uint32_t *count);
+
 /* ---- multi-GPU: after an NCCL uint64 sum of `terms` partial ciphertexts the
  * residues are < terms*q; reduce them back to [0,q). */
 int hegpu_reduce_fixup(hegpu_ctx *ctx, hegpu_ct *ct, uint32_t terms);

@@ -136,6 +136,26 @@ def test_error_behaviour_matches_seal(hg):
         ctx.relinearize(out, out)
 
 
+def test_transparent_ciphertext_query(hg):
+    """Ciphertext::is_transparent (SEAL 4.1): polynomials 1..size-1 all zero; the adapter turns a non-zero count
+    into std::logic_error("result ciphertext is transparent") when the check is switched on."""
+    S = setup(4096, (36, 36, 37))
+    ctx = make_ctx(hg, S)
+    rng = np.random.default_rng(4)
+    a = rand_residues(rng, S.moduli[:2], (3, 2), S.n)
+    a[1, 1] = 0  # second ciphertext: c1 = 0
+    A = ctx.upload_ct(a, 2.0**20)
+    assert ctx.transparent_count(A) == 1
+    a[1, 1, 1, 77] = 5  # one non-zero word anywhere in c1 is enough
+    assert ctx.transparent_count(ctx.upload_ct(a, 2.0**20)) == 0
+    out = ctx.ct(3)
+    ctx.sub(out, A, A)
+    assert ctx.transparent_count(out) == 3
+    a3 = rand_residues(rng, S.moduli[:2], (2, 3), S.n)
+    a3[0, 2] = 0  # size 3 with c2 = 0 but c1 != 0: not transparent
+    assert ctx.transparent_count(ctx.upload_ct(a3, 2.0**20)) == 0
+
+
 # ------------------------------------------------------------------ rescale / key switching
 @pytest.mark.parametrize("n,bits", [(8192, (60, 40, 40, 60)), (16384, (60, 31, 30, 30, 30, 60)), (4096, (36, 36, 37)),
                                     (32768, (60, 40, 40, 60))])

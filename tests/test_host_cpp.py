@@ -101,7 +101,7 @@ def test_errors_keep_seal_types_and_messages(tmp_path):
     rng = np.random.default_rng(2)
     a = rand_residues(rng, S.moduli[:3], (2,), S.n)
     _, _, _, stdout = run(tmp_path, S, "errors", [], cts=[(a, 2.0**40), (a, 2.0**40)])
-    assert "errors_ok=3" in stdout
+    assert "errors_ok=5" in stdout
 
 
 @pytest.mark.parametrize("case_b", [0, 1])
