@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
             "hegpu_ct_copy_wait": [vp],
             "hegpu_ct_info": [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(dbl)],
             "hegpu_ct_set_scale": [vp, dbl],
+            "hegpu_ct_set_meta": [vp, u32, u32, dbl],
             "hegpu_ct_copy": [vp, vp, vp],
             "hegpu_ct_copy_one": [vp, vp, u32, vp, u32],
             "hegpu_ct_device_view": [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)],
@@ -421,6 +422,10 @@ class CtBatch:
 
     def copy_from(self, src: "CtBatch"):
         _ck(lib().hegpu_ct_copy(self.ctx._h, self._h, src._h))
+
+    def set_meta(self, size: int, L: int, scale: float):
+        """Declare the contents after the device buffer was filled externally (NCCL receive)."""
+        _ck(lib().hegpu_ct_set_meta(self._h, size, L, float(scale)))
 
     def device_view(self):
         p, sb, sp, sl = C.c_void_p(), C.c_size_t(), C.c_size_t(), C.c_size_t()

@@ -618,6 +618,15 @@ extern "C" int hegpu_ct_set_scale(hegpu_ct *t, double scale)
     t->scale = scale;
     return HEGPU_OK;
 }
+extern "C" int hegpu_ct_set_meta(hegpu_ct *t, uint32_t size, uint32_t L, double scale)
+{
+    if (!t) INVALID("null argument");
+    if (size < 2 || size > t->size_cap || L == 0 || L > t->L_cap) INVALID("size or level exceeds the batch's capacity");
+    t->size = size;
+    t->L = L;
+    t->scale = scale;
+    return HEGPU_OK;
+}
 extern "C" int hegpu_ct_device_view(hegpu_ct *t, void **dptr, size_t *sb, size_t *sp, size_t *sl)
 {
     if (!t) INVALID("null argument");

@@ -86,6 +86,28 @@ def allreduce_sum(ct, world: int, group=None):
     ctx.reduce_fixup(ct, world)
 
 
+def reduce_scatter_sum(part, mine, world: int, group=None):
+    """Sum of the partial ciphertext batches over the ranks, scattered over the batch dimension:
+    rank r of the group receives ciphertexts [r*B/world, (r+1)*B/world) of the sum in `mine` (canonical residues).
+    Half the bytes of an all-reduce on the wire, and every rank rescales only its own share afterwards."""
+    import torch
+    import torch.distributed as dist
+
+    ctx = part.ctx
+    if world > 16:
+        raise ValueError("at most 16 partial sums of 60-bit residues fit in 64 bits; reduce hierarchically")
+    if part.batch % world or mine.batch != part.batch // world:
+        raise ValueError("the batch must split evenly over the ranks of the group")
+    src, dst = as_torch_i64(part), as_torch_i64(mine)
+    if dst.numel() * world != src.numel():
+        raise ValueError("partial and scattered batches must share their layout (size_cap, L_cap)")
+    with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream, device=ctx.device)):
+        dist.reduce_scatter_tensor(dst, src, op=dist.ReduceOp.SUM, group=group)
+    _, _, L, scale = part.info()
+    mine.set_meta(2, L, scale)
+    ctx.reduce_fixup(mine, world)
+
+
 def matvec_bsgs_diag_sharded(ctx, out, x, diags_local, n1: int, n2_total: int, rank: int, world: int, hoist: bool = True,
                              partial=None, group=None, dh: bool = False):
     """Diagonal-sharded BSGS matvec.  diags_local holds the n1*cnt pre-rotated diagonals of this

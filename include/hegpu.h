@@ -84,6 +84,9 @@ int hegpu_ct_download_async(hegpu_ct *ct, uint64_t *host);
 int hegpu_ct_copy_wait(hegpu_ct *ct);
 int hegpu_ct_info(const hegpu_ct *ct, uint32_t *batch, uint32_t *size, uint32_t *L, double *scale);
 int hegpu_ct_set_scale(hegpu_ct *ct, double scale);
+/* declare what a batch holds after its device buffer was written through hegpu_ct_device_view (e.g. by an NCCL
+ * receive): `size` polynomials at level L with the given scale, strides as reported by hegpu_ct_device_view */
+int hegpu_ct_set_meta(hegpu_ct *ct, uint32_t size, uint32_t L, double scale);
 int hegpu_ct_copy(hegpu_ctx *ctx, hegpu_ct *dst, const hegpu_ct *src);
 /* copy src[src_index] into dst[dst_index] (metadata must agree or dst is uninitialised) */
 int hegpu_ct_copy_one(hegpu_ctx *ctx, hegpu_ct *dst, uint32_t dst_index, const hegpu_ct *src, uint32_t src_index);

@@ -53,7 +53,12 @@ def _gloo_worker(rank, world, port, q):
     part = S.o.matvec_bsgs(cts, N1, cnt, pts[g0 * N1:(g0 + cnt) * N1], bk, gkeys[g0:g0 + cnt], hoist=True, lazy=False,
                            rescale=False, g_first=g0)
     t = torch.from_numpy(part.view(np.int64))
+    # reduce-scatter over the batch dimension (multigpu.reduce_scatter_sum): rank r receives its share of the sum
+    share = torch.empty(t.numel() // world, dtype=torch.int64)
+    dist.reduce_scatter_tensor(share, t.reshape(-1).clone(), op=dist.ReduceOp.SUM)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)  # uint64 sum == int64 sum bit for bit
+    per = B // world
+    assert torch.equal(share, t[rank * per:(rank + 1) * per].reshape(-1))
     summed = t.numpy().view(np.uint64)
     for i, qi in enumerate(S.moduli[:L]):
         summed[:, :, i, :] %= np.uint64(qi)  # what hegpu_reduce_fixup does on the device
@@ -216,8 +221,18 @@ def _nccl_worker(rank, world, port, q):
     D = ctx.upload_pt(pts[g0 * N1:(g0 + cnt) * N1], SCALE, L_cap=L)
     out = ctx.ct(B, 2, L - 1)
     matvec_bsgs_diag_sharded(ctx, out, X, D, N1, N2, rank, world, hoist=True)
+    # the same sum as a reduce-scatter over the batch: this rank ends with ciphertexts [rank*B/world, ...) only
+    from hegpu_b200.multigpu import reduce_scatter_sum
+
+    part, mine, out_rs = ctx.ct(B, 2, L), ctx.ct(B // world, 2, L), ctx.ct(B // world, 2, L - 1)
+    ctx.matvec_bsgs(part, X, D, N1, cnt, rescale=False, hoist=True, lazy=False, g_first=g0)
+    reduce_scatter_sum(part, mine, world)
+    ctx.rescale_to_next(out_rs, mine)
+    per = B // world
+    full = out.download()
+    assert np.array_equal(out_rs.download(), full[rank * per:(rank + 1) * per])
     if rank == 0:
-        q.put(out.download())
+        q.put(full)
     dist.barrier()
     dist.destroy_process_group()
 
