@@ -1416,7 +1416,8 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
         return align256((size_t)Bc * L * n) + align256((size_t)Bc * L * (L + 1) * n) + align256(inv_scratch_words(c, (size_t)Bc * std::max<u32>(L, 2))) +
                align256((size_t)nbaby * Bc * accw) + align256((size_t)n2 * Bc * accw) + align256((size_t)nr1 * Bc * ctw) +
                align256((size_t)nr1 * Bc * 2 * n) + align256(inv_scratch_words(c, (size_t)nr1 * Bc * 2)) + align256((size_t)Bc * accw) +
-               align256((size_t)Bc * 2 * n) + 2 * align256((size_t)Bc * ctw) + ks_scratch(c, (size_t)nr1 * Bc, L) + rescale_scratch(c, Bc, 2);
+               align256((size_t)Bc * 2 * n) + 2 * align256((size_t)Bc * ctw) + align256((size_t)Bc * L * n) +
+               ks_scratch(c, (size_t)nr1 * Bc, L) + rescale_scratch(c, Bc, 2);
     };
     // two execution slots: alternate batch chunks go to the main and the auxiliary stream (own scratch
     // each), so the small grids of one chunk (a single wave of NTT CTAs) overlap the other chunk's kernels
@@ -1455,6 +1456,7 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
         u64 *accsum = ap.take((size_t)Bc * accw);
         u64 *tsum = ap.take((size_t)Bc * 2 * n);
         u64 *accb = ap.take((size_t)Bc * ctw);
+        u64 *c0p = ap.take((size_t)Bc * L * n);
         auto view_of = [&](u64 *p, size_t batch_off) { return CtView{ p + batch_off * ctw, ctw, (size_t)L * n, n }; };
         auto qp_view = [&](u64 *p, size_t batch_off) { return CtView{ p + batch_off * accw, accw, (size_t)(L + 1) * n, n }; };
         const CtView vin = in->view_at(b0);
@@ -1476,8 +1478,16 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
         TRY(ks_decompose(c, pl0));
         if (fused) {
             // 2-4 fused: baby-step key inner products and the inner sums of every giant step in one kernel
+            {   // P * c0 once per ciphertext instead of one product per baby step inside dh_inner
+                const size_t total = (size_t)Bn * L * n;
+                Prof pf(c, PK_ELEMENTWISE, total, total * 16);
+                scale_c0_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(vin, c0p, Bn, L, c->n, c->d_mods);
+                c->launches++;
+                CU(cudaGetLastError());
+            }
             DhInnerParams P{};
             P.in = vin;
+            P.c0p = c0p;
             P.ext = ext;
             for (u32 k = 1; k < n1; ++k) {
                 P.key[k] = c->galois_keys[belt[k]];

@@ -365,6 +365,7 @@ struct DhInnerParams {
     const u32 *perm[MAXB]; // gather table of baby step k; [0] unused
     const u64 *diag;       // [n1*n2][Lcap][N] Montgomery form, limb L = special prime
     size_t diag_si;
+    const u64 *c0p;        // [B][L][N]: P * c0 mod q_i (scale_c0_kernel), gathered into b_k[0] instead of a product per baby step
     u64 *u;                // [n2][B][2][L+1][N]
     u32 n1, n2, B, L, K, n;
     u32 g0, ng;            // this launch accumulates giant steps g0 .. g0+ng-1 (ng <= N2)
@@ -398,12 +399,16 @@ struct DhArI64 {
     static __device__ __forceinline__ Opnd from_staged(u64 v) { return v; }
     static __device__ __forceinline__ Acc zero() { return Acc{ 0, 0 }; }
     static __device__ __forceinline__ void mac(Acc &a, Opnd x, Opnd y) { mac128(a.h, a.l, x, y); }
-    // b_k only feeds further products: below 2q is enough (n1 <= 32 products of a value < 2q < 2^61 and a
-    // canonical diagonal word stay below 2^126)
-    static __device__ __forceinline__ u64 reduce(const Acc &a, const ModConst &m) { return mont_reduce_lazy(a.h, a.l, m); }
+    // b_k only feeds further products: a lazy value is enough (n1 <= 32 products of a value < 2.2 q < 2^62 and a
+    // canonical diagonal word stay below 2^127)
+    // `add` (canonical) joins the result: (hi:lo) + add * 2^64 reduces to (hi:lo) * 2^-64 + add.  With three key
+    // products below q^2 <= q * 2^60 the result stays below 2.2 q.
+    static __device__ __forceinline__ u64 reduce(const Acc &a, u64 add, const ModConst &m) { return mont_reduce_lazy(a.h + add, a.l, m); }
     static __device__ __forceinline__ u64 reduce_wide(const Acc &a, const ModConst &m)
     {
-        return csub(mont_reduce_wide(a.h, a.l, m), m.q);  // sum < 4 * q * 2^64: one more subtraction than the canonical-operand bound
+        // 32 products of a value below 2.2 q and a canonical word: sum < 4.4 * q * 2^64, reduced value < 5.4 q
+        const u64 r = mont_reduce_lazy(a.h, a.l, m);
+        return csub(csub(csub(r, 4 * m.q), 2 * m.q), m.q);
     }
 };
 struct DhArF64 {
@@ -424,13 +429,13 @@ struct DhArF64 {
         a.c1 = __fma_rn(x.hi, y.lo, a.c1);
         a.c2 = __fma_rn(x.hi, y.hi, a.c2);
     }
-    static __device__ __forceinline__ u64 reduce(const Acc &a, const ModConst &m)
+    static __device__ __forceinline__ u64 reduce(const Acc &a, u64 add, const ModConst &m)
     {
         const unsigned __int128 t = (unsigned __int128)f64_to_u64(a.c0) + ((unsigned __int128)f64_to_u64(a.c1) << 20) +
                                     ((unsigned __int128)f64_to_u64(a.c2) << 40);
-        return mont_reduce_lazy((u64)(t >> 64), (u64)t, m);  // t < 64 * 2^82 << q * 2^64; result < 2q < 2^41
+        return mont_reduce_lazy((u64)(t >> 64) + add, (u64)t, m);  // t < 64 * 2^83 << q * 2^64; result < add + q + 1 < 2^41
     }
-    static __device__ __forceinline__ u64 reduce_wide(const Acc &a, const ModConst &m) { return csub(reduce(a, m), m.q); }
+    static __device__ __forceinline__ u64 reduce_wide(const Acc &a, const ModConst &m) { return csub(reduce(a, 0, m), m.q); }
 };
 
 template <int LT, int N2, class Ar>
@@ -466,7 +471,7 @@ __device__ __forceinline__ void dh_inner_body(const DhInnerParams &P, const ModC
             const u64 *eb = P.ext + ((size_t)b * L * (L + 1) + i) * n;
 #pragma unroll
             for (int j = 0; j < LT; ++j) src[j] = ((u32)j == i) ? cb + P.in.sp + j * P.in.sl : eb + (size_t)j * (L + 1) * n;
-            src[LT] = cb + (data_limb ? i : 0) * P.in.sl;
+            src[LT] = P.c0p + ((size_t)b * L + (data_limb ? i : 0)) * n;  // P * c0, limb i
         }
         auto fetch = [&](u32 k, u64 (&d)[LT + 1]) {
             const u32 xs = sperm[k * TX + lane];
@@ -484,11 +489,10 @@ __device__ __forceinline__ void dh_inner_body(const DhInnerParams &P, const ModC
         auto step = [&](u32 k, const u64 (&cur)[LT + 1], u64 (&nxt)[LT + 1]) {
             if (k + 2 < n1) fetch(k + 2, nxt);
             typename Ar::Acc s0 = Ar::zero(), s1 = Ar::zero();
-            if (k == 0) {  // b_0 = P * (c0, c1)
+            if (k == 0) {  // b_0 = P * (c0, c1): component 0 is the gathered word itself
                 u64 w1 = cur[0];
 #pragma unroll
                 for (int j = 1; j < LT; ++j) w1 = ((u32)j == i) ? cur[j] : w1;
-                Ar::mac(s0, Ar::from_word(cur[LT]), pm);
                 Ar::mac(s1, Ar::from_word(w1), pm);
             } else {
                 const u64 *kp = skey + (size_t)k * 2 * L * TX + lane;
@@ -498,9 +502,9 @@ __device__ __forceinline__ void dh_inner_body(const DhInnerParams &P, const ModC
                     Ar::mac(s0, dj, Ar::from_staged(kp[(2 * j) * TX]));
                     Ar::mac(s1, dj, Ar::from_staged(kp[(2 * j + 1) * TX]));
                 }
-                Ar::mac(s0, Ar::from_word(cur[LT]), pm);
             }
-            const typename Ar::Opnd a0 = Ar::from_word(Ar::reduce(s0, m)), a1 = Ar::from_word(Ar::reduce(s1, m));
+            // b_k[0] = key products + P * pi_k(c0): the pre-scaled word joins the Montgomery reduction
+            const typename Ar::Opnd a0 = Ar::from_word(Ar::reduce(s0, cur[LT], m)), a1 = Ar::from_word(Ar::reduce(s1, 0, m));
             const u64 *dp = sdiag + (size_t)k * N2 * TX + lane;
 #pragma unroll
             for (int g = 0; g < N2; ++g) {
@@ -659,6 +663,23 @@ __global__ void __launch_bounds__(256) scale_by_p_kernel(const CtView in, u64 *_
             v = mont_reduce(h, lo, m);
         }
         out[idx] = v;
+    }
+}
+
+// P * c0 mod q_i for the fused double-hoisted inner kernel: out[b][i][x], canonical
+__global__ void __launch_bounds__(256) scale_c0_kernel(const CtView in, u64 *__restrict__ out, u32 B, u32 L, u32 n,
+                                                       const ModConst *__restrict__ mods)
+{
+    const size_t per_b = (size_t)L * n;
+    const size_t total = (size_t)B * per_b;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(idx / per_b);
+        const u32 r = (u32)(idx % per_b);
+        const u32 x = r % n, i = r / n;
+        const ModConst m = mods[i];
+        u64 h = 0, lo = 0;
+        mac128(h, lo, in.p[b * in.sb + i * in.sl + x], m.pmont);
+        out[idx] = mont_reduce(h, lo, m);
     }
 }
 
