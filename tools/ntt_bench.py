@@ -3,6 +3,7 @@
 batch of limb polynomials resident in HBM, GB/s at the algorithmic 16*N bytes per limb.
 
   python tools/ntt_bench.py [--n 16384] [--count 4096] [--iters 20] [--bits 60,40,40,60]
+  python tools/ntt_bench.py --sweep      # N in {8192, 16384, 32768} x batches of 1 .. 4096 limbs, one JSON line each
 """
 import argparse
 import json
@@ -15,6 +16,24 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--count", type=int, default=4096)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--bits", default="60,40,40,60")
+    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--sweep", action="store_true")
+    a = ap.parse_args()
+    if a.sweep:
+        for n in (8192, 16384, 32768):
+            for count in (1, 16, 256, 4096):
+                a.n, a.count, a.check = n, count, count == 16
+                run(a)
+    else:
+        run(a)
+
+
+def run(a):
     import torch
 
     import hegpu_loader
@@ -22,13 +41,6 @@ def main():
     hg = hegpu_loader.load()
     from hegpu_b200.client import coeff_modulus_create
 
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=16384)
-    ap.add_argument("--count", type=int, default=4096)
-    ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--bits", default="60,40,40,60")
-    ap.add_argument("--check", action="store_true")
-    a = ap.parse_args()
     bits = [int(x) for x in a.bits.split(",")]
     moduli = coeff_modulus_create(a.n, bits)
     ctx = hg.Context(a.n, moduli)
@@ -61,7 +73,7 @@ def main():
     if a.check:  # fwd then inv the same number of times must return the input
         back = d.cpu().numpy().view(np.uint64)
         out["roundtrip_ok"] = bool(np.array_equal(back, host))
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":
