@@ -175,6 +175,7 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     if (const char *e = getenv("HEGPU_DH_FUSED")) c->dh_fused = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_F64")) c->dh_f64 = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_FUSE_FINAL")) c->fuse_final = atoi(e) != 0;
+    if (const char *e = getenv("HEGPU_PARK32K")) c->park32k = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->main_stream = c->stream;
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -1432,7 +1433,7 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
         const size_t park_need = (size_t)nr1 * Bc * (L * L + 2 * L) * (n / 2);  // largest NTT launch of a chunk
         for (int sl = 0; sl < NS; ++sl) {
             select_slot(c, sl);
-            if (c->logn == 14 && c->use_park) TRY(park_reserve(c, park_need));
+            if ((c->logn == 14 || (c->logn == 15 && c->park32k)) && c->use_park) TRY(park_reserve(c, park_need));
         }
         select_slot(c, 0);
         CU(cudaEventRecord(c->ev_fork, c->main_stream));

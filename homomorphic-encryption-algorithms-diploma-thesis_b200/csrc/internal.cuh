@@ -99,6 +99,7 @@ struct hegpu_ctx {
     int sms = 148;
     int dh_f64 = 1;    // fused kernel: FP64-pipe arithmetic on the limbs whose modulus is below 2^40 (HEGPU_DH_F64=0: integer everywhere)
     int fuse_final = 1;  // double-hoisted matvec: final mod-down and rescale as one pass (HEGPU_FUSE_FINAL=0: two steps)
+    int park32k = 1;     // N = 32768: one CTA per transform with the park scheme (HEGPU_PARK32K=0: two CTAs + finishing pass)
     int dh_fused = 1;  // double-hoisted matvec: fused baby-step + inner-sum kernel (HEGPU_DH_FUSED=0: unfused kernels)
     int loge = 3;  // NTT register-set size at N = 16384: 3 = radix-8 passes, 256 threads x 80 registers, 3 CTAs per SM (HEGPU_LOGE=4: radix-16, 2 CTAs)
     size_t ws_budget = (size_t)24 << 30;  // scratch budget per composite chunk

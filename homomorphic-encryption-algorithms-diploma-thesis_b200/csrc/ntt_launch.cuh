@@ -65,7 +65,9 @@ int launch_ntt_fwd(hegpu_ctx *c, const Job &job, u32 jobs, int kind, u64 words_p
             return c->loge == 3 ? launch_fwd_park<13, 3>(c, job, jobs, kind, words_per_job)
                                 : launch_fwd_park<13, 4>(c, job, jobs, kind, words_per_job);
         return launch_fwd_shape<14, 0, 4>(c, job, jobs, kind, words_per_job);
-    case 15: return launch_fwd_shape<14, 1, 4>(c, job, jobs, kind, words_per_job);
+    case 15:
+        if (c->use_park && c->park32k) return launch_fwd_park<14, 4>(c, job, jobs, kind, words_per_job);
+        return launch_fwd_shape<14, 1, 4>(c, job, jobs, kind, words_per_job);
     }
     LOGIC("unsupported ring degree");
 }
@@ -103,7 +105,9 @@ int launch_ntt_inv(hegpu_ctx *c, const Job &job, u32 jobs, u64 *scratch, int kin
         if (c->use_park)
             return c->loge == 3 ? launch_inv_park<13, 3>(c, job, jobs, kind) : launch_inv_park<13, 4>(c, job, jobs, kind);
         return launch_inv_shape<14, 0, 4>(c, job, jobs, scratch, kind);
-    case 15: return launch_inv_shape<14, 1, 4>(c, job, jobs, scratch, kind);
+    case 15:
+        if (c->use_park && c->park32k) return launch_inv_park<14, 4>(c, job, jobs, kind);
+        return launch_inv_shape<14, 1, 4>(c, job, jobs, scratch, kind);
     }
     LOGIC("unsupported ring degree");
 }
