@@ -2,6 +2,7 @@
 // inner sums (unfused and double-hoisted fused), accumulations, repacking.  Included by hegpu.cu only
 // (the NTT kernels and their job resolvers live in kernels.cuh, shared with the ntt_inst_*.cu units).
 #pragma once
+#include <type_traits>
 #include "kernels.cuh"
 
 namespace hegpu {
@@ -485,26 +486,8 @@ __device__ __forceinline__ void dh_inner_body(const DhInnerParams &P, const ModC
         u64 d0[LT + 1], d1[LT + 1], d2[LT + 1];
         fetch(0, d0);
         if (n1 > 1) fetch(1, d1);
-        // one baby step: start the gathers of step k+2 into `nxt`, then consume `cur`
-        auto step = [&](u32 k, const u64 (&cur)[LT + 1], u64 (&nxt)[LT + 1]) {
-            if (k + 2 < n1) fetch(k + 2, nxt);
-            typename Ar::Acc s0 = Ar::zero(), s1 = Ar::zero();
-            if (k == 0) {  // b_0 = P * (c0, c1): component 0 is the gathered word itself
-                u64 w1 = cur[0];
-#pragma unroll
-                for (int j = 1; j < LT; ++j) w1 = ((u32)j == i) ? cur[j] : w1;
-                Ar::mac(s1, Ar::from_word(w1), pm);
-            } else {
-                const u64 *kp = skey + (size_t)k * 2 * L * TX + lane;
-#pragma unroll
-                for (int j = 0; j < LT; ++j) {
-                    const typename Ar::Opnd dj = Ar::from_word(cur[j]);
-                    Ar::mac(s0, dj, Ar::from_staged(kp[(2 * j) * TX]));
-                    Ar::mac(s1, dj, Ar::from_staged(kp[(2 * j + 1) * TX]));
-                }
-            }
-            // b_k[0] = key products + P * pi_k(c0): the pre-scaled word joins the Montgomery reduction
-            const typename Ar::Opnd a0 = Ar::from_word(Ar::reduce(s0, cur[LT], m)), a1 = Ar::from_word(Ar::reduce(s1, 0, m));
+        // the tail of a baby step: b_k -> the 2 * n2 giant-step sums
+        auto feed = [&](u32 k, const typename Ar::Opnd a0, const typename Ar::Opnd a1) {
             const u64 *dp = sdiag + (size_t)k * N2 * TX + lane;
 #pragma unroll
             for (int g = 0; g < N2; ++g) {
@@ -513,10 +496,42 @@ __device__ __forceinline__ void dh_inner_body(const DhInnerParams &P, const ModC
                 Ar::mac(acc[g][1], a1, dg);
             }
         };
-        for (u32 k = 0; k < n1; k += 3) {  // the three operand sets rotate by name, not by copying
-            step(k, d0, d2);
-            if (k + 1 < n1) step(k + 1, d1, d0);
-            if (k + 2 < n1) step(k + 2, d2, d1);
+        // baby step 0: b_0 = P * (c0, c1); component 0 is the gathered (pre-scaled) word itself
+        {
+            if (2 < n1) fetch(2, d2);
+            u64 w1 = d0[0];
+#pragma unroll
+            for (int j = 1; j < LT; ++j) w1 = ((u32)j == i) ? d0[j] : w1;
+            typename Ar::Acc s1 = Ar::zero();
+            Ar::mac(s1, Ar::from_word(w1), pm);
+            feed(0, Ar::from_word(d0[LT]), Ar::from_word(Ar::reduce(s1, 0, m)));
+        }
+        // baby step k >= 1: start the gathers of step k+2 into `nxt` (GUARD: only if it exists), then consume `cur`
+        auto step = [&](auto guard, u32 k, const u64 (&cur)[LT + 1], u64 (&nxt)[LT + 1]) {
+            if (!decltype(guard)::value || k + 2 < n1) fetch(k + 2, nxt);
+            typename Ar::Acc s0 = Ar::zero(), s1 = Ar::zero();
+            const u64 *kp = skey + (size_t)k * 2 * L * TX + lane;
+#pragma unroll
+            for (int j = 0; j < LT; ++j) {
+                const typename Ar::Opnd dj = Ar::from_word(cur[j]);
+                Ar::mac(s0, dj, Ar::from_staged(kp[(2 * j) * TX]));
+                Ar::mac(s1, dj, Ar::from_staged(kp[(2 * j + 1) * TX]));
+            }
+            // b_k[0] = key products + P * pi_k(c0): the pre-scaled word joins the Montgomery reduction
+            feed(k, Ar::from_word(Ar::reduce(s0, cur[LT], m)), Ar::from_word(Ar::reduce(s1, 0, m)));
+        };
+        // the three operand sets rotate by name, not by copying; whole triples run without range checks so that
+        // the loop body is one straight block (no register moves where guarded paths would merge)
+        u32 k = 1;
+        for (; k + 4 < n1; k += 3) {
+            step(std::false_type{}, k, d1, d0);
+            step(std::false_type{}, k + 1, d2, d1);
+            step(std::false_type{}, k + 2, d0, d2);
+        }
+        for (; k < n1; k += 3) {
+            step(std::true_type{}, k, d1, d0);
+            if (k + 1 < n1) step(std::true_type{}, k + 1, d2, d1);
+            if (k + 2 < n1) step(std::true_type{}, k + 2, d0, d2);
         }
 #pragma unroll
         for (int g = 0; g < N2; ++g) {
