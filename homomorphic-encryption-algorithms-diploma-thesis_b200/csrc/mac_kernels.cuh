@@ -419,9 +419,14 @@ struct DhArF64 {
     struct Acc {
         double c0, c1, c2;
     };
-    static __device__ __forceinline__ u64 stage(u64 v) { return (v & 0xFFFFFull) | ((v >> 20) << 32); }
+    // staged words (keys, diagonals; canonical, below 2^40): the two 20-bit limbs as a pair of floats, exact, so
+    // that a use costs one F2F.F64.F32 per limb on the conversion unit instead of mask / pair-move / DADD
+    static __device__ __forceinline__ u64 stage(u64 v)
+    {
+        return (u64)__float_as_uint((float)((u32)v & 0xFFFFFu)) | ((u64)__float_as_uint((float)(u32)(v >> 20)) << 32);
+    }
     static __device__ __forceinline__ Opnd from_word(u64 v) { return Opnd{ u32_to_f64((u32)v & 0xFFFFFu), u32_to_f64((u32)(v >> 20)) }; }
-    static __device__ __forceinline__ Opnd from_staged(u64 p) { return Opnd{ u32_to_f64((u32)p), u32_to_f64((u32)(p >> 32)) }; }
+    static __device__ __forceinline__ Opnd from_staged(u64 p) { return Opnd{ (double)__uint_as_float((u32)p), (double)__uint_as_float((u32)(p >> 32)) }; }
     static __device__ __forceinline__ Acc zero() { return Acc{ 0.0, 0.0, 0.0 }; }
     static __device__ __forceinline__ void mac(Acc &a, const Opnd x, const Opnd y)
     {
