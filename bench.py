@@ -350,7 +350,7 @@ def run_gpu(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": traffic, "ncu": ncu_extra,
                 "avg_launch_ms": d["ms"] / max(d["launches"], 1), "share_of_step": d["ms"] / tot_ms,
-                "note": ("dh_inner is bound by 64-bit integer multiply issue, not by HBM (ncu: fmaheavy pipe ~80 % busy, DRAM < 5 %): "
+                "note": ("dh_inner is bound by 64-bit integer multiply issue, not by HBM (ncu: fmaheavy pipe 61-84 % busy depending on the variant, DRAM ~10 %): "
                          "fusing the baby-step key inner products with the giant-step sums removed the traffic, so its HBM "
                          "fraction is small by construction; the HBM-bound family is the NTT (all_ntt_kernels)") if dom == "dh_inner" else None,
                 "all_ntt_kernels": {"achieved": ntt_bytes / (ntt_ms * 1e-3) / 1e9 if ntt_ms else 0.0,
