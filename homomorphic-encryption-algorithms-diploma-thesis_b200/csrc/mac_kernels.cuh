@@ -342,7 +342,8 @@ __global__ void __launch_bounds__(32 * BSGS_GT) bsgs_inner_kernel(const BsgsPara
 // Double-hoisted BSGS, fused: baby-step key inner products + inner sums of every giant step in one
 // pass (replaces scale_by_p + ks_inner(add_pc0) + bsgs_inner of the unfused path; same values):
 //   b_0[c]   = P * ct[c]                                              (limb L: 0)
-//   b_k[c]   = sum_j pi_k(digit_j) * key_k[j][c]  (+ P * pi_k(c0) for c = 0, limbs < L)
+//   b_k[c]   = sum_j pi_k(digit_j) * key_k[j][c]  (+ P * pi_k(c0) for c = 0, limbs < L: the word of the
+//              pre-scaled copy c0p = P * c0 (scale_c0_kernel) joins the Montgomery reduction of the sum)
 //   u_g[c]   = sum_k b_k[c] * diag[g*n1+k]                            all in the extended basis
 // A CTA owns one extended limb i and a tile of DH_TX = 32 coefficients; it stages the key words
 // (n1 x 2L), the diagonal words (n1*n2) and the gather indices of that tile in shared memory ONCE
@@ -352,9 +353,10 @@ __global__ void __launch_bounds__(32 * BSGS_GT) bsgs_inner_kernel(const BsgsPara
 // from HBM/L2 -- a Galois permutation maps an aligned 32-word tile to an aligned tile, so a gather
 // is one fully used 256-byte line -- and prefetched two baby steps ahead) and feeds it straight
 // into the 2*n2 independent 128-bit accumulators of the giant steps: no barrier and no
-// shared-memory round trip in the main loop, one Montgomery reduction per output word.  The kernel
-// is bound by integer-multiply issue (ncu: fmaheavy pipe 80 % busy), not by HBM: keys, diagonals,
-// digits and outputs cross HBM once (a few hundred MB per launch).
+// shared-memory round trip in the main loop, one Montgomery reduction per output word.  Baby step 0 is
+// peeled and whole triples of baby steps run as one straight block (the three operand sets rotate by name).
+// The kernel is bound by integer-multiply issue and dependent-issue latency (ncu: fmaheavy pipe 61-84 %
+// busy depending on the variant), not by HBM: keys, diagonals, digits and outputs cross HBM once.
 // More than 4 giant steps run as several launches of at most 4 (registers hold the accumulators; b_k is
 // rebuilt per launch).  grid = ((N / 32) * (L+1), 1, batch chunks), block = 32 * DH_KG.
 // ---------------------------------------------------------------------------------------
