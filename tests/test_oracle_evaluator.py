@@ -244,3 +244,23 @@ def test_matvec_double_hoisted_vs_bigint(bits, L, n1, n2, g_first):
     want = ref.matvec_dh_ref(ct.tolist(), n1, n2, ptsx.tolist(), [None if k is None else k.tolist() for k in bk],
                              [k.tolist() for k in gkeys], moduli, psis, L, rescale=rescale, g_first=g_first)
     assert got.tolist() == want
+
+
+def test_mod_down_commutes_with_galois():
+    """The mod-down by the (odd) special prime commutes with a Galois map bit for bit: the map acts limb-wise, also
+    on the limb mod P, and the centred remainder is symmetric.  The double-hoisted matvec relies on it twice:
+    component 0 of a rotated giant step is permuted in the extended basis, and the rotation of component 1 may be
+    applied before or after its mod-down."""
+    import random
+
+    n, L = 64, 2
+    R = ref
+    mods = R.coeff_modulus_create(n, [30, 30, 31])
+    psis = [R.minimal_primitive_root(q, n) for q in mods]
+    rnd = random.Random(3)
+    for step in (1, 3, -2):
+        tab = R.galois_table_ntt(n, R.galois_elt_from_step(n, step))
+        acc = [[rnd.randrange(m) for _ in range(n)] for m in mods[:L] + [mods[-1]]]
+        down_then_rot = [[row[tab[x]] for x in range(n)] for row in R._mod_down_one_ref([list(r) for r in acc], mods, psis, L)]
+        rot_then_down = R._mod_down_one_ref([[row[tab[x]] for x in range(n)] for row in acc], mods, psis, L)
+        assert down_then_rot == rot_then_down
