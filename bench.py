@@ -175,7 +175,7 @@ def run_reference(args):
     pts = np.empty((c["dim"], len(pmods), c["N"]), dtype=np.uint64)
     for i, q in enumerate(pmods):
         pts[:, i, :] = rng.integers(0, q, size=(c["dim"], c["N"]), dtype=np.uint64)
-    per_step = threads  # one ciphertext per host thread per step (bounded sample of the 64-batch)
+    per_step = threads  # one ciphertext per host thread per step (bounded sample of the batch)
     cts = np.empty((per_step, 2, c["L"], c["N"]), dtype=np.uint64)
     for i, q in enumerate(mods):
         cts[:, :, i, :] = rng.integers(0, q, size=(per_step, 2, c["N"]), dtype=np.uint64)
@@ -186,7 +186,7 @@ def run_reference(args):
         o.matvec_bsgs(cts, c["n1"], c["n2"], pts, bk, gkeys, threads=threads, fast=not dh, dh=dh)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
-    sample = f"{per_step} ciphertexts per step (1 per host thread) of the 64-ciphertext batch, same BSGS {c['n1']}x{c['n2']} matvec ({c['mode']})"
+    sample = f"{per_step} ciphertexts per step (1 per host thread) of the {c['batch']}-ciphertext batch, same BSGS {c['n1']}x{c['n2']} matvec ({c['mode']})"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "matvecs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
