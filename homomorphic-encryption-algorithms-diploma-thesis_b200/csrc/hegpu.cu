@@ -119,9 +119,15 @@ void select_slot(hegpu_ctx *c, int slot)
     c->park_words = c->park_words_slots[slot];
     c->stream = slot ? c->aux_stream[slot] : c->main_stream;
 }
-struct SlotGuard {  // composites return to slot 0 on every exit path
-    hegpu_ctx *c;
-    ~SlotGuard() { select_slot(c, 0); }
+struct SlotGuard {  // composites return to slot 0 on every exit path, and the main stream waits for every
+    hegpu_ctx *c;   // auxiliary stream that was forked off it (also on an early error return)
+    int forked = 0;
+    ~SlotGuard()
+    {
+        select_slot(c, 0);
+        for (int sl = 1; sl < forked; ++sl)
+            if (cudaEventRecord(c->ev_join[sl], c->aux_stream[sl]) == cudaSuccess) cudaStreamWaitEvent(c->main_stream, c->ev_join[sl], 0);
+    }
 };
 
 int stage_reserve(hegpu_ctx *c, size_t words)
@@ -133,6 +139,15 @@ int stage_reserve(hegpu_ctx *c, size_t words)
     c->stage_words = 0;
     CU(cudaMalloc(&c->stage, words * sizeof(u64)));
     c->stage_words = words;
+    return HEGPU_OK;
+}
+
+int configure_smem(hegpu_ctx *c, const void *kernel, size_t bytes)
+{
+    auto it = c->smem_configured.find(kernel);
+    if (it != c->smem_configured.end() && it->second >= bytes) return HEGPU_OK;
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    c->smem_configured[kernel] = bytes;
     return HEGPU_OK;
 }
 
@@ -149,6 +164,11 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     if (!out || !moduli) INVALID("null argument");
     if (n != 4096 && n != 8192 && n != 16384 && n != 32768) INVALID("poly_modulus_degree must be 4096, 8192, 16384 or 32768");
     if (K < 1 || K > 62) INVALID("coeff_modulus size out of range");
+    {   // the key inner product sums K-1 products below q^2 lazily and reduces once: needs (K-1) * q < 2^64
+        u64 mx = 0;
+        for (u32 i = 0; i < K; ++i) mx = std::max<u64>(mx, moduli[i]);
+        if (K > 1 && mx > (~0ull) / (K - 1)) INVALID("coeff_modulus too large: (size - 1) * max prime must stay below 2^64");
+    }
     int ndev = 0;
     cudaError_t de = cudaGetDeviceCount(&ndev);
     if (de != cudaSuccess || ndev == 0)
@@ -298,6 +318,11 @@ extern "C" int hegpu_ctx_destroy(hegpu_ctx *c)
     cudaFree(c->relin_key);
     for (auto &kv : c->galois_keys) cudaFree(kv.second);
     for (auto &kv : c->perms) cudaFree(kv.second);
+    for (auto &kv : c->tmp_cache) {
+        hegpu_ct *t = kv.second;
+        kv.second = nullptr;
+        hegpu_ct_destroy(t);
+    }
     cudaFree(c->arena.base);
     cudaFree(c->stage);
     select_slot(c, 0);
@@ -521,6 +546,7 @@ extern "C" int hegpu_ct_upload_async(hegpu_ct *t, const uint64_t *host, uint32_t
 {
     if (!t || !host) INVALID("null argument");
     if (size < 2 || size > t->size_cap || L == 0 || L > t->L_cap) INVALID("ciphertext does not fit the batch capacity");
+    if (size != t->size_cap || L != t->L_cap) INVALID("asynchronous copies need size == size_cap and L == L_cap");
     t->size = size;
     t->L = L;
     t->scale = scale;
@@ -677,6 +703,8 @@ extern "C" int hegpu_ct_copy_one(hegpu_ctx *c, hegpu_ct *dst, uint32_t di, const
     if (src->size > dst->size_cap || src->L > dst->L_cap) INVALID("destination capacity too small");
     if (dst->L && (dst->L != src->L || dst->size != src->size)) INVALID("metadata mismatch");
     TRY(set_device(c));
+    TRY(await_copy(src));
+    TRY(await_copy(dst));
     TRY(launch_ew<EW_COPY>(c, dst->view_at(di), src->view_at(si), src->view_at(si), 1, src->size, src->L));
     dst->size = src->size;
     dst->L = src->L;
@@ -1029,6 +1057,7 @@ extern "C" int hegpu_mod_switch_to_next(hegpu_ctx *c, hegpu_ct *out, const hegpu
     if (!c || !out) INVALID("null argument");
     TRY(check_ct(a));
     if (a->L < 2) INVALID("end of modulus switching chain reached");
+    if (!scale_in_bounds(c, a->scale, a->L - 1)) INVALID("scale out of bounds");  // SEAL mod_switch_drop_to_next
     TRY(set_device(c));
     TRY(fits(out, a->batch, a->size, a->L - 1));
     if (out != a) TRY(launch_ew<EW_COPY>(c, out->view(), a->view(), a->view(), a->batch, a->size, a->L - 1));
@@ -1387,11 +1416,7 @@ static int launch_dh_inner(hegpu_ctx *c, const DhInnerParams &P)
     const size_t smem = dh_inner_smem(P.n1, N2, LT);
     auto kern = dh_inner_kernel<LT, N2>;
     DhInnerParams Q = P;
-    static size_t configured[16] = {};
-    if (configured[c->device] < smem) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[c->device] = smem;
-    }
+    TRY(configure_smem(c, (const void *)kern, smem));
     dim3 grid(P.n / DH_TX * (LT + 1), 1, (P.B + DH_BCH - 1) / DH_BCH);
     for (u32 g0 = 0; g0 < P.n2; g0 += N2) {
         Q.g0 = g0;
@@ -1438,6 +1463,7 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
         select_slot(c, 0);
         CU(cudaEventRecord(c->ev_fork, c->main_stream));
         for (int sl = 1; sl < NS; ++sl) CU(cudaStreamWaitEvent(c->aux_stream[sl], c->ev_fork, 0));
+        guard.forked = NS;
     }
     u32 chunk_no = 0;
     for (u32 b0 = 0; b0 < B; b0 += Bc, ++chunk_no) {
@@ -1634,11 +1660,7 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
             }
         }
     }
-    for (int sl = 1; sl < NS; ++sl) {
-        CU(cudaEventRecord(c->ev_join[sl], c->aux_stream[sl]));
-        CU(cudaStreamWaitEvent(c->main_stream, c->ev_join[sl], 0));
-    }
-    return HEGPU_OK;
+    return HEGPU_OK;  // SlotGuard joins the auxiliary streams
 }
 
 extern "C" int hegpu_matvec_bsgs(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, uint32_t n1,
@@ -1688,7 +1710,7 @@ extern "C" int hegpu_matvec_bsgs_range(hegpu_ctx *c, hegpu_ct *out, const hegpu_
     const size_t n = c->n, ctw = (size_t)2 * L * n;
     // chunk the batch so that the scratch stays within the budget
     auto need = [&](u32 Bc) {
-        const u32 gmax = std::min<u32>(MAXG, std::max(n1 - 1, n2 - 1));
+        const u32 gmax = std::min<u32>(MAXG, std::max(n1 - 1, nrot));  // nrot = n2 when g_first > 0
         return ks_scratch(c, (size_t)gmax * Bc, L) + align256((size_t)(n1 - 1) * Bc * ctw) + align256((size_t)n2 * Bc * ctw) +
                align256((size_t)std::max<u32>(nrot, 1) * Bc * ctw) + align256((size_t)Bc * ctw) + rescale_scratch(c, Bc, 2) +
                align256((size_t)Bc * 2 * (L + 1) * n) + align256((size_t)Bc * 2 * n) + align256((size_t)Bc * ctw);
@@ -1834,9 +1856,24 @@ extern "C" int hegpu_matvec_bsgs_range(hegpu_ctx *c, hegpu_ct *out, const hegpu_
 
 // temporaries for the loop-order-exact composites
 struct TmpCt {
-    hegpu_ct *t = nullptr;
-    ~TmpCt() { hegpu_ct_destroy(t); }
+    hegpu_ct *t = nullptr;  // owned by the context's cache
 };
+// Temporary batch `slot` of a composite: cached in the context by (slot, batch, size_cap), grown when a deeper level
+// is asked for.  Reuse across calls is ordered by the context stream, so the composites never block the host.
+static int tmp_ct(hegpu_ctx *c, int slot, hegpu_ct **out, u32 batch, u32 size_cap, u32 L_cap)
+{
+    hegpu_ct *&t = c->tmp_cache[std::make_tuple(slot, batch, size_cap)];
+    if (t && t->L_cap < L_cap) {
+        hegpu_ct_destroy(t);
+        t = nullptr;
+    }
+    if (!t) TRY(hegpu_ct_create(c, &t, batch, size_cap, L_cap));
+    t->size = 0;
+    t->L = 0;
+    t->scale = 1.0;
+    *out = t;
+    return HEGPU_OK;
+}
 
 extern "C" int hegpu_bmatmul(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *ths, const hegpu_ct *oth, uint32_t n, uint32_t p,
                              int case_b)
@@ -1853,12 +1890,12 @@ extern "C" int hegpu_bmatmul(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *ths, c
     TRY(set_device(c));
     const u32 L = ths->L;
     TmpCt acc, rot, prod, one;
-    TRY(hegpu_ct_create(c, &acc.t, p, 3, L));
+    TRY(tmp_ct(c, 0, &acc.t, p, 3, L));
     if (!case_b) {
         // case A: res_i = sum_j rot(other_i, j) * this_j; batch over i, `this_j` broadcast
-        TRY(hegpu_ct_create(c, &rot.t, p, 2, L));
-        TRY(hegpu_ct_create(c, &prod.t, p, 3, L));
-        TRY(hegpu_ct_create(c, &one.t, 1, 2, L));
+        TRY(tmp_ct(c, 1, &rot.t, p, 2, L));
+        TRY(tmp_ct(c, 2, &prod.t, p, 3, L));
+        TRY(tmp_ct(c, 3, &one.t, 1, 2, L));
         for (u32 j = 0; j < n; ++j) {
             TRY(hegpu_rotate_vector(c, rot.t, oth, (int)j));
             TRY(hegpu_ct_copy_one(c, one.t, 0, ths, j));
@@ -1872,8 +1909,8 @@ extern "C" int hegpu_bmatmul(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *ths, c
         }
     } else {
         // case B: res_i = sum_j rot(other_j, i) * this_j; batch over j, summed over the batch
-        TRY(hegpu_ct_create(c, &rot.t, n, 2, L));
-        TRY(hegpu_ct_create(c, &prod.t, n, 3, L));
+        TRY(tmp_ct(c, 1, &rot.t, n, 2, L));
+        TRY(tmp_ct(c, 2, &prod.t, n, 3, L));
         for (u32 i = 0; i < p; ++i) {
             TRY(hegpu_rotate_vector(c, rot.t, oth, (int)i));
             TRY(hegpu_multiply(c, prod.t, rot.t, ths));
@@ -1950,7 +1987,7 @@ extern "C" int hegpu_matmul_elemwise(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct
     if (!scale_in_bounds(c, ns, a->L)) INVALID("scale out of bounds");
     TRY(set_device(c));
     TmpCt acc;
-    TRY(hegpu_ct_create(c, &acc.t, rows * cols, 3, a->L));
+    TRY(tmp_ct(c, 0, &acc.t, rows * cols, 3, a->L));
     const size_t total = (size_t)rows * cols * a->L * c->n;
     Prof pf(c, PK_TENSOR, total, total * 8 * (4 * inner + 3));
     matmul_tensor_kernel<<<ew_grid(c, total), 256, 0, c->stream>>>(acc.t->view(), a->view(), b->view(), rows, inner, cols, at, bt,
@@ -1972,15 +2009,15 @@ extern "C" int hegpu_bfft_stage(hegpu_ctx *c, hegpu_ct *y, const hegpu_pt *pts, 
     TRY(check_ct(y));
     if (pts->count < (with_d2 ? 3u : 2u)) INVALID("stage needs the D0, D1 (and D2) plaintexts");
     TmpCt y0, y1, y2;
-    TRY(hegpu_ct_create(c, &y0.t, y->batch, 2, y->L));
-    TRY(hegpu_ct_create(c, &y1.t, y->batch, 2, y->L));
+    TRY(tmp_ct(c, 4, &y0.t, y->batch, 2, y->L));
+    TRY(tmp_ct(c, 5, &y1.t, y->batch, 2, y->L));
     TRY(hegpu_multiply_plain(c, y0.t, y, pts, 0));
     TRY(hegpu_rescale_to_next(c, y0.t, y0.t));
     TRY(hegpu_rotate_vector(c, y1.t, y, steps));
     TRY(hegpu_multiply_plain(c, y1.t, y1.t, pts, 1));
     TRY(hegpu_rescale_to_next(c, y1.t, y1.t));
     if (with_d2) {
-        TRY(hegpu_ct_create(c, &y2.t, y->batch, 2, y->L));
+        TRY(tmp_ct(c, 6, &y2.t, y->batch, 2, y->L));
         TRY(hegpu_rotate_vector(c, y2.t, y, -steps));
         TRY(hegpu_multiply_plain(c, y2.t, y2.t, pts, 2));
         TRY(hegpu_rescale_to_next(c, y2.t, y2.t));
@@ -2000,8 +2037,8 @@ extern "C" int hegpu_fft_butterflies(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct
     if (odd->batch != half || out->batch != 2 * half || w->count != half) INVALID("batch sizes do not match");
     if (out == even || out == odd) INVALID("output must not alias an input");
     TmpCt t, e;
-    TRY(hegpu_ct_create(c, &t.t, half, 2, odd->L));
-    TRY(hegpu_ct_create(c, &e.t, half, 2, even->L));
+    TRY(tmp_ct(c, 7, &t.t, half, 2, odd->L));
+    TRY(tmp_ct(c, 8, &e.t, half, 2, even->L));
     TRY(hegpu_multiply_plain(c, t.t, odd, w, -1));
     TRY(hegpu_rescale_to_next(c, t.t, t.t));
     TRY(hegpu_multiply_plain(c, e.t, even, one, 0));

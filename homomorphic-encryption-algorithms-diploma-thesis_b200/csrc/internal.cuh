@@ -12,6 +12,7 @@
 #include <limits>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "kernels.cuh"
@@ -103,7 +104,14 @@ struct hegpu_ctx {
     int dh_fused = 1;  // double-hoisted matvec: fused baby-step + inner-sum kernel (HEGPU_DH_FUSED=0: unfused kernels)
     int loge = 3;  // NTT register-set size at N = 16384: 3 = radix-8 passes, 256 threads x 80 registers, 3 CTAs per SM (HEGPU_LOGE=4: radix-16, 2 CTAs)
     size_t ws_budget = (size_t)24 << 30;  // scratch budget per composite chunk
+    // kernels whose dynamic shared-memory limit this context has raised (kernel address -> bytes); per context, so
+    // that contexts driven from different host threads never share mutable state
+    std::map<const void *, size_t> smem_configured;
+    // temporaries of the loop-order-exact composites, cached by (slot, batch, size_cap) and grown on demand: the
+    // composites stay asynchronous on the context stream (no cudaMalloc / cudaFree / synchronize per call)
+    std::map<std::tuple<int, u32, u32>, struct hegpu_ct *> tmp_cache;
 };
+int configure_smem(hegpu_ctx *c, const void *kernel, size_t bytes);  // raise a kernel's dynamic smem limit once
 
 struct hegpu_ct {
     hegpu_ctx *ctx;
@@ -176,6 +184,10 @@ struct ArenaPlan {  // first pass sizes the scratch, second pass hands out point
     u64 *take(size_t words)
     {
         size_t bytes = (words * sizeof(u64) + 255) & ~(size_t)255;
+        if (off + bytes > c->arena.cap) {  // a sizing bug: fail loudly instead of writing past the arena
+            fprintf(stderr, "hegpu: scratch arena overrun (%zu + %zu > %zu bytes)\n", off, bytes, c->arena.cap);
+            abort();
+        }
         u64 *p = (u64 *)(c->arena.base + off);
         off += bytes;
         return p;

@@ -9,11 +9,7 @@ int launch_fwd_shape(hegpu_ctx *c, const Job &job, u32 jobs, int kind, u64 words
 {
     Prof pf(c, kind, jobs, (u64)jobs * words_per_job * 8 * c->n);
     auto kern = ntt_fwd_kernel<LOGL, SPLIT, LOGE, Job>;
-    static bool configured[16] = {};
-    if (!configured[c->device]) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL, LOGE>::SMEM));
-        configured[c->device] = true;
-    }
+    TRY(configure_smem(c, (const void *)kern, NttShape<LOGL, LOGE>::SMEM));
     kern<<<jobs << SPLIT, NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::SMEM, c->stream>>>(job, c->tabs);
     c->launches++;
     CU(cudaGetLastError());
@@ -25,11 +21,7 @@ int launch_fwd_park(hegpu_ctx *c, const Job &job, u32 jobs, int kind, u64 words_
     TRY(park_reserve(c, (size_t)jobs << LOGL));
     Prof pf(c, kind, jobs, (u64)jobs * words_per_job * 8 * c->n);
     auto kern = ntt_fwd_park_kernel<LOGL, LOGE, Job>;
-    static bool configured[16] = {};
-    if (!configured[c->device]) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL, LOGE>::SMEM));
-        configured[c->device] = true;
-    }
+    TRY(configure_smem(c, (const void *)kern, NttShape<LOGL, LOGE>::SMEM));
     kern<<<jobs, NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::SMEM, c->stream>>>(job, c->tabs, c->park);
     c->launches++;
     CU(cudaGetLastError());
@@ -41,11 +33,7 @@ int launch_inv_park(hegpu_ctx *c, const Job &job, u32 jobs, int kind)
     TRY(park_reserve(c, (size_t)jobs << LOGL));
     Prof pf(c, kind, jobs, (u64)jobs * 16 * c->n);
     auto kern = ntt_inv_park_kernel<LOGL, LOGE, Job>;
-    static bool configured[16] = {};
-    if (!configured[c->device]) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL, LOGE>::SMEM));
-        configured[c->device] = true;
-    }
+    TRY(configure_smem(c, (const void *)kern, NttShape<LOGL, LOGE>::SMEM));
     kern<<<jobs, NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::SMEM, c->stream>>>(job, c->tabs, c->park);
     c->launches++;
     CU(cudaGetLastError());
@@ -77,11 +65,7 @@ int launch_inv_shape(hegpu_ctx *c, const Job &job, u32 jobs, u64 *scratch, int k
 {
     Prof pf(c, kind, jobs, (u64)jobs * 16 * c->n);
     auto kern = ntt_inv_kernel<LOGL, SPLIT, LOGE, Job>;
-    static bool configured[16] = {};
-    if (!configured[c->device]) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttShape<LOGL, LOGE>::SMEM));
-        configured[c->device] = true;
-    }
+    TRY(configure_smem(c, (const void *)kern, NttShape<LOGL, LOGE>::SMEM));
     kern<<<jobs << SPLIT, NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::SMEM, c->stream>>>(job, c->tabs, scratch);
     c->launches++;
     CU(cudaGetLastError());

@@ -157,6 +157,16 @@ int main(int argc, char **argv)
                 E *= eval % rk % B;  // element-wise
                 for (auto &e : E.get_elems()) out.push_back(e);
             }
+        } else if (cmd == "matpow") {  // args: d powr   (Matrix::matmul_pow, he_linalg.cpp:316-349)
+            const std::size_t d = (std::size_t)arg(4);
+            std::vector<Ciphertext> ea(cts.begin(), cts.begin() + (std::ptrdiff_t)(d * d));
+            Matrix A(d, d, std::move(ea));
+            try {
+                Matrix R = A.matmul_pow(eval, rk, arg(5));
+                for (auto &e : R.get_elems()) out.push_back(e);
+            } catch (const std::invalid_argument &e) {  // SEAL's own error when the power mixes levels (e.g. 3 = A * A^2)
+                std::printf("matpow_error=%s\n", e.what());
+            }
         } else if (cmd == "sum_elems") {  // args: dim
             BatchedVector v((std::size_t)arg(4), cts[0]);
             v.sum_elems_inplace(eval, gk);

@@ -120,6 +120,80 @@ def galois_coeff(a: list[int], elt: int, q: int) -> list[int]:
     return out
 
 
+# ---------------------------------------------------------------- big-int NTT in O(N log N)
+def _dft(b: list[int], w: int, q: int) -> list[int]:
+    """Cyclic DFT over Z_q, natural order in and out: recursive radix-2 decimation in time (textbook form,
+    nothing shared with the oracle's in-place Harvey butterflies)."""
+    n = len(b)
+    if n == 1:
+        return b
+    w2 = w * w % q
+    ev, od = _dft(b[0::2], w2, q), _dft(b[1::2], w2, q)
+    out = [0] * n
+    t, h = 1, n // 2
+    for j in range(h):
+        x = t * od[j] % q
+        out[j] = (ev[j] + x) % q
+        out[j + h] = (ev[j] - x) % q
+        t = t * w % q
+    return out
+
+
+def ntt_fast(a: list[int], q: int, psi: int) -> list[int]:
+    """Same function as ntt_naive (a^[k] = a(psi^(2 brev(k)+1))): twist by psi^i, cyclic DFT with omega = psi^2,
+    bit-reversed read-out.  Checked against ntt_naive in tests/test_oracle_evaluator.py."""
+    n = len(a)
+    logn = n.bit_length() - 1
+    tw, p = [], 1
+    for c in a:
+        tw.append(c * p % q)
+        p = p * psi % q
+    big = _dft(tw, psi * psi % q, q)
+    return [big[brev(k, logn)] for k in range(n)]
+
+
+def intt_fast(ah: list[int], q: int, psi: int) -> list[int]:
+    n = len(ah)
+    logn = n.bit_length() - 1
+    nat = [0] * n
+    for k in range(n):
+        nat[brev(k, logn)] = ah[k]
+    ipsi = pow(psi, q - 2, q)
+    b = _dft(nat, ipsi * ipsi % q, q)
+    ninv = pow(n, q - 2, q)
+    out, p = [], ninv
+    for c in b:
+        out.append(c * p % q)
+        p = p * ipsi % q
+    return out
+
+
+# the spec restatements below call the transforms through these two names: O(N^2) direct evaluation by default,
+# the O(N log N) form inside `with fast_transforms():` (full-size cross-checks)
+_NTT, _INTT = ntt_naive, intt_naive
+
+
+class fast_transforms:
+    def __enter__(self):
+        global _NTT, _INTT
+        _NTT, _INTT = ntt_fast, intt_fast
+
+    def __exit__(self, *exc):
+        global _NTT, _INTT
+        _NTT, _INTT = ntt_naive, intt_naive
+        return False
+
+
+def apply_galois_ref(ct, elt, key, moduli, psis, L):
+    """SURVEY 9.4 apply_galois_inplace on a size-2 ciphertext [2][L][N]: c0 <- pi(c0); switch_key(pi(c1))."""
+    n = len(ct[0][0])
+    tab = galois_table_ntt(n, elt)
+    c0 = [[ct[0][i][tab[x]] for x in range(n)] for i in range(L)]
+    t = [[ct[1][i][tab[x]] for x in range(n)] for i in range(L)]
+    zero = [[0] * n for _ in range(L)]
+    return switch_key_ref([c0, zero], t, key, moduli, psis, L)
+
+
 # ---------------------------------------------------------------- spec 9.6 / 9.7 in big ints
 def switch_key_ref(ct, target, key, moduli, psis, L):
     """SURVEY 9.6. ct [2][L][N], target [L][N], key [Lmax][2][K][N] as nested int lists."""
@@ -127,7 +201,7 @@ def switch_key_ref(ct, target, key, moduli, psis, L):
     P = moduli[K - 1]
     half = P // 2
     n = len(target[0])
-    coef = [intt_naive(target[j], moduli[j], psis[j]) for j in range(L)]
+    coef = [_INTT(target[j], moduli[j], psis[j]) for j in range(L)]
     acc = [[None] * (L + 1) for _ in range(2)]
     for I in range(L + 1):
         ki = K - 1 if I == L else I
@@ -137,16 +211,16 @@ def switch_key_ref(ct, target, key, moduli, psis, L):
             if I == J:
                 ops.append(target[J])
             else:
-                ops.append(ntt_naive([x % m for x in coef[J]], m, psis[ki]))
+                ops.append(_NTT([x % m for x in coef[J]], m, psis[ki]))
         for c in range(2):
             acc[c][I] = [sum(ops[J][x] * key[J][c][ki][x] for J in range(L)) % m for x in range(n)]
     out = [[None] * L for _ in range(2)]
     for c in range(2):
-        t = intt_naive(acc[c][L], P, psis[K - 1])
+        t = _INTT(acc[c][L], P, psis[K - 1])
         t = [(x + half) % P for x in t]
         for i in range(L):
             q = moduli[i]
-            d = ntt_naive([(x % q - half % q) % q for x in t], q, psis[i])
+            d = _NTT([(x % q - half % q) % q for x in t], q, psis[i])
             pinv = pow(P % q, q - 2, q)
             out[c][i] = [(ct[c][i][x] + (acc[c][i][x] - d[x]) * pinv) % q for x in range(n)]
     return out
@@ -158,12 +232,12 @@ def rescale_ref(ct, moduli, psis, L):
     half = ql // 2
     out = []
     for poly in ct:
-        t = intt_naive(poly[L - 1], ql, psis[L - 1])
+        t = _INTT(poly[L - 1], ql, psis[L - 1])
         t = [(x + half) % ql for x in t]
         res = []
         for i in range(L - 1):
             q = moduli[i]
-            d = ntt_naive([(x % q - half % q) % q for x in t], q, psis[i])
+            d = _NTT([(x % q - half % q) % q for x in t], q, psis[i])
             inv = pow(ql % q, q - 2, q)
             res.append([(poly[i][x] - d[x]) * inv % q for x in range(len(t))])
         out.append(res)
@@ -190,10 +264,10 @@ def _decompose_ref(target, moduli, psis, L):
     K = len(moduli)
     ext = [[None] * (L + 1) for _ in range(L)]
     for J in range(L):
-        coef = intt_naive(target[J], moduli[J], psis[J])
+        coef = _INTT(target[J], moduli[J], psis[J])
         for I in range(L + 1):
             ki = K - 1 if I == L else I
-            ext[J][I] = list(target[J]) if I == J else ntt_naive([x % moduli[ki] for x in coef], moduli[ki], psis[ki])
+            ext[J][I] = list(target[J]) if I == J else _NTT([x % moduli[ki] for x in coef], moduli[ki], psis[ki])
     return ext
 
 
@@ -215,10 +289,10 @@ def _mod_down_ref(acc, moduli, psis, L):
     half = P // 2
     out = [[None] * L for _ in range(2)]
     for c in range(2):
-        t = [(x + half) % P for x in intt_naive(acc[c][L], P, psis[K - 1])]
+        t = [(x + half) % P for x in _INTT(acc[c][L], P, psis[K - 1])]
         for i in range(L):
             q = moduli[i]
-            d = ntt_naive([(x % q - half % q) % q for x in t], q, psis[i])
+            d = _NTT([(x % q - half % q) % q for x in t], q, psis[i])
             pinv = pow(P % q, q - 2, q)
             out[c][i] = [(acc[c][i][x] - d[x]) * pinv % q for x in range(len(t))]
     return out
@@ -229,11 +303,11 @@ def _mod_down_one_ref(acc1, moduli, psis, L):
     K = len(moduli)
     P = moduli[K - 1]
     half = P // 2
-    t = [(x + half) % P for x in intt_naive(acc1[L], P, psis[K - 1])]
+    t = [(x + half) % P for x in _INTT(acc1[L], P, psis[K - 1])]
     out = []
     for i in range(L):
         q = moduli[i]
-        d = ntt_naive([(x % q - half % q) % q for x in t], q, psis[i])
+        d = _NTT([(x % q - half % q) % q for x in t], q, psis[i])
         pinv = pow(P % q, q - 2, q)
         out.append([(acc1[i][x] - d[x]) * pinv % q for x in range(len(t))])
     return out

@@ -74,11 +74,25 @@ def outputs(n, bits):
             res[f"matvec_2x2_hoist{hoist}_lazy{lazy}"] = digest(o.matvec_bsgs(cts, 2, 2, pts, bk, gkeys, hoist=bool(hoist), lazy=bool(lazy)))
     # double-hoisted mode: plaintexts with a limb mod the special prime (pseudo-random residues over all K limbs)
     res["matvec_2x2_dh"] = digest(o.matvec_bsgs(cts, 2, 2, dh_plaintexts(o, s, L, n), bk, gkeys, dh=True))
+    # 2 baby x 3 giant steps WITHOUT the final rescale: LAZY (one mod-down for the sum of the two rotated giant
+    # steps) differs from the step-by-step form by the rounding of a mod-down, +-1 per coefficient, which the
+    # rescale of the 2x2 cases above absorbs (lazy0 == lazy1 there); before the rescale it is visible
+    pts3, gkeys3 = matvec_2x3_inputs(o, s, L, n, gk)
+    for hoist in (0, 1):
+        for lazy in (0, 1):
+            res[f"matvec_2x3_hoist{hoist}_lazy{lazy}"] = digest(o.matvec_bsgs(cts, 2, 3, pts3, bk, gkeys3, hoist=bool(hoist), lazy=bool(lazy), rescale=False))
+    res["matvec_2x3_dh"] = digest(o.matvec_bsgs(cts, 2, 3, dh_plaintexts(o, s, L, n, 6), bk, gkeys3, dh=True, rescale=False))
     return res
 
 
-def dh_plaintexts(o, s, L, n):
-    return np.stack([o.encrypt_symmetric(50 + i, s, np.zeros((L + 1, n), dtype=np.uint64))[0] for i in range(4)])
+def matvec_2x3_inputs(o, s, L, n, gk):
+    pts3 = np.stack([o.encrypt_symmetric(60 + i, s, np.zeros((L, n), dtype=np.uint64))[0] for i in range(6)])
+    gkeys3 = [None, gk[orc.galois_elt_from_step(n, 2)], gk[orc.galois_elt_from_step(n, 4)]]
+    return pts3, gkeys3
+
+
+def dh_plaintexts(o, s, L, n, count=4):
+    return np.stack([o.encrypt_symmetric(50 + i, s, np.zeros((L + 1, n), dtype=np.uint64))[0] for i in range(count)])
 
 
 def small_vectors():
@@ -99,7 +113,7 @@ def small_vectors():
 
 
 def main():
-    gold = {"format": 1, "generator": "tests/golden/make_golden.py",
+    gold = {"format": 2, "generator": "tests/golden/make_golden.py",
             "cases": {"n4096_36_36_37": outputs(4096, [36, 36, 37]), "n8192_60_40_40_60": outputs(8192, [60, 40, 40, 60])}}
     with open(os.path.join(HERE, "golden_v1.json"), "w") as f:
         json.dump(gold, f, indent=1, sort_keys=True)

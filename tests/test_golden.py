@@ -31,6 +31,15 @@ def test_oracle_reproduces_golden_digests(name):
     assert make_golden.outputs(n, bits) == GOLD["cases"][name]
 
 
+def test_golden_matvec_digests_are_not_vacuous():
+    """Every mode of the 2x3 matvec (taken before the rescale) is a different ciphertext: the modes differ in where
+    they round, also the lazy flag alone (the rescaled 2x2 digests hide that +-1)."""
+    for name in CASES:
+        g = GOLD["cases"][name]
+        d = [g[f"matvec_2x3_hoist{h}_lazy{l}"] for h in (0, 1) for l in (0, 1)] + [g["matvec_2x3_dh"]]
+        assert len(set(d)) == len(d)
+
+
 def test_small_vectors_against_oracle_and_bigint():
     z = np.load(os.path.join(HERE, "golden_small.npz"))
     n, moduli = int(z["n"]), [int(q) for q in z["moduli"]]
@@ -98,3 +107,12 @@ def test_gpu_matches_golden_digests(name):
     Dx = ctx.upload_pt_ext(make_golden.dh_plaintexts(o, s, L, n), sc)
     ctx.matvec_bsgs(mv, X, Dx, 2, 2, dh=True)
     assert digest(mv.download()) == g["matvec_2x2_dh"]
+    pts3, _ = make_golden.matvec_2x3_inputs(o, s, L, n, gk)
+    D3 = ctx.upload_pt(pts3, sc)
+    for hoist in (0, 1):
+        for lazy in (0, 1):
+            ctx.matvec_bsgs(mv, X, D3, 2, 3, hoist=bool(hoist), lazy=bool(lazy), rescale=False)
+            assert digest(mv.download()) == g[f"matvec_2x3_hoist{hoist}_lazy{lazy}"]
+    Dx3 = ctx.upload_pt_ext(make_golden.dh_plaintexts(o, s, L, n, 6), sc)
+    ctx.matvec_bsgs(mv, X, Dx3, 2, 3, dh=True, rescale=False)
+    assert digest(mv.download()) == g["matvec_2x3_dh"]

@@ -245,9 +245,9 @@ def test_matvec_bsgs_bit_exact_and_decrypts(hg, n, dim, n1, n2):
     X = ctx.upload_ct(cts, scale)
     D = ctx.upload_pt(pts, scale)
     out = ctx.ct(B, 2)
-    tol = ckks_tol(dim, n, scale)
     # exact chain of SEAL primitives, and every fast mode against its own oracle restatement
     for hoist, lazy in ((False, False), (True, True), (True, False), (False, True)):
+        tol = ckks_tol(dim, n, scale, "hoisted" if hoist else "exact")
         want = S.o.matvec_bsgs(cts, n1, n2, pts, bk, gkeys, threads=4, hoist=hoist, lazy=lazy)
         ctx.matvec_bsgs(out, X, D, n1, n2, hoist=hoist, lazy=lazy)
         got = out.download()
@@ -261,6 +261,34 @@ def test_matvec_bsgs_bit_exact_and_decrypts(hg, n, dim, n1, n2):
     part = out.download()
     want = S.o.matvec_bsgs(cts, n1, n2, pts, bk, gkeys, threads=4, fast=True)
     assert np.array_equal(np.stack([S.o.rescale(part[i]) for i in range(B)]), want)
+
+
+@pytest.mark.parametrize("n1,n2,L", [(2, 2, 2), (2, 4, 3), (4, 4, 3)])
+def test_matvec_bsgs_range_all_rotated_giant_steps(hg, n1, n2, L):
+    """A diagonal shard with g_first > 0 rotates EVERY giant step of the call (nrot = n2), one more key-switch
+    group than a g_first = 0 call of the same shape: the scratch plan used to be one group short when n2 >= n1
+    (silent arena overrun).  Fresh context per case (nothing grown by an earlier call), every non-DH
+    mode against the oracle's restatement, no final rescale (multi-GPU partial sums) and with it."""
+    n, B = 8192, 3
+    S = setup(n, (60, 40, 40, 60))
+    rng = np.random.default_rng(27)
+    scale = 2.0**40
+    cts = rand_residues(rng, S.moduli[:L], (B, 2), n)
+    g0 = n2  # the second shard of a 2 * n2 giant-step matvec
+    pts = rand_residues(rng, S.moduli[:L], (n1 * n2,), n)
+    bsteps, gsteps = list(range(1, n1)), [(g0 + g) * n1 for g in range(n2)]
+    gk = S.gk(bsteps + gsteps)
+    bk = [None] + [gk[orc.galois_elt_from_step(n, s)] for s in bsteps]
+    gkeys = [gk[orc.galois_elt_from_step(n, s)] for s in gsteps]
+    for hoist, lazy, rescale in ((True, True, False), (False, False, False), (False, True, True), (True, False, True)):
+        ctx = hg.Context(n, S.moduli)  # fresh arena: the first call must size it correctly on its own
+        ctx.load_galois_keys(gk)
+        X = ctx.upload_ct(cts, scale, size_cap=2, L_cap=L)
+        D = ctx.upload_pt(pts, scale)
+        out = ctx.ct(B, 2, L)
+        want = S.o.matvec_bsgs(cts, n1, n2, pts, bk, gkeys, threads=4, hoist=hoist, lazy=lazy, rescale=rescale, g_first=g0)
+        ctx.matvec_bsgs(out, X, D, n1, n2, hoist=hoist, lazy=lazy, rescale=rescale, g_first=g0)
+        assert np.array_equal(out.download(), want), (hoist, lazy, rescale)
 
 
 def _diag_plaintexts_ext(S, M, n1, n2, scale, L):
@@ -302,7 +330,7 @@ def test_matvec_bsgs_double_hoisted(hg, n, dim, n1, n2):
     X = ctx.upload_ct(cts, scale)
     D = ctx.upload_pt_ext(ptsx, scale)
     out = ctx.ct(B, 2)
-    tol = ckks_tol(dim, n, scale)
+    tol = ckks_tol(dim, n, scale, "hoisted")
     want = S.o.matvec_bsgs(cts, n1, n2, ptsx, bk, gkeys, threads=4, dh=True)
     ctx.matvec_bsgs(out, X, D, n1, n2, dh=True)
     got = out.download()
@@ -357,7 +385,7 @@ def test_matvec_double_hoisted_levels(hg, bits, L):
     assert out.L == (L - 1 if rescale else L)
     assert np.array_equal(got, want)
     if rescale:
-        tol = ckks_tol(dim, n, scale)
+        tol = ckks_tol(dim, n, scale, "hoisted")
         for i in range(B):
             assert np.max(np.abs(S.decrypt(got[i], out.scale).real[:dim] - M @ V[i])) < tol
 
