@@ -16,7 +16,7 @@ def rand_residues(rng, moduli, prefix, n):
     return out
 
 
-def ckks_tol(n_terms, N, scale, mode="exact"):
+def ckks_tol(n_terms, N, scale, mode="exact", out_scale=None):
     """Decryption tolerance of a diagonal matvec with n_terms diagonals (DESIGN.md "Tolerance"), calibrated on
     the oracle (tools/calibrate_tolerance.py; VERDICT r1 asked for <= ~10x the measured error):
 
@@ -29,10 +29,15 @@ def ckks_tol(n_terms, N, scale, mode="exact"):
     mode "hoisted" -- HOIST, HOIST|LAZY and DH: the rotations act on the lifted digits, every key-switched term is
                       multiplied by a diagonal before it is summed, and the error behaves like independent noise:
                       2400 * sqrt(n_terms * N) / scale, 8x - 14x the measured error (1.0e-7 / 1.1e-7 / 2.3e-7 /
-                      1.1e-6 at (8192, 16) / (16384, 32) / (16384, 128) / (32768, 512))."""
+                      1.1e-6 at (8192, 16) / (16384, 32) / (16384, 128) / (32768, 512)).
+    out_scale      -- scale of the rescaled result, when it differs from `scale` (chains whose data primes are
+                      not close to the scale)."""
+    # the final rescale rounds every coefficient: ~N / (4 * out_scale) per slot (secret of Hamming weight 2N/3);
+    # only visible when the dropped prime is much larger than the scale (3.4e-6 measured at N = 8192, out_scale 2^30)
+    round_term = 4.0 * N / out_scale if out_scale else 0.0
     if mode == "hoisted":
-        return 2400.0 * (n_terms * N) ** 0.5 / scale
-    return n_terms * 3.2 * N**1.5 / (8.0 * scale)
+        return 2400.0 * (n_terms * N) ** 0.5 / scale + round_term
+    return n_terms * 3.2 * N**1.5 / (8.0 * scale) + round_term
 
 
 class Setup:

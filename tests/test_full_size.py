@@ -273,7 +273,7 @@ def test_cfg3_matrix_matmul_64x64():
         dec = S.decrypt(got, out.scale).real
         worst = max(worst, float(np.max(np.abs(dec - C[i, j] * ramp * ramp))))
     print(f"cfg3 Matrix::matmul 64x64: max |err| = {worst:.3e}")
-    assert worst < 1e-4
+    assert worst < 3e-7  # measured 3.0e-8 (values up to 16, one relinearisation per output)
 
 
 def test_shipped_bfft_n128(tmp_path):
@@ -306,7 +306,7 @@ def test_shipped_bfft_n128(tmp_path):
     brev = np.array([int(format(i, "07b")[::-1], 2) for i in range(m)])
     err = float(np.max(np.abs(dec - ref[brev])))
     print(f"shipped bfft: max |err| = {err:.3e} on outputs up to {np.max(np.abs(ref)):.1f}")
-    assert err < 2e-2 * float(np.max(np.abs(ref)))  # 30-bit scale, 7 levels, values up to 9e3
+    assert err < 5e-6 * float(np.max(np.abs(ref)))  # measured 5.0e-3 on outputs up to 9.0e3 (30-bit scale, 7 levels): 5.5e-7 relative
 
 
 def test_shipped_fft_128_ciphertexts(tmp_path):
@@ -350,7 +350,7 @@ def test_shipped_fft_128_ciphertexts(tmp_path):
         dec = S.decrypt(outs[k][0], outs[k][1])
         worst = max(worst, float(np.max(np.abs(dec - ref[k]))))
     print(f"shipped fft: max |err| = {worst:.3e} on outputs up to {np.max(np.abs(ref)):.3e}")
-    assert worst < 2e-2 * float(np.max(np.abs(ref)))
+    assert worst < 5e-10 * float(np.max(np.abs(ref)))  # measured 5.1e-4 on outputs up to 1.1e7
 
 
 def test_matmul_pow(tmp_path):

@@ -385,7 +385,7 @@ def test_matvec_double_hoisted_levels(hg, bits, L):
     assert out.L == (L - 1 if rescale else L)
     assert np.array_equal(got, want)
     if rescale:
-        tol = ckks_tol(dim, n, scale, "hoisted")
+        tol = ckks_tol(dim, n, scale, "hoisted", out_scale=out.scale)
         for i in range(B):
             assert np.max(np.abs(S.decrypt(got[i], out.scale).real[:dim] - M @ V[i])) < tol
 
