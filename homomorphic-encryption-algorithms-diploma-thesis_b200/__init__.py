@@ -121,7 +121,9 @@ def lib() -> C.CDLL:
             "hegpu_bfft_stage": [vp, vp, vp, i32, i32],
             "hegpu_fft_butterflies": [vp, vp, vp, vp, vp, vp],
             "hegpu_reduce_fixup": [vp, vp, u32],
+            "hegpu_rescale_sum_to_next": [vp, vp, vp, u32],
             "hegpu_ct_transparent": [vp, vp, C.POINTER(u32)],
+            "hegpu_pipe_peak": [vp, i32, C.POINTER(dbl)],
             "hegpu_profile_enable": [vp, i32],
             "hegpu_profile_reset": [vp],
             "hegpu_profile_read": [vp, i32, C.POINTER(dbl), u64p, u64p, u64p],
@@ -256,6 +258,12 @@ class Context:
     def ntt_inverse_device(self, dptr: int, count: int, first_mod: int, n_mods: int):
         _ck(lib().hegpu_ntt_inverse_device(self._h, C.c_void_p(dptr), count, first_mod, n_mods))
 
+    def pipe_peak(self, kind: int) -> float:
+        """Measured issue rate (thread-level ops/s) of IMAD.WIDE.U32 (0), DFMA (1) or IMAD (2) on this device."""
+        v = C.c_double()
+        _ck(lib().hegpu_pipe_peak(self._h, kind, C.byref(v)))
+        return v.value
+
     # ---- evaluator (out may alias a)
     def negate(self, out, a):
         _ck(lib().hegpu_negate(self._h, out._h, a._h))
@@ -340,6 +348,10 @@ class Context:
 
     def reduce_fixup(self, ct, terms: int):
         _ck(lib().hegpu_reduce_fixup(self._h, ct._h, terms))
+
+    def rescale_sum_to_next(self, out, a, terms: int):
+        """rescale_to_next of the uint64 sum of `terms` partial ciphertexts (the fix-up rides in the rescale's loads)."""
+        _ck(lib().hegpu_rescale_sum_to_next(self._h, out._h, a._h, terms))
 
     def transparent_count(self, ct) -> int:
         """Number of transparent ciphertexts of the batch (Ciphertext::is_transparent); blocking."""

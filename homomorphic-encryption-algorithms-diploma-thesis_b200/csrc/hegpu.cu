@@ -408,6 +408,73 @@ extern "C" int hegpu_profile_read(hegpu_ctx *c, int kind, double *ms, uint64_t *
     return HEGPU_OK;
 }
 
+// ------------------------------------------------------------------------- pipe peaks (measurement)
+// Issue-rate microbenchmarks behind the integer / FP64 rooflines that bench.py reports for the multiply-accumulate
+// kernels: 8 independent dependent-chains per thread of ONE instruction kind, enough CTAs to fill every SM.
+//   kind 0: IMAD.WIDE.U32 (32 x 32 -> 64 multiply-add, the building block of every 64-bit modular product)
+//   kind 1: DFMA
+//   kind 2: IMAD (32-bit low multiply-add)
+template <int KIND>
+__global__ void __launch_bounds__(256) pipe_peak_kernel(u64 *__restrict__ out, u32 iters, u32 seed)
+{
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 x = t * 2654435761u + seed, y = (t ^ seed) | 1u;
+    u64 a[8];
+    double d[8];
+    u32 r[8];
+    const double dx = 1.0 + (double)(x & 1023u) * 1e-9, dy = 1e-9 * (double)(y & 1023u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = (u64)t + i;
+        d[i] = (double)i;
+        r[i] = t + i;
+    }
+    for (u32 it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 4; ++rep) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (KIND == 0) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(x), "r"(y));
+                if (KIND == 1) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dx), "d"(dy));
+                if (KIND == 2) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(x), "r"(y));
+            }
+        }
+    }
+    u64 acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += a[i] + (u64)__double_as_longlong(d[i]) + r[i];
+    if (acc == 0x1234567887654321ull) out[0] = acc;  // never true in practice; keeps the chains alive
+}
+
+extern "C" int hegpu_pipe_peak(hegpu_ctx *c, int kind, double *ops_per_second)
+{
+    if (!c || !ops_per_second) INVALID("null argument");
+    if (kind < 0 || kind > 2) INVALID("pipe kind out of range");
+    TRY(set_device(c));
+    TRY(arena_reserve(c, 256));
+    const u32 iters = 2048, grid = (u32)c->sms * 8, block = 256;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float best = 0;
+    for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+        CU(cudaEventRecord(e0, c->stream));
+        if (kind == 0) pipe_peak_kernel<0><<<grid, block, 0, c->stream>>>((u64 *)c->arena.base, iters, 12345u + rep);
+        if (kind == 1) pipe_peak_kernel<1><<<grid, block, 0, c->stream>>>((u64 *)c->arena.base, iters, 12345u + rep);
+        if (kind == 2) pipe_peak_kernel<2><<<grid, block, 0, c->stream>>>((u64 *)c->arena.base, iters, 12345u + rep);
+        c->launches++;
+        CU(cudaEventRecord(e1, c->stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep && (best == 0 || ms < best)) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ops_per_second = (double)grid * block * iters * 32.0 / (best * 1e-3);
+    return HEGPU_OK;
+}
+
 // ------------------------------------------------------------------------- keys
 static size_t key_words(hegpu_ctx *c) { return (size_t)(c->K - 1) * 2 * c->K * c->n; }
 // device copies of key-switching keys are kept in Montgomery form (k * 2^64 mod m) for ks_inner
@@ -1024,14 +1091,14 @@ extern "C" int hegpu_square(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a) { re
 // ------------------------------------------------------------------------- rescale / mod switch
 // a: view of B ciphertexts with `size` polys at level L; out at level L-1 (may alias a)
 static size_t rescale_scratch(hegpu_ctx *c, u32 B, u32 size) { return align256((size_t)B * size * c->n) + align256(inv_scratch_words(c, (size_t)B * size)); }
-static int rescale_views(hegpu_ctx *c, CtView out, CtView a, u32 B, u32 size, u32 L, ArenaPlan &ap)
+static int rescale_views(hegpu_ctx *c, CtView out, CtView a, u32 B, u32 size, u32 L, ArenaPlan &ap, bool lazy_in = false)
 {
     const u32 jobs = B * size;
     u64 *t = ap.take((size_t)jobs * c->n);
     u64 *scr = ap.take(inv_scratch_words(c, jobs));
-    HalfInttJob hj{ a.p + (size_t)(L - 1) * a.sl, t, a.sb, a.sp, size, L - 1, c->n };
+    HalfInttJob hj{ a.p + (size_t)(L - 1) * a.sl, t, a.sb, a.sp, size, L - 1, c->n, lazy_in ? 1u : 0u };
     TRY(launch_ntt_inv(c, hj, jobs, scr, PK_HALF_INTT));
-    RescaleJob rj{ a, out, t, c->d_md + (size_t)(L - 1) * c->K, c->d_mods, size, L - 1, L - 1, c->n };
+    RescaleJob rj{ a, out, t, c->d_md + (size_t)(L - 1) * c->K, c->d_mods, size, L - 1, L - 1, c->n, lazy_in ? 1u : 0u };
     TRY(launch_ntt_fwd(c, rj, jobs * (L - 1), PK_RESCALE_NTT, 3));
     return HEGPU_OK;
 }
@@ -1046,6 +1113,26 @@ extern "C" int hegpu_rescale_to_next(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct
     TRY(arena_reserve(c, rescale_scratch(c, a->batch, a->size)));
     ArenaPlan ap{ c };
     TRY(rescale_views(c, out->view(), a->view(), a->batch, a->size, a->L, ap));
+    out->size = a->size;
+    out->scale = a->scale / (double)c->q[a->L - 1];
+    out->L = a->L - 1;
+    return HEGPU_OK;
+}
+
+// rescale of the element-wise uint64 SUM of up to `terms` partial ciphertexts (what an NCCL sum of the
+// diagonal shards leaves behind): the reduction to [0,q) rides in the loads of the rescale's two transforms
+extern "C" int hegpu_rescale_sum_to_next(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *a, uint32_t terms)
+{
+    if (!c || !out) INVALID("null argument");
+    TRY(check_ct(a));
+    if (terms == 0 || terms > 16) INVALID("at most 16 partial sums of 60-bit residues fit in 64 bits");
+    if (a->L < 2) INVALID("end of modulus switching chain reached");
+    if (out == a) INVALID("the rescale of a partial sum must not run in place");  // the epilogue re-reads the unreduced words
+    TRY(set_device(c));
+    TRY(fits(out, a->batch, a->size, a->L - 1));
+    TRY(arena_reserve(c, rescale_scratch(c, a->batch, a->size)));
+    ArenaPlan ap{ c };
+    TRY(rescale_views(c, out->view(), a->view(), a->batch, a->size, a->L, ap, true));
     out->size = a->size;
     out->scale = a->scale / (double)c->q[a->L - 1];
     out->L = a->L - 1;
@@ -1185,13 +1272,13 @@ static int ks_moddown(hegpu_ctx *c, KsPlan &pl)
     const KsParams &P = pl.P;
     const u32 L = P.L;
     if (P.only_c1) {  // component 1 of every element: t is [E][N]
-        HalfInttJob j4{ P.acc + (size_t)(2 * L + 1) * c->n, P.t, (size_t)2 * (L + 1) * c->n, 0, 1, c->K - 1, c->n };
+        HalfInttJob j4{ P.acc + (size_t)(2 * L + 1) * c->n, P.t, (size_t)2 * (L + 1) * c->n, 0, 1, c->K - 1, c->n, 0 };
         TRY(launch_ntt_inv(c, j4, (u32)pl.E, pl.scr, PK_HALF_INTT));
         KsModDownJob j5{ P, c->d_md + (size_t)(c->K - 1) * c->K, c->d_mods };
         TRY(launch_ntt_fwd(c, j5, (u32)(pl.E * L), PK_KS_MODDOWN_NTT, 3));
         return HEGPU_OK;
     }
-    HalfInttJob j4{ P.acc + (size_t)L * c->n, P.t, (size_t)(L + 1) * c->n, 0, 1, c->K - 1, c->n };
+    HalfInttJob j4{ P.acc + (size_t)L * c->n, P.t, (size_t)(L + 1) * c->n, 0, 1, c->K - 1, c->n, 0 };
     TRY(launch_ntt_inv(c, j4, (u32)(pl.E * 2), pl.scr, PK_HALF_INTT));
     KsModDownJob j5{ P, c->d_md + (size_t)(c->K - 1) * c->K, c->d_mods };
     TRY(launch_ntt_fwd(c, j5, (u32)(pl.E * 2 * L), PK_KS_MODDOWN_NTT, P.has_base1 ? 4 : 3));
@@ -1204,7 +1291,7 @@ static int ks_moddown_rescale(hegpu_ctx *c, KsPlan &pl, CtView out, u64 *t2)
 {
     const KsParams &P = pl.P;
     const u32 L = P.L, B = P.B;
-    HalfInttJob j4{ P.acc + (size_t)L * c->n, P.t, (size_t)(L + 1) * c->n, 0, 1, c->K - 1, c->n };
+    HalfInttJob j4{ P.acc + (size_t)L * c->n, P.t, (size_t)(L + 1) * c->n, 0, 1, c->K - 1, c->n, 0 };
     TRY(launch_ntt_inv(c, j4, B * 2, pl.scr, PK_HALF_INTT));
     FinalParams F{};
     F.acc = P.acc;

@@ -147,9 +147,10 @@ struct HalfInttJob {
     u64 *dst;        // [jobs][N]
     size_t s_outer, s_inner;
     u32 inner, drop_mod, n;
+    u32 lazy_in;  // the words are sums of up to 16 canonical residues (multi-GPU partial sums): reduce while loading
     __device__ __forceinline__ u32 mod(u32) const { return drop_mod; }
     __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const { return src[(j / inner) * s_outer + (j % inner) * s_inner + i]; }
-    __device__ __forceinline__ u64 load_fix(u32, u64 v, const ModConst &) const { return v; }
+    __device__ __forceinline__ u64 load_fix(u32, u64 v, const ModConst &m) const { return lazy_in ? barrett64(v, m) : v; }
     __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m) const
     {
         dst[(size_t)j * n + i] = addmod(x, m.q >> 1, m.q);
@@ -215,6 +216,7 @@ struct RescaleJob {
     const MdConst *md;  // constants of dropped modulus q_{L-1} per target limb
     const ModConst *mods;
     u32 size, Lm1, drop_mod, n;  // Lm1 = L-1 target limbs
+    u32 lazy_in;                 // `a` holds sums of up to 16 canonical residues: reduced in the epilogue's operand fetch
     __device__ __forceinline__ u32 mod(u32 j) const { return j % Lm1; }
     __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const { return t[(size_t)(j / Lm1) * n + i]; }
     __device__ __forceinline__ u64 load_fix(u32 j, u64 v, const ModConst &m) const
@@ -227,7 +229,8 @@ struct RescaleJob {
     __device__ __forceinline__ Ops fetch(u32 j, u32 i, const ModConst &) const
     {
         const u32 l = j % Lm1, bp = j / Lm1, p = bp % size, b = bp / size;
-        return Ops{ a.p[b * a.sb + p * a.sp + l * a.sl + i] };
+        const u64 v = a.p[b * a.sb + p * a.sp + l * a.sl + i];
+        return Ops{ lazy_in ? barrett64(v, mods[l]) : v };
     }
     __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m, const Ops &o) const
     {

@@ -72,8 +72,9 @@ def as_torch_i64(ct):
     return torch.as_tensor(_CudaArray(ptr, ct.batch * sb), device=f"cuda:{ct.ctx.device}")
 
 
-def allreduce_sum(ct, world: int, group=None):
-    """In-place sum of a partial ciphertext batch over all ranks, canonical residues on return."""
+def allreduce_sum(ct, world: int, group=None, fixup: bool = True):
+    """In-place sum of a partial ciphertext batch over all ranks; canonical residues on return, or -- fixup=False --
+    the raw uint64 sums (< world * q), to be consumed by Context.rescale_sum_to_next, which reduces while it loads."""
     import torch
     import torch.distributed as dist
 
@@ -83,13 +84,15 @@ def allreduce_sum(ct, world: int, group=None):
     t = as_torch_i64(ct)
     with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream, device=ctx.device)):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)  # NCCL over NVLink / NVSwitch
-    ctx.reduce_fixup(ct, world)
+    if fixup:
+        ctx.reduce_fixup(ct, world)
 
 
-def reduce_scatter_sum(part, mine, world: int, group=None):
+def reduce_scatter_sum(part, mine, world: int, group=None, fixup: bool = True):
     """Sum of the partial ciphertext batches over the ranks, scattered over the batch dimension:
     rank r of the group receives ciphertexts [r*B/world, (r+1)*B/world) of the sum in `mine` (canonical residues).
-    Half the bytes of an all-reduce on the wire, and every rank rescales only its own share afterwards."""
+    Half the bytes of an all-reduce on the wire, and every rank rescales only its own share afterwards.
+    fixup=False leaves the raw uint64 sums for Context.rescale_sum_to_next."""
     import torch
     import torch.distributed as dist
 
@@ -105,7 +108,8 @@ def reduce_scatter_sum(part, mine, world: int, group=None):
         dist.reduce_scatter_tensor(dst, src, op=dist.ReduceOp.SUM, group=group)
     _, _, L, scale = part.info()
     mine.set_meta(2, L, scale)
-    ctx.reduce_fixup(mine, world)
+    if fixup:
+        ctx.reduce_fixup(mine, world)
 
 
 def matvec_bsgs_diag_sharded(ctx, out, x, diags_local, n1: int, n2_total: int, rank: int, world: int, hoist: bool = True,
@@ -123,6 +127,8 @@ def matvec_bsgs_diag_sharded(ctx, out, x, diags_local, n1: int, n2_total: int, r
     else:  # more ranks than giant steps: contribute zero
         part.upload(np.zeros((x.batch, 2, L, ctx.n), dtype=np.uint64), x.scale * diags_local.scale if diags_local else x.scale)
     if world > 1:
-        allreduce_sum(part, world, group)
-    ctx.rescale_to_next(out, part)
+        allreduce_sum(part, world, group, fixup=False)
+        ctx.rescale_sum_to_next(out, part, world)  # the mod-q fix-up of the sum rides in the rescale's loads
+    else:
+        ctx.rescale_to_next(out, part)
     return out

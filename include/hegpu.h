@@ -142,6 +142,11 @@ int hegpu_ntt_inverse_device(hegpu_ctx *ctx, void *d_data, uint32_t count, uint3
 int hegpu_ntt_forward_host(hegpu_ctx *ctx, uint64_t *host, uint32_t count, uint32_t first_mod, uint32_t n_mods);
 int hegpu_ntt_inverse_host(hegpu_ctx *ctx, uint64_t *host, uint32_t count, uint32_t first_mod, uint32_t n_mods);
 
+/* Issue-rate microbenchmark of one arithmetic pipe on this device (bench.py's integer / FP64 rooflines of the
+ * multiply-accumulate kernels): kind 0 = IMAD.WIDE.U32 (32x32->64 multiply-add), 1 = DFMA, 2 = IMAD (32-bit).
+ * *ops_per_second = thread-level operations per second with every SM busy.  Blocking. */
+int hegpu_pipe_peak(hegpu_ctx *ctx, int kind, double *ops_per_second);
+
 /* ---- composites that stay on the device.
  *
  * hegpu_matvec_bsgs: plaintext-diagonal x encrypted-vector product, baby-step/giant-step,
@@ -231,6 +236,11 @@ int hegpu_ct_transparent(hegpu_ctx *ctx, const hegpu_ct *ct, uint32_t *count);
 /* ---- multi-GPU: after an NCCL uint64 sum of `terms` partial ciphertexts the
  * residues are < terms*q; reduce them back to [0,q). */
 int hegpu_reduce_fixup(hegpu_ctx *ctx, hegpu_ct *ct, uint32_t terms);
+/* The same fix-up folded into the rescale that follows it ("a fused fix-up kernel ... as the first step
+ * of rescale"): `a` holds the element-wise uint64 sum of `terms` <= 16 partial ciphertexts at level L, out =
+ * rescale_to_next(a mod q) at level L-1.  The reduction rides in the operand loads of the rescale's two transforms,
+ * so the summed batch crosses HBM once instead of three times.  out must not be `a`. */
+int hegpu_rescale_sum_to_next(hegpu_ctx *ctx, hegpu_ct *out, const hegpu_ct *a, uint32_t terms);
 
 #ifdef __cplusplus
 }

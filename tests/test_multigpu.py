@@ -163,11 +163,13 @@ def test_diag_sharded_emulated_on_one_gpu():
     for p in parts[1:]:
         acc += as_torch_i64(p)  # stands in for the NCCL uint64 sum
     torch.cuda.synchronize()
+    out, out2 = ctx.ct(B, 2, L - 1), ctx.ct(B, 2, L - 1)
+    ctx.rescale_sum_to_next(out2, parts[0], world)  # fix-up folded into the rescale's loads (raw sums in)
     ctx.reduce_fixup(parts[0], world)
-    out = ctx.ct(B, 2, L - 1)
     ctx.rescale_to_next(out, parts[0])
     want = S.o.matvec_bsgs(cts, N1, N2, pts, bk, gkeys, hoist=True, lazy=False)
     assert np.array_equal(out.download(), want)
+    assert np.array_equal(out2.download(), want)
 
 
 @pytest.mark.gpu
@@ -226,8 +228,8 @@ def _nccl_worker(rank, world, port, q):
 
     part, mine, out_rs = ctx.ct(B, 2, L), ctx.ct(B // world, 2, L), ctx.ct(B // world, 2, L - 1)
     ctx.matvec_bsgs(part, X, D, N1, cnt, rescale=False, hoist=True, lazy=False, g_first=g0)
-    reduce_scatter_sum(part, mine, world)
-    ctx.rescale_to_next(out_rs, mine)
+    reduce_scatter_sum(part, mine, world, fixup=False)
+    ctx.rescale_sum_to_next(out_rs, mine, world)
     per = B // world
     full = out.download()
     assert np.array_equal(out_rs.download(), full[rank * per:(rank + 1) * per])
