@@ -409,59 +409,145 @@ extern "C" int hegpu_profile_read(hegpu_ctx *c, int kind, double *ms, uint64_t *
 }
 
 // ------------------------------------------------------------------------- pipe peaks (measurement)
-// Issue-rate microbenchmarks behind the integer / FP64 rooflines that bench.py reports for the multiply-accumulate
-// kernels: 8 independent dependent-chains per thread of ONE instruction kind, enough CTAs to fill every SM.
+// Issue-rate microbenchmarks behind the integer / FP64 rooflines that bench.py reports: independent dependent-chains
+// per thread of ONE instruction kind or ONE arithmetic sequence of the product kernels, enough CTAs to fill every SM.
 //   kind 0: IMAD.WIDE.U32 (32 x 32 -> 64 multiply-add, the building block of every 64-bit modular product)
 //   kind 1: DFMA
 //   kind 2: IMAD (32-bit low multiply-add)
+//   kind 3: mac128 (modarith.cuh): one 64 x 64 -> 128-bit multiply-accumulate, the unit of dh_inner / ks_inner
+//   kind 4: the 60-bit forward NTT butterfly (ArI64<true>::fwd_bfly: Shoup product + add/sub) with the per-pass
+//           range correction every third stage, as in the radix-8 passes
+//   kind 5: the FP64 forward NTT butterfly (ArF64::fwd_bfly, primes below 2^43)
+// Kinds 3-5 run the product's own device functions on register operands only: what the arithmetic alone allows
+// when no load, exchange, address computation or barrier is in the way.
 template <int KIND>
-__global__ void __launch_bounds__(256) pipe_peak_kernel(u64 *__restrict__ out, u32 iters, u32 seed)
+__global__ void __launch_bounds__(256) pipe_peak_kernel(u64 *__restrict__ out, u32 iters, u32 seed, u32 sink, const ModConst *mods,
+                                                        const ModF64 *modsd)
 {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     u32 x = t * 2654435761u + seed, y = (t ^ seed) | 1u;
-    u64 a[8];
-    double d[8];
-    u32 r[8];
-    const double dx = 1.0 + (double)(x & 1023u) * 1e-9, dy = 1e-9 * (double)(y & 1023u);
+    u64 acc = 0;
+    if constexpr (KIND <= 2) {
+        u64 a[8];
+        double d[8];
+        u32 r[8];
+        const double dx = 1.0 + (double)(x & 1023u) * 1e-9, dy = 1e-9 * (double)(y & 1023u);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        a[i] = (u64)t + i;
-        d[i] = (double)i;
-        r[i] = t + i;
-    }
-    for (u32 it = 0; it < iters; ++it) {
+        for (int i = 0; i < 8; ++i) {
+            a[i] = (u64)t + i;
+            d[i] = (double)i;
+            r[i] = t + i;
+        }
+        for (u32 it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int rep = 0; rep < 4; ++rep) {
+            for (int rep = 0; rep < 4; ++rep) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (KIND == 0) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(x), "r"(y));
-                if (KIND == 1) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dx), "d"(dy));
-                if (KIND == 2) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(x), "r"(y));
+                for (int i = 0; i < 8; ++i) {
+                    if (KIND == 0) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(x), "r"(y));
+                    if (KIND == 1) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dx), "d"(dy));
+                    if (KIND == 2) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(x), "r"(y));
+                }
             }
         }
-    }
-    u64 acc = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc += a[i] + (u64)__double_as_longlong(d[i]) + r[i];
-    if (acc == 0x1234567887654321ull) out[0] = acc;  // never true in practice; keeps the chains alive
+        for (int i = 0; i < 8; ++i) acc += a[i] + (u64)__double_as_longlong(d[i]) + r[i];
+    } else if constexpr (KIND == 3) {
+        // 8 accumulators x 4 operand pairs per iteration = 32 products; operands below 2^62 in distinct registers
+        u64 hi[8], lo[8], xs[8], ys[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            hi[i] = 0;
+            lo[i] = t + i;
+            xs[i] = (((u64)x << 29) ^ ((u64)y * (2 * i + 1))) & 0x3FFFFFFFFFFFFFFFull;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ys[j] = (((u64)y << 30) ^ ((u64)x * (2 * j + 3))) & 0x3FFFFFFFFFFFFFFFull;
+        for (u32 it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int rep = 0; rep < 4; ++rep) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mac128(hi[i], lo[i], xs[(i + rep) & 7], ys[rep]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hi[i] &= 0xFFFFFFFull;  // keep the sums from wrapping (one LOP3 per 4 products)
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += hi[i] ^ lo[i];
+    } else if constexpr (KIND == 4) {
+        // 4 independent butterflies per stage (a radix-8 register set), 3 stages between range corrections, 32 per iteration
+        const ModConst m = mods[0];
+        const ArI64<true> ar(m, make_ulonglong2(0, 0));
+        u64 v[8];
+        ulonglong2 W[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = ((u64)x * (i + 1) + y) % m.q;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            W[j].x = ((u64)y * (j + 5) + x) % m.q;
+            W[j].y = (u64)(((unsigned __int128)W[j].x << 64) / m.q);
+        }
+        for (u32 it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int rep = 0; rep < 8; ++rep) {
+                if (rep % 3 == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = ar.fwd_fix(v[i]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int s = rep % 3, lo_ = j & ((1 << s) - 1), k = ((j >> s) << (s + 1)) | lo_;
+                    ar.fwd_bfly(v[k], v[k | (1 << s)], W[(j + rep) & 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += v[i];
+    } else {
+        const ArF64 ar(modsd[1]);
+        double v[8], W[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (double)((x * (i + 1) + y) & 0xFFFFFu);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) W[j] = (double)((y * (j + 5) + x) & 0xFFFFFFFu);
+        for (u32 it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int s = rep % 3, lo_ = j & ((1 << s) - 1), k = ((j >> s) << (s + 1)) | lo_;
+                    ar.fwd_bfly(v[k], v[k | (1 << s)], W[(j + rep) & 3]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = ar.reduce(v[i]);  // once per 8 stages, as the per-pass fix of the inverse transform
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += (u64)__double_as_longlong(v[i]);
+    }
+    if (sink) out[t] = acc;  // sink = 0 at run time; keeps the chains alive
 }
 
 extern "C" int hegpu_pipe_peak(hegpu_ctx *c, int kind, double *ops_per_second)
 {
     if (!c || !ops_per_second) INVALID("null argument");
-    if (kind < 0 || kind > 2) INVALID("pipe kind out of range");
+    if (kind < 0 || kind > 5) INVALID("pipe kind out of range");
+    if (kind == 5 && (c->K < 2 || c->q[1] >= (1ull << 43))) INVALID("kind 5 needs modulus 1 of the chain below 2^43");
     TRY(set_device(c));
     TRY(arena_reserve(c, 256));
-    const u32 iters = 2048, grid = (u32)c->sms * 8, block = 256;
+    const u32 iters = kind >= 3 ? 512 : 2048, grid = (u32)c->sms * 8, block = 256;
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     float best = 0;
+    u64 *o = (u64 *)c->arena.base;
     for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
         CU(cudaEventRecord(e0, c->stream));
-        if (kind == 0) pipe_peak_kernel<0><<<grid, block, 0, c->stream>>>((u64 *)c->arena.base, iters, 12345u + rep);
-        if (kind == 1) pipe_peak_kernel<1><<<grid, block, 0, c->stream>>>((u64 *)c->arena.base, iters, 12345u + rep);
-        if (kind == 2) pipe_peak_kernel<2><<<grid, block, 0, c->stream>>>((u64 *)c->arena.base, iters, 12345u + rep);
+        if (kind == 0) pipe_peak_kernel<0><<<grid, block, 0, c->stream>>>(o, iters, 12345u + rep, 0u, c->d_mods, c->d_modsd);
+        if (kind == 1) pipe_peak_kernel<1><<<grid, block, 0, c->stream>>>(o, iters, 12345u + rep, 0u, c->d_mods, c->d_modsd);
+        if (kind == 2) pipe_peak_kernel<2><<<grid, block, 0, c->stream>>>(o, iters, 12345u + rep, 0u, c->d_mods, c->d_modsd);
+        if (kind == 3) pipe_peak_kernel<3><<<grid, block, 0, c->stream>>>(o, iters, 12345u + rep, 0u, c->d_mods, c->d_modsd);
+        if (kind == 4) pipe_peak_kernel<4><<<grid, block, 0, c->stream>>>(o, iters, 12345u + rep, 0u, c->d_mods, c->d_modsd);
+        if (kind == 5) pipe_peak_kernel<5><<<grid, block, 0, c->stream>>>(o, iters, 12345u + rep, 0u, c->d_mods, c->d_modsd);
         c->launches++;
         CU(cudaEventRecord(e1, c->stream));
         CU(cudaEventSynchronize(e1));

@@ -142,8 +142,10 @@ int hegpu_ntt_inverse_device(hegpu_ctx *ctx, void *d_data, uint32_t count, uint3
 int hegpu_ntt_forward_host(hegpu_ctx *ctx, uint64_t *host, uint32_t count, uint32_t first_mod, uint32_t n_mods);
 int hegpu_ntt_inverse_host(hegpu_ctx *ctx, uint64_t *host, uint32_t count, uint32_t first_mod, uint32_t n_mods);
 
-/* Issue-rate microbenchmark of one arithmetic pipe on this device (bench.py's integer / FP64 rooflines of the
- * multiply-accumulate kernels): kind 0 = IMAD.WIDE.U32 (32x32->64 multiply-add), 1 = DFMA, 2 = IMAD (32-bit).
+/* Issue-rate microbenchmarks on this device (bench.py's integer / FP64 rooflines): kind 0 = IMAD.WIDE.U32 (32x32->64
+ * multiply-add), 1 = DFMA, 2 = IMAD (32-bit); and of the product's own arithmetic sequences on register operands:
+ * 3 = one 64x64->128-bit multiply-accumulate (the unit of the key inner products), 4 = one 60-bit forward NTT
+ * butterfly (Shoup), 5 = one FP64 NTT butterfly (modulus 1 of the chain must be below 2^43).
  * *ops_per_second = thread-level operations per second with every SM busy.  Blocking. */
 int hegpu_pipe_peak(hegpu_ctx *ctx, int kind, double *ops_per_second);
 
