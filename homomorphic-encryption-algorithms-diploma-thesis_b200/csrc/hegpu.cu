@@ -194,6 +194,7 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     if (const char *e = getenv("HEGPU_PARK")) c->use_park = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_FUSED")) c->dh_fused = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_F64")) c->dh_f64 = atoi(e) != 0;
+    if (const char *e = getenv("HEGPU_DH_SWZ")) c->dh_swz = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_FUSE_FINAL")) c->fuse_final = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_PARK32K")) c->park32k = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -443,7 +444,11 @@ __global__ void __launch_bounds__(256) pipe_peak_kernel(u64 *__restrict__ out, u
             for (int rep = 0; rep < 4; ++rep) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    if (KIND == 0) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(x), "r"(y));
+                    // multiplicand = low word of the neighbouring chain: changes every iteration, so nothing can be hoisted
+                    if (KIND == 0)
+                        asm volatile("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tmad.wide.u32 %0, lo, %2, %0;\n\t}"
+                                     : "+l"(a[i])
+                                     : "l"(a[(i + 1) & 7]), "r"(y));
                     if (KIND == 1) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dx), "d"(dy));
                     if (KIND == 2) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(x), "r"(y));
                 }
@@ -468,8 +473,14 @@ __global__ void __launch_bounds__(256) pipe_peak_kernel(u64 *__restrict__ out, u
 #pragma unroll
                 for (int i = 0; i < 8; ++i) mac128(hi[i], lo[i], xs[(i + rep) & 7], ys[rep]);
             }
+            // new operands every iteration (in the product kernels they come from loads): nothing loop-invariant to hoist
 #pragma unroll
-            for (int i = 0; i < 8; ++i) hi[i] &= 0xFFFFFFFull;  // keep the sums from wrapping (one LOP3 per 4 products)
+            for (int i = 0; i < 8; ++i) {
+                hi[i] &= 0xFFFFFFFull;  // keep the sums from wrapping
+                xs[i] = (xs[i] + lo[(i + 3) & 7]) & 0x3FFFFFFFFFFFFFFFull;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ys[j] = (ys[j] ^ lo[j]) & 0x3FFFFFFFFFFFFFFFull;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc += hi[i] ^ lo[i];
@@ -1594,7 +1605,8 @@ static int launch_dh_inner(hegpu_ctx *c, const DhInnerParams &P)
     for (u32 g0 = 0; g0 < P.n2; g0 += N2) {
         Q.g0 = g0;
         Q.ng = std::min<u32>(N2, P.n2 - g0);
-        kern<<<grid, DH_TX * DH_KG, smem, c->stream>>>(Q, c->d_mods, c->dh_f64);
+        const int swz = (c->dh_swz && LT == 3 && c->sms % 4 == 0) ? (c->sms << 8) : 0;
+        kern<<<grid, DH_TX * DH_KG, smem, c->stream>>>(Q, c->d_mods, c->dh_f64 | swz);
         c->launches++;
         CU(cudaGetLastError());
     }

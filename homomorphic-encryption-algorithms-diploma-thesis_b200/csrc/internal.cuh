@@ -99,6 +99,7 @@ struct hegpu_ctx {
     u64 launches = 0;
     int sms = 148;
     int dh_f64 = 1;    // fused kernel: FP64-pipe arithmetic on the limbs whose modulus is below 2^40 (HEGPU_DH_F64=0: integer everywhere)
+    int dh_swz = 0;    // fused kernel: limb order rotated per wave of CTAs so that co-resident CTAs mix the two policies (HEGPU_DH_SWZ=1)
     int fuse_final = 1;  // double-hoisted matvec: final mod-down and rescale as one pass (HEGPU_FUSE_FINAL=0: two steps)
     int park32k = 1;     // N = 32768: one CTA per transform with the park scheme (HEGPU_PARK32K=0: two CTAs + finishing pass)
     int dh_fused = 1;  // double-hoisted matvec: fused baby-step + inner-sum kernel (HEGPU_DH_FUSED=0: unfused kernels)

@@ -558,7 +558,15 @@ __global__ void __launch_bounds__(DH_TX * DH_KG, 2) dh_inner_kernel(const DhInne
     constexpr u32 TX = DH_TX, L = LT;
     // neighbouring CTAs take different limbs of the same tile: the CTAs that share an SM then mix the
     // integer-pipe policy (60-bit limbs) with the FP64-pipe policy (40-bit limbs)
-    const u32 x0 = (blockIdx.x / (L + 1)) * TX, i = blockIdx.x % (L + 1);
+    const u32 x0 = (blockIdx.x / (L + 1)) * TX;
+    u32 i = blockIdx.x % (L + 1);
+    if (const u32 period = (u32)use_f64 >> 8) {
+        // L + 1 == 4 and `period` (the SM count) a multiple of 4: CTAs c and c + period land on the same SM in the first
+        // wave and would take the same limb; rotate the limb by the wave number and order the limbs int, fp, int, fp
+        const u32 j = (i + blockIdx.x / period) & 3u;
+        i = j == 2 ? 3u : j == 3 ? 2u : j;
+    }
+    use_f64 &= 1;
     const u32 b0 = blockIdx.z * DH_BCH, b1 = min(P.B, b0 + DH_BCH);
     const ModConst m = mods[(i == L) ? P.K - 1 : i];
     u64 *skey = dh_smem;                                                // [n1][2L][TX]

@@ -209,7 +209,7 @@ def write_with_oracle(path, n=4096, bits=(36, 36, 37), seed=3):
     for e, k in gk.items():
         rec[f"galois_key.{e}"] = k
     rec["galois_elts"] = np.array(sorted(gk), dtype=np.int64)
-    scale = float(2 ** bits[1])
+    scale = float(2**20)  # small enough for the product of two fresh ciphertexts on short chains
 
     def residues(*prefix):
         a = np.empty(prefix + (L, n), dtype=np.uint64)
