@@ -1,0 +1,4 @@
+#!/bin/bash
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r2i_bench_8gpu.json 2> gpurun_out/r2i_bench_8gpu.err
+nvidia-smi topo -m > gpurun_out/r2i_topo.txt 2>&1
+numactl --hardware >> gpurun_out/r2i_topo.txt 2>&1 || lscpu | grep -i numa >> gpurun_out/r2i_topo.txt
