@@ -195,6 +195,65 @@ int main(int argc, char **argv)
             else if (which == 1) out.push_back(he::math::inv_sqrt_twice(cencd, eval, rk, cts[0], a, iters));
             else if (which == 2) out.push_back(he::math::sqrt(ctx, cencd, eval, rk, cts[0], a, iters));
             else out.push_back(he::math::abs(ctx, cencd, eval, rk, cts[0], a, iters));
+        } else if (cmd == "least_squares") {  // args: n   (bench_he_least_squares_2d, src/demos/matrix_operations.cpp:833-1040, statement by statement)
+            const std::size_t nn = (std::size_t)arg(4);
+            BatchedVector x_ctv(nn, cts[0]), y_ctv(nn, cts[1]);
+            Ciphertext sum_x_ct = x_ctv.sum_elems(eval, gk).get_bvec();
+            Ciphertext sum_y_ct = y_ctv.sum_elems(eval, gk).get_bvec();
+            Ciphertext sum_xx_ct = x_ctv.square(eval, rk).sum_elems(eval, gk).get_bvec();
+            Ciphertext sum_xy_ct = (eval % rk % x_ctv * y_ctv).sum_elems(eval, gk).get_bvec();
+            // denominator n * sum(xx) - sum(x)^2
+            Plaintext n_pt;
+            cencd.encode((double)nn, sum_xx_ct.parms_id(), sum_xx_ct.scale(), n_pt);
+            Ciphertext n_sum_xx_ct = eval % sum_xx_ct * n_pt;
+            n_sum_xx_ct ^= eval;
+            Ciphertext sum_x_sqr_ct;
+            eval.square(sum_x_ct, sum_x_sqr_ct);
+            sum_x_sqr_ct &= eval % rk;
+            sum_x_sqr_ct ^= eval;
+            Plaintext one_pt;
+            cencd.encode(1.0, sum_x_sqr_ct.parms_id(), sum_x_sqr_ct.scale(), one_pt);
+            sum_x_sqr_ct *= eval % one_pt;
+            sum_x_sqr_ct ^= eval;
+            Ciphertext denom_ct = eval % n_sum_xx_ct - sum_x_sqr_ct;
+            Plaintext one_pt_;  // slot 0 only (the reference's FIXME: the inverse must not see the other slots)
+            cencd.encode(std::vector<double>{ 1 }, denom_ct.parms_id(), denom_ct.scale(), one_pt_);
+            denom_ct *= eval % one_pt_;
+            denom_ct ^= eval;
+            Ciphertext denom_inv_ct = he::math::signed_inv(cencd, eval, rk, denom_ct, 0.05, 6);
+            // numerator of a: n * sum(xy) - sum(x) sum(y)
+            Ciphertext n_sum_xy_ct = eval % sum_xy_ct * n_pt;
+            n_sum_xy_ct ^= eval;
+            Ciphertext sum_x_sum_y_ct = eval % sum_x_ct * sum_y_ct;
+            sum_x_sum_y_ct &= eval % rk;
+            sum_x_sum_y_ct ^= eval;
+            sum_x_sum_y_ct *= eval % one_pt;
+            sum_x_sum_y_ct ^= eval;
+            Ciphertext a_num_ct = eval % n_sum_xy_ct - sum_x_sum_y_ct;
+            // numerator of b: sum(y) sum(xx) - sum(x) sum(xy)
+            cencd.encode(1.0, sum_y_ct.parms_id(), sum_y_ct.scale(), one_pt);
+            Ciphertext sum_y_sum_xx_ct = sum_y_ct;
+            sum_y_sum_xx_ct *= eval % one_pt;
+            sum_y_sum_xx_ct ^= eval;
+            sum_y_sum_xx_ct *= eval % sum_xx_ct;
+            sum_y_sum_xx_ct &= eval % rk;
+            sum_y_sum_xx_ct ^= eval;
+            Ciphertext sum_x_sum_xy_ct = sum_x_ct;
+            sum_x_sum_xy_ct *= eval % one_pt;
+            sum_x_sum_xy_ct ^= eval;
+            sum_x_sum_xy_ct *= eval % sum_xy_ct;
+            sum_x_sum_xy_ct &= eval % rk;
+            sum_x_sum_xy_ct ^= eval;
+            Ciphertext b_num_ct = eval % sum_y_sum_xx_ct - sum_x_sum_xy_ct;
+            // a, b
+            he::util::reach_chain_level(ctx, cencd, eval, one_pt, std::vector<Ciphertext *>{ &a_num_ct, &b_num_ct }, denom_inv_ct);
+            Ciphertext a_ct = eval % a_num_ct * denom_inv_ct;
+            a_ct &= eval % rk;
+            a_ct ^= eval;
+            Ciphertext b_ct = eval % b_num_ct * denom_inv_ct;
+            b_ct &= eval % rk;
+            b_ct ^= eval;
+            for (const Ciphertext *c : { &denom_ct, &denom_inv_ct, &a_num_ct, &b_num_ct, &a_ct, &b_ct }) out.push_back(*c);
         } else if (cmd == "errors") {
             // exception types and messages must be SEAL's
             int ok = 0;

@@ -386,3 +386,27 @@ def test_matmul_pow(tmp_path):
         assert abs(S.decrypt(got, got_scale).real[0] - A4[idx % d, idx // d]) < 1e-4
     _, _, _, stdout = run(tmp_path, S, "matpow", [d, 3], cts=[(c, sc) for c in cts], rk=True)
     assert "matpow_error=encrypted1 and encrypted2 parameter mismatch" in stdout
+
+
+def test_least_squares_2d_demo(tmp_path):
+    """bench_he_least_squares_2d (src/demos/matrix_operations.cpp:833-1040) end to end through the C++ host mirror at
+    the demo's own parameters: N = 32768, {60, 40 x 15, 60}, scale 2^40, the demo's five (x, y) points.  sum_elems
+    (rotations 1 and 2), BatchedVector square / product, the operator DSL, he::math::signed_inv (6 iterations) and
+    he::util::reach_chain_level, all on the device; slot 0 of the results against the closed-form line fit."""
+    n = 32768
+    S = setup(n, (60,) + (40,) * 15 + (60,))
+    sc, L = 2.0**40, 16
+    x = np.array([6, 5.8, 6.5, 5.4, 6.8])
+    y = np.array([2, 1.4, 2.4, 1.5, 2.4])
+    cx, cy = S.encrypt(x, sc, L, seed=1), S.encrypt(y, sc, L, seed=2)
+    outs, _, _, _ = run(tmp_path, S, "least_squares", [len(x)], cts=[(cx, sc), (cy, sc)], rk=True, gk_steps=[1, 2])
+    k = len(x)
+    denom = k * np.sum(x * x) - np.sum(x) ** 2
+    a_num = k * np.sum(x * y) - np.sum(x) * np.sum(y)
+    b_num = np.sum(y) * np.sum(x * x) - np.sum(x) * np.sum(x * y)
+    want = [denom, 1.0 / denom, a_num, b_num, a_num / denom, b_num / denom]
+    got = [float(S.decrypt(ct, scale).real[0]) for ct, scale in outs]
+    slope, intercept = np.polyfit(x, y, 1)
+    assert abs(want[4] - slope) < 1e-9 and abs(want[5] - intercept) < 1e-9
+    for name, g, w in zip(("denom", "1/denom", "a_num", "b_num", "a", "b"), got, want):
+        assert abs(g - w) < 2e-4 * max(1.0, abs(w)), (name, g, w)
