@@ -39,7 +39,8 @@ def _stale() -> bool:
 
 
 HOST = os.path.join(HERE, "host")
-HOST_SRC = ["ckks_encoder.cpp", "he_operators.cpp", "he_linalg.cpp", "he_fft.cpp", "he_math.cpp"]
+HOST_SRC = ["ckks_encoder.cpp", "he_operators.cpp", "he_linalg.cpp", "he_fft.cpp", "he_math.cpp", "seal_wire.cpp", "he_server.cpp"]
+WIRE_LIB = os.path.join(HERE, "libseal_wire.so")  # the wire layer alone: pure host code, loadable without a GPU
 HOST_LIB = os.path.join(HERE, "libhe_host.so")
 HOST_TEST = os.path.join(HERE, "he_host_test")
 
@@ -48,16 +49,17 @@ def build_host(force: bool = False) -> str:
     """C++ host mirror of the reference's interface (he_operators / he_linalg / he_fft / he_util)
     over the C ABI, plus the test driver binary."""
     deps = [os.path.join(HOST, f) for f in os.listdir(HOST)] + [LIB]
-    if not force and os.path.exists(HOST_LIB) and os.path.exists(HOST_TEST):
-        t = min(os.path.getmtime(HOST_LIB), os.path.getmtime(HOST_TEST))
+    if not force and os.path.exists(HOST_LIB) and os.path.exists(HOST_TEST) and os.path.exists(WIRE_LIB):
+        t = min(os.path.getmtime(HOST_LIB), os.path.getmtime(HOST_TEST), os.path.getmtime(WIRE_LIB))
         if all(os.path.getmtime(d) <= t for d in deps):
             return HOST_LIB
     cxx = os.environ.get("CXX", "/usr/bin/g++")
     inc = ["-I", os.path.join(HERE, "..", "include"), "-I", HOST]
     common = [cxx, "-std=c++20", "-O2", "-fPIC", "-Wall"] + inc
-    link = ["-L", HERE, "-lhegpu", "-Wl,-rpath,$ORIGIN"]
-    for cmd in (common + ["-shared", "-o", HOST_LIB] + [os.path.join(HOST, f) for f in HOST_SRC] + link,
-                common + ["-o", HOST_TEST, os.path.join(HOST, "he_host_test.cpp"), "-L", HERE, "-lhe_host", "-lhegpu", "-Wl,-rpath,$ORIGIN"]):
+    link = ["-L", HERE, "-lhegpu", "-lz", "-ldl", "-Wl,-rpath,$ORIGIN"]
+    for cmd in (common + ["-shared", "-o", WIRE_LIB, os.path.join(HOST, "seal_wire.cpp"), os.path.join(HOST, "seal_wire_c.cpp"), "-lz", "-ldl"],
+                common + ["-shared", "-o", HOST_LIB] + [os.path.join(HOST, f) for f in HOST_SRC] + link,
+                common + ["-o", HOST_TEST, os.path.join(HOST, "he_host_test.cpp"), "-L", HERE, "-lhe_host", "-lhegpu", "-lz", "-ldl", "-Wl,-rpath,$ORIGIN"]):
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout)

@@ -10,8 +10,11 @@
 #include <iostream>
 #include <string>
 
+#include <iterator>
+
 #include "he_fft.h"
 #include "he_linalg.h"
+#include "he_server.hpp"
 #include "he_math.h"
 #include "he_util.h"
 
@@ -67,6 +70,18 @@ int main(int argc, char **argv)
         std::ifstream f(argv[1], std::ios::binary);
         const std::string cmd = argv[2];
         auto arg = [&](int i) { return i < argc ? std::atoi(argv[i]) : 0; };
+        if (cmd.rfind("serve_", 0) == 0) {  // the reference server's modes: argv[1] is the request payload, argv[3] receives the reply
+            const he::wire::bytes req((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+            he::wire::bytes rep;
+            if (cmd == "serve_simple") rep = he::server::server_side_simple(req);
+            else if (cmd == "serve_batch_matmul") rep = he::server::server_side_batch_matmul(req, (std::size_t)arg(4), (std::size_t)arg(5), (std::size_t)arg(6), (std::size_t)arg(7));
+            else if (cmd == "serve_fft") rep = he::server::server_side_fft(req, (std::size_t)arg(4));
+            else throw std::invalid_argument("unknown server mode");
+            std::ofstream o(argv[3], std::ios::binary);
+            o.write(reinterpret_cast<const char *>(rep.data()), (std::streamsize)rep.size());
+            std::printf("ok %zu reply bytes\n", rep.size());
+            return 0;
+        }
         auto argd = [&](int i) { return i < argc ? std::atof(argv[i]) : 0.0; };
         const std::uint32_t n = rd<std::uint32_t>(f), K = rd<std::uint32_t>(f);
         const auto moduli = rdv(f, K);
