@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark: CKKS matvecs/s, N = 2^14, 128x128 plaintext matrix x
-encrypted vector, double-hoisted BSGS 32x4, batch of 128 ciphertexts per step (BASELINE.json
+encrypted vector, double-hoisted BSGS 32x4, batch of 256 ciphertexts per step (BASELINE.json
 configs[1]).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
                   [--mode dh|hoist|exact] [--n1 N1] [--batch B] [--no-cfg5] [--no-micro] [--diag-ranks D]
 
 One process per GPU (torchrun for N > 1).  A step is one pass of hegpu_matvec_bsgs over a
-batch of 128 encrypted vectors on every rank (batch sharding, no data-path collective ->
+batch of 256 encrypted vectors on every rank (batch sharding, no data-path collective ->
 weak scaling).  Prints ONE JSON line (rank 0).
 
   value     matvecs/s with inputs resident in HBM (CUDA events on the context's stream)
@@ -41,7 +41,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(N=16384, bits=(60, 40, 40, 60), dim=128, n1=32, n2=4, batch=128, scale=2.0**40, L=3, mode="dh")
+CFG = dict(N=16384, bits=(60, 40, 40, 60), dim=128, n1=32, n2=4, batch=256, scale=2.0**40, L=3, mode="dh")
 CFG5 = dict(N=32768, bits=(60, 40, 40, 60), dim=512, n1=32, n2=16, total_batch=1024, scale=2.0**40, L=3)
 MODES = {
     "exact": "no flags: the exact chain of SEAL primitives (rotate_vector, multiply_plain, add, rescale_to_next per diagonal)",

@@ -73,6 +73,11 @@ struct NttShape {
     static constexpr size_t SMEM = sizeof(u64) << LOGL;
 };
 
+// Bank swizzle of the in-place exchange buffer (64-bit words, 16 banks per half-warp access): two ALU operations per
+// address.  The pass whose register field sits at index bit 1 runs with 2-way conflicts under this fold (index bits 0
+// and 4 land in the same bank bit; ncu: 23 % of a transform's shared-memory wavefronts).  The conflict-free linear map
+// idx[3:0] ^ (h ^ h << 1), h = idx[7:4], was built and measured: bit-identical, zero conflicts, and 1-2 % SLOWER --
+// it costs two more ALU operations per address in kernels that are bound by instruction issue, not by shared memory.
 __device__ __forceinline__ u32 swz(u32 idx) { return idx ^ ((idx >> 4) & 15u); }
 
 // Position of the 2^LOGE coefficients a thread owns in a pass.  The low S bits of the register
