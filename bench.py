@@ -585,13 +585,16 @@ def run_gpu(args):
     ntt_launches = sum(prof[k]["launches"] for k in ntt_keys)
     ntt_gbs = ntt_bytes / (ntt_ms * 1e-3) / 1e9 if ntt_ms else 0.0
     # DRAM traffic per launch comes from the committed ncu capture of this configuration (profiles/), not from this run
-    profiled = {}
+    profiled, capture_config = {}, None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            if tj.get("config") == f"{mode}-{c['n1']}x{c['n2']}-b{B}":
+            # the captures are per LAUNCH: one launch covers one execution slot's chunk (128 ciphertexts at batch 128 with
+            # one slot and at batch 256 with two), so they hold for any batch with the same mode and BSGS split
+            if str(tj.get("config", "")).startswith(f"{mode}-{c['n1']}x{c['n2']}-"):
                 profiled = tj.get("kernels", {})
+                capture_config = tj.get("config")
         except Exception:
             pass
     # arithmetic ceilings measured in this run: the product's own butterfly / multiply-accumulate sequences on
@@ -603,7 +606,7 @@ def run_gpu(args):
         "bound": "hbm", "kernel": "ntt family (" + ", ".join(sorted(ntt_keys)) + ")", "achieved": ntt_gbs, "peak": peak, "unit": "GB/s",
         "frac": ntt_gbs / peak, "peak_source": peak_src,
         "traffic": (sum(profiled[k]["dram_bytes_per_launch"] for k in profiled if "ntt" in k) or None) if profiled else None,
-        "traffic_source": "from_profile (profiles/ncu_traffic.json: ncu --set full captures of the NTT kernels named there, per launch; not measured in this run)" if profiled else None,
+        "traffic_source": f"from_profile (profiles/ncu_traffic.json, capture config {capture_config}: ncu --set full captures of the NTT kernels named there, per launch; not measured in this run)" if profiled else None,
         "avg_launch_ms": ntt_ms / max(ntt_launches, 1), "share_of_step": ntt_ms / tot_ms,
         "arith_ceiling_GBps": {"60bit_butterfly": pk["bfly60"] * bfly_to_gbs, "fp64_butterfly": pk["bfly_fp64"] * bfly_to_gbs,
                                "note": "butterflies/s of the product's own butterfly code on register operands (no loads, exchanges, barriers) "
