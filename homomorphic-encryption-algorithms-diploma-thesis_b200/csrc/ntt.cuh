@@ -31,6 +31,8 @@
 //    memory and then own one half (forward), or finish with one element-wise stage kernel
 //    (inverse) -- see ntt_fwd_kernel / ntt_inv_kernel SPLIT.
 #pragma once
+#include <type_traits>
+
 #include "modarith.cuh"
 
 namespace hegpu {
@@ -224,28 +226,64 @@ struct ArF64 {
     __device__ __forceinline__ u64 inv_final(V v) const { return to_canonical(v); }
 };
 
+// compile-time loop: the body receives std::integral_constant<int, i>
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+// CNT consecutive twiddles starting at an index that is a multiple of CNT (a thread's butterflies of one stage use the
+// twiddles CNT*a .. CNT*a + CNT-1): doubles come as 128-bit loads (two per instruction) instead of one LDG.64 each --
+// in the last passes, where every lane pair reads its own twiddles, that halves the load instructions and the number
+// of partially used sectors
+template <int CNT>
+__device__ __forceinline__ void load_tw(const double *__restrict__ p, double (&w)[CNT])
+{
+    if constexpr (CNT == 1) {
+        w[0] = __ldg(p);
+    } else {
+#pragma unroll
+        for (int i = 0; i < CNT; i += 2) {
+            const double2 v = __ldg(reinterpret_cast<const double2 *>(p + i));
+            w[i] = v.x;
+            w[i + 1] = v.y;
+        }
+    }
+}
+template <int CNT>
+__device__ __forceinline__ void load_tw(const ulonglong2 *__restrict__ p, ulonglong2 (&w)[CNT])
+{
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) w[i] = __ldg(p + i);
+}
+
 // ------------------------------------------------------------------ forward butterflies
 // S stages on register bits S-1..0 (descending).  gbase = N + (global index of x[0]).
 template <int LOGE, int S, int PLO, int PHI, class A>
 __device__ __forceinline__ void fwd_stages(typename A::V (&x)[1 << LOGE], u32 gbase, const typename A::TW *__restrict__ tw, const A &ar)
 {
-#pragma unroll
-    for (int ss = 0; ss < S; ++ss) {
-        const int s = S - 1 - ss;
+    static_for<0, S>([&](auto ssc) {
+        constexpr int ss = decltype(ssc)::value;
+        constexpr int s = S - 1 - ss;
 #pragma unroll
         for (int kh = 0; kh < (1 << (LOGE - S)); ++kh) {
             const u32 g = (S == LOGE) ? gbase : gbase + ((u32)kh << PHI);
+            typename A::TW W[1 << ss];
+            load_tw<(1 << ss)>(tw + (g >> (PLO + s + 1)), W);  // g has zeros in the register field: the index is a multiple of 2^ss
 #pragma unroll
             for (int hi = 0; hi < (1 << ss); ++hi) {
-                const typename A::TW W = __ldg(tw + (g >> (PLO + s + 1)) + hi);
 #pragma unroll
                 for (int lo = 0; lo < (1 << s); ++lo) {
                     const int k = (kh << S) | (hi << (s + 1)) | lo;
-                    ar.fwd_bfly(x[k], x[k | (1 << s)], W);
+                    ar.fwd_bfly(x[k], x[k | (1 << s)], W[hi]);
                 }
             }
         }
-    }
+    });
 }
 
 // full radix-16 passes of the forward transform, field position descending
@@ -355,13 +393,16 @@ __device__ __forceinline__ void ntt_fwd_cta(Load load, Fetch fetch, Store store,
 template <int LOGE, int S, int PLO, int PHI, int LAST_BIT, class A>
 __device__ __forceinline__ void inv_stages(typename A::V (&x)[1 << LOGE], u32 gbase, const typename A::TW *__restrict__ tw, const A &ar)
 {
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
+    static_for<0, S>([&](auto sc) {
+        constexpr int s = decltype(sc)::value;
 #pragma unroll
         for (int kh = 0; kh < (1 << (LOGE - S)); ++kh) {
             const u32 g = (S == LOGE) ? gbase : gbase + ((u32)kh << PHI);
+            constexpr int CNT = 1 << (S - 1 - s);
+            typename A::TW Wv[CNT];
+            if (PLO + s != LAST_BIT) load_tw<CNT>(tw + (g >> (PLO + s + 1)), Wv);  // the index is a multiple of CNT (zeros in the register field)
 #pragma unroll
-            for (int hi = 0; hi < (1 << (S - 1 - s)); ++hi) {
+            for (int hi = 0; hi < CNT; ++hi) {
                 if (PLO + s == LAST_BIT) {
 #pragma unroll
                     for (int lo = 0; lo < (1 << s); ++lo) {
@@ -372,7 +413,7 @@ __device__ __forceinline__ void inv_stages(typename A::V (&x)[1 << LOGE], u32 gb
                         if (s == 3) ar.template inv_bfly_last<PLO + 3>(x[k], x[k | 8]);
                     }
                 } else {
-                    const typename A::TW W = __ldg(tw + (g >> (PLO + s + 1)) + hi);
+                    const typename A::TW W = Wv[hi];
 #pragma unroll
                     for (int lo = 0; lo < (1 << s); ++lo) {
                         const int k = (kh << S) | (hi << (s + 1)) | lo;
@@ -384,7 +425,7 @@ __device__ __forceinline__ void inv_stages(typename A::V (&x)[1 << LOGE], u32 gb
                 }
             }
         }
-    }
+    });
 }
 
 // full radix-16 passes of the inverse transform, field position ascending
