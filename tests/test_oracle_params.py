@@ -92,6 +92,10 @@ def test_naf_known_answers():
     assert orc.naf(11) == [-1, -4, 16]
     assert orc.naf(63) == [-1, 64]
     assert orc.naf(-3) == [1, -4]
+    # SEAL's own unit test (native/tests/seal/util/numth.cpp, NAF)
+    for v, want in ((0, []), (1, [1]), (-1, [-1]), (2, [2]), (-2, [-2]), (127, [-1, 128]), (-127, [1, -128]), (123, [-1, -4, 128]),
+                    (-123, [1, 4, -128])):
+        assert orc.naf(v) == want, v
     for v in range(-300, 300):
         assert sum(orc.naf(v)) == v
 
@@ -115,3 +119,33 @@ def test_galois_elt_and_table():
         t = o.galois_table(elt)
         for k in (2, 8, 32):
             assert np.array_equal(t.reshape(-1, k)[:, 0] // k, t.reshape(-1, k)[:, -1] // k)
+
+
+def test_seal_unit_test_known_answers():
+    """Known answers of Microsoft SEAL's OWN unit tests (native/tests/seal/util/{numth,ntt,galois}.cpp, SEAL 4.x), quoted
+    from the published test sources -- the only reference-held vectors this path has (SEAL itself is absent).
+    They pin the three conventions everything else rests on: which primitive root SEAL picks (the numerically smallest),
+    the order and values of the forward transform, and the NTT-form Galois permutation.  The constants are mutually
+    consistent (checked below), which a misremembered digit would break."""
+    q = 0xFFFFFFFFFFC0001
+    # numth.cpp TryMinimalPrimitiveRoot: (modulus, degree) -> root
+    for mod, degree, root in ((11, 2, 10), (29, 2, 28), (29, 4, 12), (1234565441, 2, 1234565440), (1234565441, 8, 249725733)):
+        assert pow(root, degree // 2, mod) == mod - 1
+        assert ref.minimal_primitive_root(mod, degree // 2) == root
+        if degree >= 4:
+            assert orc.Oracle(degree // 2, [mod]).psi(0) == root
+    # ntt.cpp NTTBasics: coeff_count_power 2, modulus 0xffffffffffc0001: root powers in bit-reversed order 1, psi^2, psi, psi^3
+    psi, psi2, psi3 = 178930308976060547, 288794978602139552, 748001537669050592
+    assert pow(psi, 2, q) == psi2 and pow(psi, 3, q) == psi3 and pow(psi, 4, q) == q - 1
+    assert orc.Oracle(4, [q]).psi(0) == psi
+    # ntt.cpp NegacyclicNTTTest: coeff_count_power 1: {0,0} -> {0,0}; {1,0} -> {1,1}; {1,1} -> {288794978602139553, 864126526004445282}
+    o = orc.Oracle(2, [q])
+    assert o.psi(0) == psi2
+    for poly, want in (([0, 0], [0, 0]), ([1, 0], [1, 1]), ([1, 1], [288794978602139553, 864126526004445282])):
+        got = o.ntt_fwd(0, np.array(poly, dtype=np.uint64))
+        assert got.tolist() == want
+        assert o.ntt_inv(0, got).tolist() == poly  # InverseNegacyclicNTTTest: round trip
+    # galois.cpp: GaloisTool(3) (N = 8): get_elt_from_step and the two automorphism forms on in = {0..7}
+    assert [orc.galois_elt_from_step(8, s) for s in (0, 1, -3, 2, -2, 3, -1)] == [15, 3, 3, 9, 9, 11, 11]
+    assert ref.galois_coeff(list(range(8)), 3, 17) == [0, 14, 6, 1, 13, 7, 2, 12]      # ApplyGalois, modulus 17
+    assert orc.Oracle(8, [q]).galois_table(3).tolist() == [4, 5, 7, 6, 1, 0, 2, 3]       # ApplyGaloisNTT: out[i] = in[table[i]]
