@@ -653,6 +653,24 @@ def run_gpu(args):
         "roofline": roofline,
     }
 
+    # ---- opt-in integer-MMA form of the fused inner sums (HEGPU_MATVEC_IMMA; experimental, NOT the headline: the north
+    # star keeps this path off the tensor cores): same bits as the default kernel, timed the same way
+    if dh and not args.no_imma:
+        OUT2 = ctx.ct(B, 2, c["L"] - 1)
+
+        def step_imma():
+            ctx.matvec_bsgs(OUT2, X, D, c["n1"], c["n2"], dh=True, imma=True)
+
+        for _ in range(3):
+            step_imma()
+        same = bool(np.array_equal(OUT2.download(), got))
+        ms_i = timed(step_imma, args.steps)
+        line["imma_mode"] = {"value": world * B * args.steps / (ms_i * 1e-3), "unit": "matvecs/s", "ms_per_step": ms_i / args.steps,
+                             "bit_identical_to_default": same,
+                             "what": "HEGPU_MATVEC_IMMA: the fused inner sums as exact 8-bit-limb integer matrix products on the warp-level integer MMA units "
+                                     "(mma.sync m16n8k32 u8), diagonals pre-multiplied with the baby-step keys once; opt-in, experimental, not the headline"}
+        del OUT2
+
     # ---- stand-alone transforms and rescale (N = 1 only)
     if world == 1 and not args.no_micro:
         line["ntt_micro"], line["rescale_micro"] = ntt_and_rescale_micro(torch, hg, ctx, stream, moduli, peak)
@@ -715,6 +733,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cfg5", action="store_true", help="skip the diagonal-sharded configs[4] sub-record")
     ap.add_argument("--no-micro", action="store_true", help="skip the stand-alone NTT / rescale records")
+    ap.add_argument("--no-imma", action="store_true", help="skip the opt-in integer-MMA sub-record")
     ap.add_argument("--cfg5-steps", type=int, default=3)
     ap.add_argument("--diag-ranks", type=int, default=0, help="configs[4]: ranks per diagonal group (default 2 when N >= 2)")
     ap.add_argument("--mode", default=CFG["mode"], choices=sorted(MODES))

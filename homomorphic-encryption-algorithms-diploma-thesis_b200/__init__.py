@@ -306,12 +306,12 @@ class Context:
 
     # ---- composites
     def matvec_bsgs(self, out, a, diags, n1: int, n2: int, rescale: bool = True, hoist: bool = False, lazy: bool | None = None,
-                    g_first: int = 0, dh: bool = False):
+                    g_first: int = 0, dh: bool = False, imma: bool = False):
         """hoist: HEGPU_MATVEC_HOIST (hoisted baby steps); lazy: HEGPU_MATVEC_LAZY (one mod-down for all giant
         steps; defaults to `hoist`); dh: HEGPU_MATVEC_DH (double-hoisted, diags uploaded with upload_pt_ext);
         g_first: first global giant step of a diagonal-sharded call."""
         lazy = hoist if lazy is None else lazy
-        flags = (1 if rescale else 0) | (2 if hoist else 0) | (4 if lazy else 0) | (8 if dh else 0)
+        flags = (1 if rescale else 0) | (2 if hoist else 0) | (4 if lazy else 0) | (8 if dh else 0) | (16 if imma else 0)
         _ck(lib().hegpu_matvec_bsgs_range(self._h, out._h, a._h, diags._h, n1, n2, g_first, flags))
 
     def bmatmul(self, out, this_cts, other_cts, n: int, p: int, case_b: bool):

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhegpu.so")
 SOURCES = ["hegpu.cu", "ntt_inst_plain_fwd.cu", "ntt_inst_plain_inv.cu", "ntt_inst_ks_intt.cu", "ntt_inst_ks_lift.cu",
            "ntt_inst_half_intt.cu", "ntt_inst_ks_moddown.cu", "ntt_inst_rescale.cu", "ntt_inst_final.cu"]
-HEADERS = ["modarith.cuh", "ntt.cuh", "kernels.cuh", "mac_kernels.cuh", "internal.cuh", "ntt_launch.cuh", os.path.join("..", "..", "include", "hegpu.h")]
+HEADERS = ["modarith.cuh", "ntt.cuh", "kernels.cuh", "mac_kernels.cuh", "imma_kernels.cuh", "internal.cuh", "ntt_launch.cuh", os.path.join("..", "..", "include", "hegpu.h")]
 OBJDIR = os.environ.get("HEGPU_OBJDIR", "/tmp/hegpu_obj")  # objects are scratch: only the linked .so lives in-tree
 NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",

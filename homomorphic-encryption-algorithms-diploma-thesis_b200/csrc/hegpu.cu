@@ -3,6 +3,7 @@
 // ciphertext data happens here; the host only builds constant tables and launches kernels.
 #include "ntt_launch.cuh"
 #include "mac_kernels.cuh"
+#include "imma_kernels.cuh"
 
 // ------------------------------------------------------------------------- errors
 static thread_local std::string g_err;
@@ -195,6 +196,8 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     if (const char *e = getenv("HEGPU_DH_FUSED")) c->dh_fused = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_F64")) c->dh_f64 = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_SWZ")) c->dh_swz = atoi(e) != 0;
+    if (const char *e = getenv("HEGPU_DH_IMMA")) c->dh_imma = atoi(e) != 0;
+    if (const char *e = getenv("HEGPU_IMMA_TX")) c->imma_tx = atoi(e) == 16 ? 16 : 8;
     if (const char *e = getenv("HEGPU_FUSE_FINAL")) c->fuse_final = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_PARK32K")) c->park32k = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -621,6 +624,7 @@ extern "C" int hegpu_load_galois_key(hegpu_ctx *c, uint32_t elt, const uint64_t 
     if (c->K < 2) LOGIC("keyswitching is not supported by the context");
     if (!(elt & 1) || elt >= 2 * c->n) INVALID("Galois element is not valid");
     TRY(set_device(c));
+    c->key_epoch++;
     u64 *&slot = c->galois_keys[elt];
     if (!slot) CU(cudaMalloc(&slot, key_words(c) * sizeof(u64)));
     CU(cudaMemcpyAsync(slot, host, key_words(c) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
@@ -897,6 +901,7 @@ extern "C" int hegpu_pt_destroy(hegpu_pt *t)
     cudaStreamSynchronize(t->ctx->stream);
     cudaFree(t->d);
     cudaFree(t->d_mont);
+    cudaFree(t->d_w);
     delete t;
     return HEGPU_OK;
 }
@@ -919,7 +924,10 @@ static int pt_io(hegpu_pt *t, u32 i0, u32 cnt, u64 *host, bool upload)
 {
     hegpu_ctx *c = t->ctx;
     TRY(set_device(c));
-    if (upload) t->mont_valid = false;
+    if (upload) {
+        t->mont_valid = false;
+        t->w_key.clear();
+    }
     const size_t row = (size_t)(t->L + (t->ext ? 1 : 0)) * c->n * sizeof(u64);
     u64 *d = t->d + i0 * t->stride();
     if (upload)
@@ -1613,9 +1621,51 @@ static int launch_dh_inner(hegpu_ctx *c, const DhInnerParams &P)
     return HEGPU_OK;
 }
 
+// HEGPU_MATVEC_IMMA: W = baby-step keys (.) diagonals as MMA B fragments, one block per launch group of 4 giant steps;
+// rebuilt only when the diagonals, the shape or the key set change
+static int pt_imma_w(hegpu_ctx *c, hegpu_pt *t, u32 n1, u32 n2, u32 g_first, u32 L, const std::vector<u32> &belt, const u32 **w, u32 *ksteps_out,
+                     size_t *group_words)
+{
+    const u32 ksteps = (n1 * (L + 1) + 31) / 32, groups = (n2 + 3) / 4;
+    const size_t gw = (size_t)(L + 1) * c->n * ksteps * IM_WL * 64, words = gw * groups;
+    std::vector<u64> key{ n1, n2, g_first, L, c->key_epoch };
+    for (u32 k = 1; k < n1; ++k) key.push_back(belt[k]);
+    if (t->w_key != key) {
+        if (t->w_words < words) {
+            cudaFree(t->d_w);
+            t->d_w = nullptr;
+            t->w_words = 0;
+            CU(cudaMalloc(&t->d_w, words * sizeof(u32)));
+            t->w_words = words;
+        }
+        for (u32 g = 0; g < groups; ++g) {
+            ImmaPrepParams P{};
+            for (u32 k = 1; k < n1; ++k) P.key[k] = c->galois_keys[belt[k]];
+            P.diag = t->d;
+            P.diag_si = t->stride();
+            P.w = t->d_w + g * gw;
+            P.n1 = n1;
+            P.L = L;
+            P.K = c->K;
+            P.n = c->n;
+            P.g0 = g * 4;
+            P.ng = std::min<u32>(4, n2 - g * 4);
+            P.ksteps = ksteps;
+            dh_imma_prep_kernel<<<c->sms * 8, 256, 0, c->stream>>>(P, c->d_mods);
+            c->launches++;
+            CU(cudaGetLastError());
+        }
+        t->w_key = key;
+    }
+    *w = t->d_w;
+    *ksteps_out = ksteps;
+    *group_words = gw;
+    return HEGPU_OK;
+}
+
 // hegpu_matvec_bsgs_range with HEGPU_MATVEC_DH (double-hoisted; oracle: orc_matvec_bsgs_dh)
 static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, u32 n1, u32 n2, u32 g_first,
-                          bool rescale, const std::vector<u32> &belt, const std::vector<u32> &gelt)
+                          bool rescale, const std::vector<u32> &belt, const std::vector<u32> &gelt, bool imma)
 {
     const u32 L = in->L, B = in->batch, first_rot = g_first == 0 ? 1u : 0u, nrot = n2 - first_rot;
     const size_t n = c->n, ctw = (size_t)2 * L * n, accw = (size_t)2 * (L + 1) * n;
@@ -1638,6 +1688,14 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
     TRY(arena_reserve(c, need(Bc) * NS));
     const u64 *dmont;
     TRY(pt_montgomery(const_cast<hegpu_pt *>(diags), &dmont));
+    imma = (imma || c->dh_imma) && fused && L == 3;  // the MMA form is built for the 3-limb level only
+    const u32 *imma_w = nullptr;
+    u32 imma_ksteps = 0;
+    size_t imma_gw = 0;
+    if (imma) {
+        TRY(pt_imma_w(c, const_cast<hegpu_pt *>(diags), n1, n2, g_first, L, belt, &imma_w, &imma_ksteps, &imma_gw));
+        if (dh_imma_smem(n1, (u32)c->imma_tx) > (size_t)224 * 1024) imma = false;
+    }
     SlotGuard guard{ c };
     if (NS > 1) {
         const size_t park_need = (size_t)nr1 * Bc * (L * L + 2 * L) * (n / 2);  // largest NTT launch of a chunk
@@ -1718,6 +1776,34 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
             const u64 words = (u64)Bn * ctw + (u64)Bn * L * (L + 1) * n + (u64)(n1 - 1) * 2 * L * (L + 1) * n +
                               (u64)n1 * n2 * (L + 1) * n + (u64)n2 * Bn * accw;
             Prof pf(c, PK_DH_INNER, (u64)Bn * (L + 1) * n, words * 8);
+            if (imma) {
+                ImmaParams Q{};
+                Q.in = vin;
+                Q.ext = ext;
+                Q.c0p = c0p;
+                for (u32 k = 1; k < n1; ++k) Q.perm[k] = P.perm[k];
+                Q.u = u;
+                Q.n1 = n1;
+                Q.B = Bn;
+                Q.L = L;
+                Q.K = c->K;
+                Q.n = c->n;
+                Q.ksteps = imma_ksteps;
+                const u32 tx = (u32)c->imma_tx;
+                const size_t smem = dh_imma_smem(n1, tx);
+                TRY(configure_smem(c, tx == 16 ? (const void *)dh_imma_kernel<3, 16> : (const void *)dh_imma_kernel<3, 8>, smem));
+                for (u32 g0 = 0; g0 < n2; g0 += 4) {
+                    Q.g0 = g0;
+                    Q.ng = std::min<u32>(4, n2 - g0);
+                    Q.w = imma_w + (size_t)(g0 / 4) * imma_gw;
+                    if (tx == 16)
+                        dh_imma_kernel<3, 16><<<(u32)(n / 16) * (L + 1), 512, smem, c->stream>>>(Q, c->d_mods);
+                    else
+                        dh_imma_kernel<3, 8><<<(u32)(n / 8) * (L + 1), 256, smem, c->stream>>>(Q, c->d_mods);
+                    c->launches++;
+                    CU(cudaGetLastError());
+                }
+            } else
 #define DH_CASE(LT, N2) case (LT) * 16 + (N2): TRY((launch_dh_inner<LT, N2>(c, P))); break;
             switch (L * 16 + dh_n2_pad(n2)) {
                 DH_CASE(1, 1) DH_CASE(1, 2) DH_CASE(1, 4)
@@ -1885,7 +1971,7 @@ extern "C" int hegpu_matvec_bsgs_range(hegpu_ctx *c, hegpu_ct *out, const hegpu_
         if (!c->galois_keys.count(gelt[g])) INVALID("Galois key not present");
     }
     if (dh) {
-        TRY(matvec_bsgs_dh(c, out, in, diags, n1, n2, g_first, rescale, belt, gelt));
+        TRY(matvec_bsgs_dh(c, out, in, diags, n1, n2, g_first, rescale, belt, gelt, (flags & HEGPU_MATVEC_IMMA) != 0));
         out->size = 2;
         out->L = rescale ? L - 1 : L;
         out->scale = rescale ? ns / (double)c->q[L - 1] : ns;

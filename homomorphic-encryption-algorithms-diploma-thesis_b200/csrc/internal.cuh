@@ -99,6 +99,9 @@ struct hegpu_ctx {
     u64 launches = 0;
     int sms = 148;
     int dh_f64 = 1;    // fused kernel: FP64-pipe arithmetic on the limbs whose modulus is below 2^40 (HEGPU_DH_F64=0: integer everywhere)
+    int dh_imma = 0;   // HEGPU_DH_IMMA=1: every double-hoisted matvec takes the integer-MMA inner sums (same as the HEGPU_MATVEC_IMMA flag)
+    int imma_tx = 8;   // coefficients per CTA of the integer-MMA kernel: 8 = two CTAs of 8 warps per SM (measured faster), HEGPU_IMMA_TX=16 = one CTA of 16 warps
+    u64 key_epoch = 0; // bumped whenever a Galois key is (re)loaded: invalidates pre-multiplied diagonals
     int dh_swz = 0;    // fused kernel: limb order rotated per wave of CTAs so that co-resident CTAs mix the two policies (HEGPU_DH_SWZ=1)
     int fuse_final = 1;  // double-hoisted matvec: final mod-down and rescale as one pass (HEGPU_FUSE_FINAL=0: two steps)
     int park32k = 1;     // N = 32768: one CTA per transform with the park scheme (HEGPU_PARK32K=0: two CTAs + finishing pass)
@@ -139,6 +142,11 @@ struct hegpu_pt {
     u64 *d_mont = nullptr;  // lazily built copy in Montgomery form (matvec diagonals)
     bool mont_valid = false;
     bool ext = false;       // limb L holds the residues mod the special prime (hegpu_pt_upload_ext)
+    // HEGPU_MATVEC_IMMA (opt-in): diagonals pre-multiplied with the baby-step keys, as 8-bit-limb MMA fragments; valid for
+    // one (n1, n2, g_first, L, key set) at a time
+    u32 *d_w = nullptr;
+    size_t w_words = 0;
+    std::vector<u64> w_key;
     size_t stride() const { return (size_t)L_cap * ctx->n; }
 };
 

@@ -184,6 +184,10 @@ int hegpu_pipe_peak(hegpu_ctx *ctx, int kind, double *ops_per_second);
 #define HEGPU_MATVEC_HOIST 2
 #define HEGPU_MATVEC_LAZY 4
 #define HEGPU_MATVEC_DH 8
+/* EXPERIMENTAL, opt-in (with HEGPU_MATVEC_DH, 3-limb level): the fused inner sums run as exact 8-bit-limb integer
+ * matrix products on the warp-level integer MMA units (diagonals pre-multiplied with the baby-step keys once per
+ * key set); same bits as without the flag.  Not the default: the north star keeps this path off the tensor cores. */
+#define HEGPU_MATVEC_IMMA 16
 int hegpu_matvec_bsgs(hegpu_ctx *ctx, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, uint32_t n1,
                       uint32_t n2, int flags);
 int hegpu_matvec_bsgs_range(hegpu_ctx *ctx, hegpu_ct *out, const hegpu_ct *in, const hegpu_pt *diags, uint32_t n1,

@@ -390,6 +390,36 @@ def test_matvec_double_hoisted_levels(hg, bits, L):
             assert np.max(np.abs(S.decrypt(got[i], out.scale).real[:dim] - M @ V[i])) < tol
 
 
+@pytest.mark.parametrize("n,bits,n1,n2,B,g_first", [(8192, (60, 40, 40, 60), 8, 2, 5, 0), (16384, (60, 40, 40, 60), 32, 4, 21, 0),
+                                                    (8192, (60, 40, 40, 60), 4, 6, 18, 0), (8192, (50, 50, 50, 60), 16, 3, 3, 2)])
+def test_matvec_dh_integer_mma_mode_is_bit_identical(hg, n, bits, n1, n2, B, g_first):
+    """HEGPU_MATVEC_IMMA (opt-in, experimental): the fused inner sums as 8-bit-limb integer matrix products on the
+    warp-level MMA units must return exactly the bits of the default (IMAD / FP64) kernel -- which the tests above pin to
+    the oracle -- for full and ragged ciphertext tiles, one and several k-steps, several launch groups of giant steps,
+    a sharded giant-step range, 40- and 50/60-bit limbs; a second call reuses the pre-multiplied diagonals."""
+    S = setup(n, bits)
+    ctx = make_ctx(hg, S)
+    rng = np.random.default_rng(77)
+    L, scale = 3, 2.0**40
+    cts = rand_residues(rng, S.moduli[:L], (B, 2), n)
+    ptsx = rand_residues(rng, S.moduli[:L] + [S.moduli[-1]], (n1 * n2,), n)
+    steps = list(range(1, n1)) + [g * n1 for g in range(max(g_first, 1), g_first + n2)]
+    ctx.load_galois_keys(S.gk(steps))
+    X, D = ctx.upload_ct(cts, scale), ctx.upload_pt_ext(ptsx, scale)
+    ref_out, out = ctx.ct(B, 2), ctx.ct(B, 2)
+    ctx.matvec_bsgs(ref_out, X, D, n1, n2, dh=True, g_first=g_first)
+    want = ref_out.download()
+    for _ in range(2):
+        ctx.matvec_bsgs(out, X, D, n1, n2, dh=True, g_first=g_first, imma=True)
+        assert np.array_equal(out.download(), want)
+    # new diagonals invalidate the cached products
+    ptsx2 = rand_residues(rng, S.moduli[:L] + [S.moduli[-1]], (n1 * n2,), n)
+    D.upload_ext(ptsx2, scale)
+    ctx.matvec_bsgs(ref_out, X, D, n1, n2, dh=True, g_first=g_first)
+    ctx.matvec_bsgs(out, X, D, n1, n2, dh=True, g_first=g_first, imma=True)
+    assert np.array_equal(out.download(), ref_out.download())
+
+
 def test_matvec_double_hoisted_two_execution_slots(hg):
     """Batches of 32 or more ciphertexts are split into chunks that run on two streams with separate
     scratch (and an uneven last chunk): every ciphertext must still match the oracle bit for bit, also
