@@ -156,25 +156,46 @@ __device__ __forceinline__ void dh_imma_body(const ImmaParams &P, const ModConst
     const u32 *wsrc = P.w + ((size_t)i * n + x0) * P.ksteps * IM_WL * 64;
     const u32 tiles = (P.B + IM_MT - 1) / IM_MT, steps = tiles * P.ksteps;
     __syncthreads();  // sperm
+    // shared-memory destinations of this thread's copies, as 32-bit shared addresses relative to the stage base: the XOR
+    // term of im_word depends on ct & 3 only, so four bases + compile-time ciphertext strides cover the 16 ciphertexts
+    const u32 dsh = (u32)__cvta_generic_to_shared(dbuf), wsh = (u32)__cvta_generic_to_shared(wbuf);
+    u32 dofs[4];
+#pragma unroll
+    for (u32 cc = 0; cc < 4; ++cc) dofs[cc] = dsh + im_word<TX>(cc, se, sxx) * 8;
+    u32 wofs[IM_WWORDS / 4 / IM_THREADS];
+    size_t wsofs[IM_WWORDS / 4 / IM_THREADS];
+#pragma unroll
+    for (u32 it = 0; it < IM_WWORDS / 4 / IM_THREADS; ++it) {
+        const u32 idx = tid + IM_THREADS * it, ww = idx / (IM_WL * 16), o = idx % (IM_WL * 16);
+        wofs[it] = wsh + (ww * IM_WL * 64 + o * 4) * 4;
+        wsofs[it] = (size_t)ww * P.ksteps * IM_WL * 64 + o * 4;
+    }
     auto issue = [&](u32 step, u32 ks, u32 b0) {
         const u32 st = step & 1u;
         const u32 k = (ks * 32 + se) / (L + 1);
         const bool ok = svalid && k < P.n1;
         const u32 off = ok ? sperm[k * IM_TX + sxx] : 0;
         const u64 *p = sbase + (size_t)b0 * sstride + off;
-        u64 *d = dbuf + (size_t)st * IM_DWORDS;
+        const u32 dst = st * (IM_DWORDS * 8);
+        if (ok && b0 + IM_MT <= P.B) {  // the common case: every ciphertext of the tile exists, plain 8-byte copies
 #pragma unroll
-        for (u32 ct = 0; ct < IM_MT; ++ct) {
-            const bool v = ok && b0 + ct < P.B;
-            cp_async8(d + im_word<TX>(ct, se, sxx), v ? p : sbase, v);
-            p += sstride;
-        }
-        u32 *wd = wbuf + (size_t)st * IM_WWORDS;
+            for (u32 ct = 0; ct < IM_MT; ++ct) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dofs[ct & 3u] + dst + (ct >> 2) * (4 * 32 * IM_TX * 8)), "l"(p));
+                p += sstride;
+            }
+        } else {
 #pragma unroll
-        for (u32 it = 0; it < IM_WWORDS / 4 / IM_THREADS; ++it) {
-            const u32 idx = tid + IM_THREADS * it, ww = idx / (IM_WL * 16), o = idx % (IM_WL * 16);
-            cp_async16(wd + (size_t)ww * IM_WL * 64 + o * 4, wsrc + ((size_t)ww * P.ksteps + ks) * IM_WL * 64 + o * 4);
+            for (u32 ct = 0; ct < IM_MT; ++ct) {
+                const bool v = ok && b0 + ct < P.B;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dofs[ct & 3u] + dst + (ct >> 2) * (4 * 32 * IM_TX * 8)),
+                             "l"(v ? p : sbase), "r"(v ? 8 : 0));  // src-size 0: zero fill
+                p += sstride;
+            }
         }
+        const u32 *ws = wsrc + (size_t)ks * IM_WL * 64;
+#pragma unroll
+        for (u32 it = 0; it < IM_WWORDS / 4 / IM_THREADS; ++it)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wofs[it] + st * (IM_WWORDS * 4)), "l"(ws + wsofs[it]));
         asm volatile("cp.async.commit_group;");
     };
     issue(0, 0, 0);
