@@ -1,4 +1,5 @@
 #!/bin/bash
+# NOTE: needs the HEGPU_IMMA_DBG switches of a throw-away debug build of imma_kernels.cuh (skip MMAs / gathers / epilogue / unpack); kept as the record of how profiles/r2u_imma_components.jsonl was made
 # component timing of the integer-MMA kernel (debug switches; results are wrong by construction, only the time matters)
 for dbg in 0 1 2 4 8 3 9 11 15; do
   HEGPU_IMMA_DBG=$dbg HEGPU_DH_IMMA=1 HEGPU_STREAMS=1 python - <<PY >> gpurun_out/r2u_imma_components.jsonl 2>&1
