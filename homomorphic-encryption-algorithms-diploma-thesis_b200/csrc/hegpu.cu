@@ -257,6 +257,7 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
         // bit 0: forward needs corrections; bit 1: inverse needs corrections; bit 2: FP64 butterflies
         m.big = (q >> 58 ? 1u : 0u) | (q >> 46 ? 2u : 0u) | ((q >> 43) == 0 && !getenv("HEGPU_NO_FP64") ? 4u : 0u);
         m.pad = 0;
+        m.q3 = q * 3;
         {   // -q^-1 mod 2^64 by Newton iteration; 2^64 mod q
             u64 inv = q;  // q*q = 1 mod 8
             for (int it = 0; it < 6; ++it) inv *= 2 - q * inv;
@@ -510,7 +511,10 @@ __global__ void __launch_bounds__(256) pipe_peak_kernel(u64 *__restrict__ out, u
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int s = rep % 3, lo_ = j & ((1 << s) - 1), k = ((j >> s) << (s + 1)) | lo_;
-                    ar.fwd_bfly(v[k], v[k | (1 << s)], W[(j + rep) & 3]);
+                    if (s < ArI64<true>::approx_stages(3))  // as in a radix-8 pass: the approximate quotient in two of three stages
+                        ar.fwd_bfly<true>(v[k], v[k | (1 << s)], W[(j + rep) & 3]);
+                    else
+                        ar.fwd_bfly<false>(v[k], v[k | (1 << s)], W[(j + rep) & 3]);
                 }
             }
         }
@@ -529,7 +533,7 @@ __global__ void __launch_bounds__(256) pipe_peak_kernel(u64 *__restrict__ out, u
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int s = rep % 3, lo_ = j & ((1 << s) - 1), k = ((j >> s) << (s + 1)) | lo_;
-                    ar.fwd_bfly(v[k], v[k | (1 << s)], W[(j + rep) & 3]);
+                    ar.fwd_bfly<false>(v[k], v[k | (1 << s)], W[(j + rep) & 3]);
                 }
             }
 #pragma unroll

@@ -563,14 +563,9 @@ __global__ void __launch_bounds__(256) ntt_inv_final_kernel(const Job job, const
         const ModConst m = T.mods[mi];
         const ulonglong2 wl = T.inv_last[mi];
         const u64 X = scratch[(size_t)jid * T.n + i], Y = scratch[(size_t)jid * T.n + halfn + i];
-        u64 Sm, D;
-        if (m.big & 2u) {
-            Sm = csub(X + Y, m.q << 1);
-            D = X + (m.q << 1) - Y;
-        } else {
-            Sm = X + Y;
-            D = X + (m.q << (LOGL + 1)) - Y;
-        }
+        // lazy ranges of ArI64::inv_bfly: [0, LZ q) (corrected per stage) or [0, LZ q * 2^LOGL) (sums left to double)
+        const u64 Sm = X + Y;
+        const u64 D = (m.big & 2u) ? X + (ArI64<true>::LZ == 3 ? m.q3 : m.q << 1) - Y : X + (m.q << (LOGL + 2)) - Y;
         job.store(jid, i, mul_shoup(Sm, m.ninv, m.ninv_sh, m.q), m);
         job.store(jid, i + halfn, mul_shoup(D, wl.x, wl.y, m.q), m);
     }

@@ -23,6 +23,7 @@ struct ModConst {
     u64 rmod;     // 2^64 mod q, and its Shoup quotient: x -> x*2^64 mod q (Montgomery form)
     u64 rmod_sh;
     u64 pmont;    // (special prime P mod q) * 2^64 mod q: x -> x*P mod q through one Montgomery reduction
+    u64 q3;       // 3q, loaded rather than computed: ptxas otherwise rebuilds it with an IMAD.WIDE + IMAD in every butterfly
 };
 
 __device__ __forceinline__ u64 csub(u64 v, u64 c) { return v >= c ? v - c : v; }
@@ -39,6 +40,42 @@ __device__ __forceinline__ u64 mul_shoup_lazy_nq(u64 x, u64 w, u64 wsh, u64 nq)
 {
     u64 h = __umul64hi(x, wsh);
     return x * w + h * nq;
+}
+
+// x * w mod q with an APPROXIMATE Shoup quotient, lazily in [0, 3q); any x < 2^64.  The quotient drops the lo x lo partial
+// product of x * wsh (h' = x1*s1 + floor((x0*s1 + x1*s0) / 2^32) is h or h - 1), which saves one of the four wide
+// multiplies of the high product; written as 32-bit carry chains so that ptxas emits 5 wide multiplies + 4 IMAD and the
+// additions stay on the ALU pipe (the C form of the exact product compiles to 6 IMAD.WIDE + 4 IMAD + ~1.5 IMAD.X/IADD/MOV
+// on the multiplier pipe that bounds the 60-bit transforms).  nq = 2^64 - q.
+__device__ __forceinline__ u64 mul_shoup_lazy3_nq(u64 x, u64 w, u64 wsh, u64 nq)
+{
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 x0, x1, w0, w1, s0, s1, n0, n1, m0, m1, m2, h0, h1, r0, r1;\n\t"
+        "mov.b64 {x0, x1}, %1;\n\t"
+        "mov.b64 {w0, w1}, %2;\n\t"
+        "mov.b64 {s0, s1}, %3;\n\t"
+        "mov.b64 {n0, n1}, %4;\n\t"
+        "mul.lo.u32     m0, x0, s1;\n\t"
+        "mul.hi.u32     m1, x0, s1;\n\t"
+        "mad.lo.cc.u32  m0, x1, s0, m0;\n\t"
+        "madc.hi.cc.u32 m1, x1, s0, m1;\n\t"
+        "addc.u32       m2, 0, 0;\n\t"
+        "mad.lo.cc.u32  h0, x1, s1, m1;\n\t"
+        "madc.hi.u32    h1, x1, s1, m2;\n\t"
+        "mul.lo.u32     r0, x0, w0;\n\t"
+        "mul.hi.u32     r1, x0, w0;\n\t"
+        "mad.lo.cc.u32  r0, h0, n0, r0;\n\t"
+        "madc.hi.u32    r1, h0, n0, r1;\n\t"
+        "mad.lo.u32     r1, x0, w1, r1;\n\t"
+        "mad.lo.u32     r1, x1, w0, r1;\n\t"
+        "mad.lo.u32     r1, h0, n1, r1;\n\t"
+        "mad.lo.u32     r1, h1, n0, r1;\n\t"
+        "mov.b64 %0, {r0, r1};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(x), "l"(w), "l"(wsh), "l"(nq));
+    return r;
 }
 
 // x mod q for any x < 2^64 (SEAL barrett_reduce_64)

@@ -108,6 +108,9 @@ struct PassMap {
 #define HEGPU_TWO52 4503599627370496.0
 #define HEGPU_MAGIC 6755399441055744.0 /* 1.5 * 2^52: rint() by addition for |x| < 2^51 */
 
+#ifndef HEGPU_SHOUP_APPROX
+#define HEGPU_SHOUP_APPROX 1  // 0: every butterfly uses the exact Shoup quotient (the round-1 form)
+#endif
 template <bool BIG>
 struct ArI64 {
     typedef u64 V;
@@ -115,15 +118,32 @@ struct ArI64 {
     const ModConst &m;
     const ulonglong2 wlast;
     const u64 nq;  // 2^64 - q
-    __device__ __forceinline__ ArI64(const ModConst &m_, ulonglong2 wl) : m(m_), wlast(wl), nq(0ull - m_.q) {}
+    const u64 q3;  // 3q: lazy bound of a product with the approximate quotient
+    __device__ __forceinline__ ArI64(const ModConst &m_, ulonglong2 wl) : m(m_), wlast(wl), nq(0ull - m_.q), q3(m_.q3) {}
     __device__ __forceinline__ V from_load(u64 v) const { return v; }
-    // forward: values < 8q at pass start (BIG), +2q per stage, < 16q < 2^64
+    // Forward lazy ranges.  BIG (q < 2^60, so 16q < 2^64): values < 8q at pass start, a stage adds 2q with the exact
+    // quotient (T < 2q) and 3q with the approximate one (T < 3q); a pass of S stages may use the approximate form in
+    // approx_stages(S) = min(S, 8 - 2S) of them and still end below 16q (radix-8 passes: two of three stages).
+    // !BIG (q < 2^58): < 3q at the start, 14 more stages of at most 3q stay below 45q < 2^64: always approximate.
+    static __host__ __device__ constexpr int approx_stages(int S)
+    {
+        if (!HEGPU_SHOUP_APPROX) return 0;
+        if (!BIG) return S;
+        return 8 - 2 * S < 0 ? 0 : (8 - 2 * S < S ? 8 - 2 * S : S);
+    }
     __device__ __forceinline__ V fwd_fix(V v) const { return BIG ? csub(v, m.q << 3) : v; }
+    template <bool APPROX>
     __device__ __forceinline__ void fwd_bfly(V &X, V &Y, const TW W) const
     {
-        const u64 T = mul_shoup_lazy_nq(Y, W.x, W.y, nq);
-        Y = X + (m.q << 1) - T;
-        X = X + T;
+        if constexpr (APPROX) {
+            const u64 T = mul_shoup_lazy3_nq(Y, W.x, W.y, nq);
+            Y = X + q3 - T;
+            X = X + T;
+        } else {
+            const u64 T = mul_shoup_lazy_nq(Y, W.x, W.y, nq);
+            Y = X + (m.q << 1) - T;
+            X = X + T;
+        }
     }
     __device__ __forceinline__ u64 fwd_final(V v) const
     {
@@ -135,36 +155,36 @@ struct ArI64 {
         }
         return barrett64(v, m);
     }
-    // inverse: BIG keeps [0,2q) with a correction per stage; !BIG lets the sums double
-    // (bound 2q * 2^gbit entering global stage gbit)
+    // Inverse lazy ranges: products come from the approximate quotient and lie in [0, LZ q), LZ = 3 (2 with the exact one).
+    // BIG keeps [0, LZ q) with a correction of the sum per stage; !BIG (q < 2^46) lets the sums double (bound
+    // LZ q * 2^gbit entering global stage gbit; the difference is offset by 4q * 2^gbit).
+    static constexpr int LZ = HEGPU_SHOUP_APPROX ? 3 : 2;
+    __device__ __forceinline__ u64 lzq() const { return HEGPU_SHOUP_APPROX ? q3 : m.q << 1; }
+    __device__ __forceinline__ u64 mul_lazy(u64 x, const TW W) const
+    {
+        return HEGPU_SHOUP_APPROX ? mul_shoup_lazy3_nq(x, W.x, W.y, nq) : mul_shoup_lazy_nq(x, W.x, W.y, nq);
+    }
     __device__ __forceinline__ V inv_fix(V v) const { return v; }
     template <int GBIT>
     __device__ __forceinline__ void inv_bfly(V &X, V &Y, const TW W) const
     {
-        const u64 q2 = m.q << 1;
         u64 Sm, D;
         if (BIG) {
-            Sm = csub(X + Y, q2);
-            D = X + q2 - Y;
+            Sm = csub(X + Y, lzq());
+            D = X + lzq() - Y;
         } else {
             Sm = X + Y;
-            D = X + (m.q << (GBIT + 1)) - Y;
+            D = X + (m.q << (GBIT + 2)) - Y;
         }
         X = Sm;
-        Y = mul_shoup_lazy_nq(D, W.x, W.y, nq);
+        Y = mul_lazy(D, W);
     }
     template <int GBIT>
     __device__ __forceinline__ void inv_bfly_last(V &X, V &Y) const
     {
-        const u64 q2 = m.q << 1;
-        u64 Sm, D;
-        if (BIG) {
-            Sm = csub(X + Y, q2);
-            D = X + q2 - Y;
-        } else {
-            Sm = X + Y;
-            D = X + (m.q << (GBIT + 1)) - Y;
-        }
+        // the exact products accept any 64-bit operand: the sum needs no correction here
+        const u64 Sm = X + Y;
+        const u64 D = BIG ? X + lzq() - Y : X + (m.q << (GBIT + 2)) - Y;
         X = mul_shoup(Sm, m.ninv, m.ninv_sh, m.q);
         Y = mul_shoup(D, wlast.x, wlast.y, m.q);
     }
@@ -200,6 +220,8 @@ struct ArF64 {
     }
     // forward: |T| <= 0.7q per stage, 16 stages from < 3q stay far below 2^48
     __device__ __forceinline__ V fwd_fix(V v) const { return v; }
+    static __host__ __device__ constexpr int approx_stages(int) { return 0; }
+    template <bool>
     __device__ __forceinline__ void fwd_bfly(V &X, V &Y, const TW W) const
     {
         const double T = mulmod(Y, W);
@@ -279,7 +301,7 @@ __device__ __forceinline__ void fwd_stages(typename A::V (&x)[1 << LOGE], u32 gb
 #pragma unroll
                 for (int lo = 0; lo < (1 << s); ++lo) {
                     const int k = (kh << S) | (hi << (s + 1)) | lo;
-                    ar.fwd_bfly(x[k], x[k | (1 << s)], W[hi]);
+                    ar.template fwd_bfly<(ss < A::approx_stages(S))>(x[k], x[k | (1 << s)], W[hi]);
                 }
             }
         }
