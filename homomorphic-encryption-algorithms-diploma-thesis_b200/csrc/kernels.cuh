@@ -331,6 +331,14 @@ struct PlainLoader {  // coefficient boff + i of job jid
     __device__ __forceinline__ Raw raw(u32 i) const { return job.load_raw(jid, boff + i); }
     __device__ __forceinline__ u64 fix(Raw r, u32) const { return job.load_fix(jid, r, m); }
 };
+// product of the stride-N/2 stage that the fold loaders compute while loading (canonical inputs): with the approximate
+// quotient the outputs are below 4q instead of 3q, which the range analysis of ArI64 covers (pass 0 has no correction and
+// ends below 4q + 8q)
+__device__ __forceinline__ u64 fold_mul(u64 y, const ulonglong2 W, const ModConst &m)
+{
+    return HEGPU_SHOUP_APPROX ? mul_shoup_lazy3_nq(y, W.x, W.y, 0ull - m.q) : mul_shoup_lazy(y, W.x, W.y, m.q);
+}
+__device__ __forceinline__ u64 fold_off(const ModConst &m) { return HEGPU_SHOUP_APPROX ? m.q3 : m.q << 1; }
 struct Pair64 {
     u64 x, y;
 };
@@ -349,8 +357,8 @@ struct FoldLoader {
     __device__ __forceinline__ u64 fix(Raw r, u32 i) const
     {
         const u64 X = job.load_fix(jid, r.x, m), Y = job.load_fix(jid, r.y, m);
-        const u64 Tm = mul_shoup_lazy(Y, W.x, W.y, m.q);
-        const u64 top = X + Tm, bot = X + (m.q << 1) - Tm;
+        const u64 Tm = fold_mul(Y, W, m);
+        const u64 top = X + Tm, bot = X + fold_off(m) - Tm;
         if (park) park[i] = h ? top : bot;
         return h ? bot : top;
     }
@@ -377,8 +385,8 @@ struct ParkFoldLoader {
     {
         if (half) return r.x;
         const u64 X = job.load_fix(jid, r.x, m), Y = job.load_fix(jid, r.y, m);
-        const u64 Tm = mul_shoup_lazy(Y, W.x, W.y, m.q);
-        park[i] = X + (m.q << 1) - Tm;
+        const u64 Tm = fold_mul(Y, W, m);
+        park[i] = X + fold_off(m) - Tm;
         return X + Tm;
     }
 };

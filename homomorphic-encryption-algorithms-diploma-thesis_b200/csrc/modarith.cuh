@@ -28,19 +28,44 @@ struct ModConst {
 
 __device__ __forceinline__ u64 csub(u64 v, u64 c) { return v >= c ? v - c : v; }
 
-// x * w mod q, lazily in [0, 2q); wsh = floor(w * 2^64 / q); any x < 2^64
-__device__ __forceinline__ u64 mul_shoup_lazy(u64 x, u64 w, u64 wsh, u64 q)
-{
-    u64 h = __umul64hi(x, wsh);
-    return x * w - h * q;
-}
-__device__ __forceinline__ u64 mul_shoup(u64 x, u64 w, u64 wsh, u64 q) { return csub(mul_shoup_lazy(x, w, wsh, q), q); }
-// same with nq = 2^64 - q precomputed: x*w + h*nq is one multiply-add chain (no negation of h*q)
+// x * w mod q, lazily in [0, 2q); wsh = floor(w * 2^64 / q); any x < 2^64; nq = 2^64 - q, so that x*w + h*nq is one
+// multiply-add chain (no negation of h*q).  Written as 32-bit carry chains: ptxas emits 4 IMAD.WIDE + 2 IMAD.HI + 4 IMAD
+// and keeps the additions on the ALU pipe; the C form (__umul64hi) compiles to 6 IMAD.WIDE + 4 IMAD plus ~1.5
+// IMAD.X / IMAD.IADD / IMAD.MOV per product on the multiplier pipe that bounds the 60-bit transforms
+// (tools/bfly_variants.cu: 33.6 instead of 35.6 multiplier-pipe cycles per butterfly).
 __device__ __forceinline__ u64 mul_shoup_lazy_nq(u64 x, u64 w, u64 wsh, u64 nq)
 {
-    u64 h = __umul64hi(x, wsh);
-    return x * w + h * nq;
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 x0, x1, w0, w1, s0, s1, n0, n1, c0, m0, m1, m2, h0, h1, r0, r1;\n\t"
+        "mov.b64 {x0, x1}, %1;\n\t"
+        "mov.b64 {w0, w1}, %2;\n\t"
+        "mov.b64 {s0, s1}, %3;\n\t"
+        "mov.b64 {n0, n1}, %4;\n\t"
+        "mul.hi.u32     c0, x0, s0;\n\t"
+        "mad.lo.cc.u32  m0, x0, s1, c0;\n\t"
+        "madc.hi.u32    m1, x0, s1, 0;\n\t"
+        "mad.lo.cc.u32  m0, x1, s0, m0;\n\t"
+        "madc.hi.cc.u32 m1, x1, s0, m1;\n\t"
+        "addc.u32       m2, 0, 0;\n\t"
+        "mad.lo.cc.u32  h0, x1, s1, m1;\n\t"
+        "madc.hi.u32    h1, x1, s1, m2;\n\t"
+        "mul.lo.u32     r0, x0, w0;\n\t"
+        "mul.hi.u32     r1, x0, w0;\n\t"
+        "mad.lo.cc.u32  r0, h0, n0, r0;\n\t"
+        "madc.hi.u32    r1, h0, n0, r1;\n\t"
+        "mad.lo.u32     r1, x0, w1, r1;\n\t"
+        "mad.lo.u32     r1, x1, w0, r1;\n\t"
+        "mad.lo.u32     r1, h0, n1, r1;\n\t"
+        "mad.lo.u32     r1, h1, n0, r1;\n\t"
+        "mov.b64 %0, {r0, r1};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(x), "l"(w), "l"(wsh), "l"(nq));
+    return r;
 }
+__device__ __forceinline__ u64 mul_shoup_lazy(u64 x, u64 w, u64 wsh, u64 q) { return mul_shoup_lazy_nq(x, w, wsh, 0ull - q); }
+__device__ __forceinline__ u64 mul_shoup(u64 x, u64 w, u64 wsh, u64 q) { return csub(mul_shoup_lazy(x, w, wsh, q), q); }
 
 // x * w mod q with an APPROXIMATE Shoup quotient, lazily in [0, 3q); any x < 2^64.  The quotient drops the lo x lo partial
 // product of x * wsh (h' = x1*s1 + floor((x0*s1 + x1*s0) / 2^32) is h or h - 1), which saves one of the four wide

@@ -124,7 +124,7 @@ struct ArI64 {
     // Forward lazy ranges.  BIG (q < 2^60, so 16q < 2^64): values < 8q at pass start, a stage adds 2q with the exact
     // quotient (T < 2q) and 3q with the approximate one (T < 3q); a pass of S stages may use the approximate form in
     // approx_stages(S) = min(S, 8 - 2S) of them and still end below 16q (radix-8 passes: two of three stages).
-    // !BIG (q < 2^58): < 3q at the start, 14 more stages of at most 3q stay below 45q < 2^64: always approximate.
+    // !BIG (q < 2^58): < 4q at the start (fold loaders), 14 more stages of at most 3q stay below 46q < 2^64: always approximate.
     static __host__ __device__ constexpr int approx_stages(int S)
     {
         if (!HEGPU_SHOUP_APPROX) return 0;
@@ -310,7 +310,7 @@ __device__ __forceinline__ void fwd_stages(typename A::V (&x)[1 << LOGE], u32 gb
 
 // full radix-16 passes of the forward transform, field position descending
 // Loader protocol: ld.raw(i) issues the global load(s) of coefficient i and returns them untouched
-// (type Loader::Raw); ld.fix(raw) is the arithmetic that turns them into a value < 3q.  Keeping
+// (type Loader::Raw); ld.fix(raw) is the arithmetic that turns them into a value < 4q.  Keeping
 // the two apart lets pass 0 issue the loads of register set it+1 before it computes set it
 // (Loader::PIPE; used where the extra registers do not spill: the plain transforms).
 template <int LOGL, int LOGE, int PASS, class A, class Load>
