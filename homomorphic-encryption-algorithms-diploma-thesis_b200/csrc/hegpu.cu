@@ -196,10 +196,11 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     if (const char *e = getenv("HEGPU_DH_FUSED")) c->dh_fused = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_F64")) c->dh_f64 = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_SWZ")) c->dh_swz = atoi(e) != 0;
+    if (const char *e = getenv("HEGPU_DH_STCS")) c->dh_stcs = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_IMMA")) c->dh_imma = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_IMMA_TX")) c->imma_tx = atoi(e) == 16 ? 16 : 8;
     if (const char *e = getenv("HEGPU_FUSE_FINAL")) c->fuse_final = atoi(e) != 0;
-    if (const char *e = getenv("HEGPU_PARK32K")) c->park32k = atoi(e) != 0;
+    if (const char *e = getenv("HEGPU_PARK32K")) c->park32k = atoi(e) < 0 ? 0 : atoi(e) > 2 ? 2 : atoi(e);
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->main_stream = c->stream;
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -1612,6 +1613,7 @@ static int launch_dh_inner(hegpu_ctx *c, const DhInnerParams &P)
     const size_t smem = dh_inner_smem(P.n1, N2, LT);
     auto kern = dh_inner_kernel<LT, N2>;
     DhInnerParams Q = P;
+    Q.stream_out = (u32)c->dh_stcs;
     TRY(configure_smem(c, (const void *)kern, smem));
     dim3 grid(P.n / DH_TX * (LT + 1), 1, (P.B + DH_BCH - 1) / DH_BCH);
     for (u32 g0 = 0; g0 < P.n2; g0 += N2) {
@@ -1702,7 +1704,8 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
     }
     SlotGuard guard{ c };
     if (NS > 1) {
-        const size_t park_need = (size_t)nr1 * Bc * (L * L + 2 * L) * (n / 2);  // largest NTT launch of a chunk
+        // largest NTT launch of a chunk (the two-level park of N = 32768 parks three quarters per job instead of one half)
+        const size_t park_need = (size_t)nr1 * Bc * (L * L + 2 * L) * ((c->logn == 15 && c->park32k == 2) ? 3 * (size_t)(n / 4) : n / 2);
         for (int sl = 0; sl < NS; ++sl) {
             select_slot(c, sl);
             if ((c->logn == 14 || (c->logn == 15 && c->park32k)) && c->use_park) TRY(park_reserve(c, park_need));

@@ -102,9 +102,11 @@ struct hegpu_ctx {
     int dh_imma = 0;   // HEGPU_DH_IMMA=1: every double-hoisted matvec takes the integer-MMA inner sums (same as the HEGPU_MATVEC_IMMA flag)
     int imma_tx = 8;   // coefficients per CTA of the integer-MMA kernel: 8 = two CTAs of 8 warps per SM (measured faster), HEGPU_IMMA_TX=16 = one CTA of 16 warps
     u64 key_epoch = 0; // bumped whenever a Galois key is (re)loaded: invalidates pre-multiplied diagonals
+    int dh_stcs = 1;   // fused kernel: evict-first stores of the inner sums (HEGPU_DH_STCS=0: plain stores)
     int dh_swz = 0;    // fused kernel: limb order rotated per wave of CTAs so that co-resident CTAs mix the two policies (HEGPU_DH_SWZ=1)
     int fuse_final = 1;  // double-hoisted matvec: final mod-down and rescale as one pass (HEGPU_FUSE_FINAL=0: two steps)
-    int park32k = 1;     // N = 32768: one CTA per transform with the park scheme (HEGPU_PARK32K=0: two CTAs + finishing pass)
+    int park32k = 2;     // N = 32768: 2 = two-level park (64 KiB CTAs, three per SM, the N = 16384 sub-transforms); HEGPU_PARK32K=1: one-level
+                         // park in 128 KiB (one CTA per SM); 0: two CTAs per transform + finishing pass
     int dh_fused = 1;  // double-hoisted matvec: fused baby-step + inner-sum kernel (HEGPU_DH_FUSED=0: unfused kernels)
     int loge = 3;  // NTT register-set size at N = 16384: 3 = radix-8 passes, 256 threads x 80 registers, 3 CTAs per SM (HEGPU_LOGE=4: radix-16, 2 CTAs)
     size_t ws_budget = (size_t)24 << 30;  // scratch budget per composite chunk

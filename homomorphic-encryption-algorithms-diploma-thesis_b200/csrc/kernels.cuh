@@ -558,6 +558,150 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
         inv_park_body<LOGL, LOGE>(job, jid, m, ArI64<false>(m, T.inv_last[mi]), tw, T.n, pk, sm);
 }
 
+// ---------------------------------------------------------------------------------------
+// Two-level park kernels: N = 2^(LOGL+2) (N = 32768 at LOGL = 13) transformed by ONE CTA in 2^LOGL words of shared
+// memory, so that N = 32768 runs the very same 64 KiB / 256-thread / three-CTAs-per-SM sub-transforms as N = 16384
+// (the one-level form needs 128 KiB and leaves one CTA per SM, whose load, exchange and store phases cannot overlap).
+// Forward: the stride-N/2 and stride-N/4 stages (a radix-4 butterfly on x[i], x[i+N/4], x[i+N/2], x[i+3N/4]) are
+// computed while loading quarter 0; the other three outputs are parked ([jobs][3][N/4] words, written and re-read by
+// the same thread) and transformed as quarters 1..3.  Inverse: quarters 0..2 are transformed and parked, quarter 3 is
+// transformed and its last-pass registers are combined with the parked quarters in the final two stages.
+// ---------------------------------------------------------------------------------------
+struct Quad64 {
+    u64 a, b, c, d;
+};
+template <class Job, int LOGL>
+struct Park4FoldLoader {
+    typedef Quad64 Raw;
+    static constexpr bool PIPE = false;
+    const Job &job;
+    const ModConst &m;
+    u32 jid, quarter;
+    ulonglong2 W1, W2, W3;  // twiddles of the first stage (index 1) and of the second (indices 2, 3)
+    u64 *park;              // [3][2^LOGL]
+    __device__ __forceinline__ Raw raw(u32 i) const
+    {
+        constexpr u32 Q = 1u << LOGL;
+        if (quarter) return Quad64{ park[(quarter - 1) * Q + i], 0, 0, 0 };
+        return Quad64{ job.load_raw(jid, i), job.load_raw(jid, i + Q), job.load_raw(jid, i + 2 * Q), job.load_raw(jid, i + 3 * Q) };
+    }
+    // canonical inputs; outputs below 7q with the approximate quotient (q -> 4q -> 7q), 5q with the exact one: pass 0 of
+    // the sub-transform has no correction and ends below 7q + 8q < 16q
+    __device__ __forceinline__ u64 fix(Raw r, u32 i) const
+    {
+        constexpr u32 Q = 1u << LOGL;
+        if (quarter) return r.a;
+        const u64 a = job.load_fix(jid, r.a, m), b = job.load_fix(jid, r.b, m), c = job.load_fix(jid, r.c, m), d = job.load_fix(jid, r.d, m);
+        const u64 off = fold_off(m);
+        u64 T = fold_mul(c, W1, m);
+        const u64 a1 = a + T, c1 = a + off - T;
+        T = fold_mul(d, W1, m);
+        const u64 b1 = b + T, d1 = b + off - T;
+        T = fold_mul(b1, W2, m);
+        park[i] = a1 + off - T;
+        const u64 a2 = a1 + T;
+        T = fold_mul(d1, W3, m);
+        park[Q + i] = c1 + T;
+        park[2 * Q + i] = c1 + off - T;
+        return a2;
+    }
+};
+
+template <int LOGL, int LOGE, class Job>
+__global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::MINB)
+    ntt_fwd_park4_kernel(const Job job, const NttTables T, u64 *__restrict__ park)
+{
+    extern __shared__ __align__(16) u64 sm[];
+    const u32 jid = blockIdx.x;
+    const u32 mi = job.mod(jid);
+    const ModConst m = T.mods[mi];
+    const ulonglong2 *tw = T.fwd + (size_t)mi * T.n;
+    u64 *pk = park + (size_t)jid * (3u << LOGL);
+    Park4FoldLoader<Job, LOGL> load{ job, m, jid, 0, __ldg(tw + 1), __ldg(tw + 2), __ldg(tw + 3), pk };
+    u32 boff = 0;  // block offset of the quarter being transformed
+    auto fetch = [&](u32 i) { return job.fetch(jid, boff + i, m); };
+    auto store = [&](u32 i, u64 v, const typename Job::Ops &o) { job.store(jid, boff + i, v, m, o); };
+    const ulonglong2 nowl = make_ulonglong2(0, 0);
+    if (m.big & 4u) {
+        const ArF64 ar(T.modsd[mi]);
+        const double *twd = T.fwd_d + (size_t)mi * T.n;
+#pragma unroll 1
+        for (u32 h = 0; h < 4; ++h) {
+            load.quarter = h;
+            boff = h << LOGL;
+            ntt_fwd_cta<LOGL, LOGE>(load, fetch, store, twd, T.n + boff, ar, sm);
+            __syncthreads();
+        }
+    } else if (m.big & 1u) {
+        const ArI64<true> ar(m, nowl);
+#pragma unroll 1
+        for (u32 h = 0; h < 4; ++h) {
+            load.quarter = h;
+            boff = h << LOGL;
+            ntt_fwd_cta<LOGL, LOGE>(load, fetch, store, tw, T.n + boff, ar, sm);
+            __syncthreads();
+        }
+    } else {
+        const ArI64<false> ar(m, nowl);
+#pragma unroll 1
+        for (u32 h = 0; h < 4; ++h) {
+            load.quarter = h;
+            boff = h << LOGL;
+            ntt_fwd_cta<LOGL, LOGE>(load, fetch, store, tw, T.n + boff, ar, sm);
+            __syncthreads();
+        }
+    }
+}
+
+template <int LOGL, int LOGE, class A, class TWP, class Job>
+__device__ __forceinline__ void inv_park4_body(const Job &job, u32 jid, const ModConst &m, const A &ar, const TWP tw, u32 n,
+                                               typename A::V *pk, u64 *sm)
+{
+    constexpr u32 Q = 1u << LOGL;
+    PlainLoader<Job> load{ job, m, jid, 0 };
+    u32 h = 0;
+    const typename A::TW W2 = __ldg(tw + 2), W3 = __ldg(tw + 3);  // stage LOGL: quarters (0,1) and (2,3)
+    auto store = [&](u32 i, typename A::V y) {
+        if (h < 3) {
+            pk[h * Q + i] = y;
+            return;
+        }
+        typename A::V x0 = pk[i], x1 = pk[Q + i], x2 = pk[2 * Q + i];
+        ar.template inv_bfly<LOGL>(x0, x1, W2);
+        ar.template inv_bfly<LOGL>(x2, y, W3);
+        ar.template inv_bfly_last<LOGL + 1>(x0, x2);
+        ar.template inv_bfly_last<LOGL + 1>(x1, y);
+        job.store(jid, i, ar.inv_final(x0), m);
+        job.store(jid, Q + i, ar.inv_final(x1), m);
+        job.store(jid, 2 * Q + i, ar.inv_final(x2), m);
+        job.store(jid, 3 * Q + i, ar.inv_final(y), m);
+    };
+#pragma unroll 1
+    for (h = 0; h < 4; ++h) {
+        load.boff = h << LOGL;
+        ntt_inv_cta<LOGL, LOGE, -1>(load, store, tw, n + (h << LOGL), ar, sm);
+        __syncthreads();
+    }
+}
+
+template <int LOGL, int LOGE, class Job>
+__global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::MINB)
+    ntt_inv_park4_kernel(const Job job, const NttTables T, u64 *__restrict__ park)
+{
+    extern __shared__ __align__(16) u64 sm[];
+    const u32 jid = blockIdx.x;
+    const u32 mi = job.mod(jid);
+    const ModConst m = T.mods[mi];
+    const ulonglong2 *tw = T.inv + (size_t)mi * T.n;
+    u64 *pk = park + (size_t)jid * (3u << LOGL);
+    if (m.big & 4u)
+        inv_park4_body<LOGL, LOGE>(job, jid, m, ArF64(T.modsd[mi]), T.inv_d + (size_t)mi * T.n, T.n, reinterpret_cast<double *>(pk), sm);
+    else if (m.big & 2u)
+        inv_park4_body<LOGL, LOGE>(job, jid, m, ArI64<true>(m, T.inv_last[mi]), tw, T.n, pk, sm);
+    else
+        inv_park4_body<LOGL, LOGE>(job, jid, m, ArI64<false>(m, T.inv_last[mi]), tw, T.n, pk, sm);
+}
+
 // last (stride N/2) INTT stage for N = 2^(LOGL+1), element-wise over scratch
 template <int LOGL, class Job>
 __global__ void __launch_bounds__(256) ntt_inv_final_kernel(const Job job, const NttTables T, const u64 *__restrict__ scratch,

@@ -372,6 +372,8 @@ struct DhInnerParams {
     u64 *u;                // [n2][B][2][L+1][N]
     u32 n1, n2, B, L, K, n;
     u32 g0, ng;            // this launch accumulates giant steps g0 .. g0+ng-1 (ng <= N2)
+    u32 stream_out;        // inner sums leave with evict-first stores (st.global.cs): they are > 1 GB per launch, are not read again
+                           // by this kernel and would otherwise push the lifted digits that every CTA re-gathers out of L2
 };
 static inline size_t dh_inner_smem(u32 n1, u32 n2, u32 L)
 {
@@ -544,8 +546,14 @@ __device__ __forceinline__ void dh_inner_body(const DhInnerParams &P, const ModC
         for (int g = 0; g < N2; ++g) {
             if ((u32)g < P.ng) {
                 u64 *up = P.u + ((((size_t)(P.g0 + g) * P.B + b) * 2) * (L + 1) + i) * n + x0 + lane;
-                up[0] = Ar::reduce_wide(acc[g][0], m);
-                up[(size_t)(L + 1) * n] = Ar::reduce_wide(acc[g][1], m);
+                const u64 r0 = Ar::reduce_wide(acc[g][0], m), r1 = Ar::reduce_wide(acc[g][1], m);
+                if (P.stream_out) {
+                    __stcs(up, r0);
+                    __stcs(up + (size_t)(L + 1) * n, r1);
+                } else {
+                    up[0] = r0;
+                    up[(size_t)(L + 1) * n] = r1;
+                }
             }
         }
     }

@@ -40,6 +40,32 @@ int launch_inv_park(hegpu_ctx *c, const Job &job, u32 jobs, int kind)
     return HEGPU_OK;
 }
 
+// two-level park (N = 4 * 2^LOGL): three parked quarters per job
+template <int LOGL, int LOGE, class Job>
+int launch_fwd_park4(hegpu_ctx *c, const Job &job, u32 jobs, int kind, u64 words_per_job)
+{
+    TRY(park_reserve(c, (size_t)jobs * (3u << LOGL)));
+    Prof pf(c, kind, jobs, (u64)jobs * words_per_job * 8 * c->n);
+    auto kern = ntt_fwd_park4_kernel<LOGL, LOGE, Job>;
+    TRY(configure_smem(c, (const void *)kern, NttShape<LOGL, LOGE>::SMEM));
+    kern<<<jobs, NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::SMEM, c->stream>>>(job, c->tabs, c->park);
+    c->launches++;
+    CU(cudaGetLastError());
+    return HEGPU_OK;
+}
+template <int LOGL, int LOGE, class Job>
+int launch_inv_park4(hegpu_ctx *c, const Job &job, u32 jobs, int kind)
+{
+    TRY(park_reserve(c, (size_t)jobs * (3u << LOGL)));
+    Prof pf(c, kind, jobs, (u64)jobs * 16 * c->n);
+    auto kern = ntt_inv_park4_kernel<LOGL, LOGE, Job>;
+    TRY(configure_smem(c, (const void *)kern, NttShape<LOGL, LOGE>::SMEM));
+    kern<<<jobs, NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, LOGE>::SMEM, c->stream>>>(job, c->tabs, c->park);
+    c->launches++;
+    CU(cudaGetLastError());
+    return HEGPU_OK;
+}
+
 // words_per_job: algorithmic HBM words per coefficient of one job (2 = read + write)
 template <class Job>
 int launch_ntt_fwd(hegpu_ctx *c, const Job &job, u32 jobs, int kind, u64 words_per_job)
@@ -54,6 +80,7 @@ int launch_ntt_fwd(hegpu_ctx *c, const Job &job, u32 jobs, int kind, u64 words_p
                                 : launch_fwd_park<13, 4>(c, job, jobs, kind, words_per_job);
         return launch_fwd_shape<14, 0, 4>(c, job, jobs, kind, words_per_job);
     case 15:
+        if (c->use_park && c->park32k == 2) return launch_fwd_park4<13, 3>(c, job, jobs, kind, words_per_job);
         if (c->use_park && c->park32k) return launch_fwd_park<14, 4>(c, job, jobs, kind, words_per_job);
         return launch_fwd_shape<14, 1, 4>(c, job, jobs, kind, words_per_job);
     }
@@ -90,6 +117,7 @@ int launch_ntt_inv(hegpu_ctx *c, const Job &job, u32 jobs, u64 *scratch, int kin
             return c->loge == 3 ? launch_inv_park<13, 3>(c, job, jobs, kind) : launch_inv_park<13, 4>(c, job, jobs, kind);
         return launch_inv_shape<14, 0, 4>(c, job, jobs, scratch, kind);
     case 15:
+        if (c->use_park && c->park32k == 2) return launch_inv_park4<13, 3>(c, job, jobs, kind);
         if (c->use_park && c->park32k) return launch_inv_park<14, 4>(c, job, jobs, kind);
         return launch_inv_shape<14, 1, 4>(c, job, jobs, scratch, kind);
     }
