@@ -197,6 +197,7 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     if (const char *e = getenv("HEGPU_DH_F64")) c->dh_f64 = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_SWZ")) c->dh_swz = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_STCS")) c->dh_stcs = atoi(e) != 0;
+    if (const char *e = getenv("HEGPU_LIMB_MAJOR")) c->limb_major = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_IMMA")) c->dh_imma = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_IMMA_TX")) c->imma_tx = atoi(e) == 16 ? 16 : 8;
     if (const char *e = getenv("HEGPU_FUSE_FINAL")) c->fuse_final = atoi(e) != 0;
@@ -1384,13 +1385,13 @@ static int ks_moddown(hegpu_ctx *c, KsPlan &pl)
     if (P.only_c1) {  // component 1 of every element: t is [E][N]
         HalfInttJob j4{ P.acc + (size_t)(2 * L + 1) * c->n, P.t, (size_t)2 * (L + 1) * c->n, 0, 1, c->K - 1, c->n, 0 };
         TRY(launch_ntt_inv(c, j4, (u32)pl.E, pl.scr, PK_HALF_INTT));
-        KsModDownJob j5{ P, c->d_md + (size_t)(c->K - 1) * c->K, c->d_mods };
+        KsModDownJob j5{ P, c->d_md + (size_t)(c->K - 1) * c->K, c->d_mods, c->limb_major ? (u32)pl.E : 0u };
         TRY(launch_ntt_fwd(c, j5, (u32)(pl.E * L), PK_KS_MODDOWN_NTT, 3));
         return HEGPU_OK;
     }
     HalfInttJob j4{ P.acc + (size_t)L * c->n, P.t, (size_t)(L + 1) * c->n, 0, 1, c->K - 1, c->n, 0 };
     TRY(launch_ntt_inv(c, j4, (u32)(pl.E * 2), pl.scr, PK_HALF_INTT));
-    KsModDownJob j5{ P, c->d_md + (size_t)(c->K - 1) * c->K, c->d_mods };
+    KsModDownJob j5{ P, c->d_md + (size_t)(c->K - 1) * c->K, c->d_mods, c->limb_major ? (u32)(pl.E * 2) : 0u };
     TRY(launch_ntt_fwd(c, j5, (u32)(pl.E * 2 * L), PK_KS_MODDOWN_NTT, P.has_base1 ? 4 : 3));
     return HEGPU_OK;
 }
@@ -1418,6 +1419,7 @@ static int ks_moddown_rescale(hegpu_ctx *c, KsPlan &pl, CtView out, u64 *t2)
     F.n = c->n;
     F.has_base0 = P.no_base0 ? 0u : 1u;
     F.has_base1 = P.has_base1;
+    F.per = c->limb_major ? B * 2 : 0u;
     FinalInttJob ji{ F };
     TRY(launch_ntt_inv(c, ji, B * 2, pl.scr, PK_HALF_INTT));
     FinalNttJob jn{ F };

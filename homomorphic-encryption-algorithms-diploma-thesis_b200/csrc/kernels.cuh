@@ -40,19 +40,39 @@ __device__ __forceinline__ u64 rebase(u64 v, u64 from, const ModConst &m)
     return (from >> 1) < m.q ? csub(v, m.q) : barrett64(v, m);
 }
 
+// Every resolver splits its work in two: resolve(j) runs ONCE per CTA and turns the job id into row pointers and the
+// constants of the limb (type R; the kernels keep it in shared memory when it is large), the per-coefficient functions
+// only index those rows.  In the first form every per-coefficient call redid the index arithmetic (integer divisions,
+// 64-bit stride products, key / constant table look-ups): ptxas did not hoist it out of the unrolled passes under the
+// 80-register budget -- the loader and epilogue passes of the mod-down transform were 1300-1600 instructions per
+// iteration next to 340 for a plain radix-8 pass, with 9-14 division sequences each, and stall_no_instruction was its
+// second largest stall (160-190 KB of code per kernel).
+//   u32  mod(j)                         modulus index of job j
+//   R    resolve(j)                     rows + constants of job j
+//   u64  load_raw(r, i, m)              memory only (input coefficient i)
+//   u64  load_fix(r, v, m)              arithmetic only (-> value below q, or below 16 q for lazy inputs)
+//   inverse jobs:  void store(r, i, x, m)
+//   forward jobs:  Ops fetch(r, i, m);  void store(r, i, x, m, ops)     (epilogue operands fetched before the last stages)
+
 // plain transform of `count` limb polynomials [count][N] (measurement API, host tooling)
 struct PlainJob {
     static constexpr bool PIPE = true;  // software-pipelined first-pass loads (no epilogue operands -> no spills)
+    static constexpr bool R_SMEM = false;
     const u64 *src;
     u64 *dst;
     u32 first_mod, n_mods, n;
+    struct R {
+        const u64 *src;
+        u64 *dst;
+    };
     __device__ __forceinline__ u32 mod(u32 j) const { return first_mod + j % n_mods; }
-    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const { return src[(size_t)j * n + i]; }
-    __device__ __forceinline__ u64 load_fix(u32, u64 v, const ModConst &) const { return v; }
-    __device__ __forceinline__ void store(u32 j, u32 i, u64 v, const ModConst &) const { dst[(size_t)j * n + i] = v; }
+    __device__ __forceinline__ R resolve(u32 j) const { return R{ src + (size_t)j * n, dst + (size_t)j * n }; }
+    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return r.src[i]; }
+    __device__ __forceinline__ u64 load_fix(const R &, u64 v, const ModConst &) const { return v; }
+    __device__ __forceinline__ void store(const R &r, u32 i, u64 v, const ModConst &) const { r.dst[i] = v; }
     struct Ops {};
-    __device__ __forceinline__ Ops fetch(u32, u32, const ModConst &) const { return Ops{}; }
-    __device__ __forceinline__ void store(u32 j, u32 i, u64 v, const ModConst &m, const Ops &) const { store(j, i, v, m); }
+    __device__ __forceinline__ Ops fetch(const R &, u32, const ModConst &) const { return Ops{}; }
+    __device__ __forceinline__ void store(const R &r, u32 i, u64 v, const ModConst &m, const Ops &) const { store(r, i, v, m); }
 };
 
 // key-switch launch parameters (one launch handles ngroups rotations/relinearisations of
@@ -82,25 +102,36 @@ struct KsParams {
 // K7 step 1: c_j = INTT_{q_j}( pi(target)[j] )
 struct KsInttJob {
     static constexpr bool PIPE = false;
+    static constexpr bool R_SMEM = true;
     KsParams P;
+    struct R {
+        const u64 *row;  // limb l of the target polynomial
+        const u32 *pm;   // Galois gather table or null
+        u64 *dst;
+    };
     __device__ __forceinline__ u32 mod(u32 j) const { return j % P.L; }
-    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const
+    __device__ __forceinline__ R resolve(u32 j) const
     {
         const u32 e = j / P.L, l = j % P.L, g = e / P.B, b = e % P.B;
         const CtView &v = P.in[g];
-        const u32 *pm = P.hoisted ? nullptr : P.perm[g];
-        const u32 src = pm ? __ldg(pm + i) : i;
-        return v.p[b * v.sb + P.target_poly * v.sp + l * v.sl + src];
+        return R{ v.p + b * v.sb + P.target_poly * v.sp + l * v.sl, P.hoisted ? nullptr : P.perm[g], P.coef + (size_t)j * P.n };
     }
-    __device__ __forceinline__ u64 load_fix(u32, u64 v, const ModConst &) const { return v; }
-    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &) const { P.coef[(size_t)j * P.n + i] = x; }
+    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return r.row[r.pm ? __ldg(r.pm + i) : i]; }
+    __device__ __forceinline__ u64 load_fix(const R &, u64 v, const ModConst &) const { return v; }
+    __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &) const { r.dst[i] = x; }
 };
 
 // K7 step 2: ext[e][j][i] = NTT_{m_i}( c_j mod m_i ), i != j, i in [0, L]
 struct KsLiftJob {
     static constexpr bool PIPE = false;
+    static constexpr bool R_SMEM = true;
     KsParams P;
     const ModConst *mods;
+    struct R {
+        const u64 *src;
+        u64 *dst;
+        u64 from_q;  // modulus of the digit
+    };
     __device__ __forceinline__ void split(u32 j, u32 &e, u32 &dj, u32 &di) const
     {
         const u32 LL = P.L * P.L;
@@ -116,126 +147,152 @@ struct KsLiftJob {
         split(j, e, dj, di);
         return di == P.L ? P.K - 1 : di;
     }
-    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const
+    __device__ __forceinline__ R resolve(u32 j) const
     {
         u32 e, dj, di;
         split(j, e, dj, di);
-        return P.coef[((size_t)e * P.L + dj) * P.n + i];
+        return R{ P.coef + ((size_t)e * P.L + dj) * P.n, P.ext + (((size_t)e * P.L + dj) * (P.L + 1) + di) * P.n, mods[dj].q };
     }
-    __device__ __forceinline__ u64 load_fix(u32 j, u64 v, const ModConst &m) const
-    {
-        u32 e, dj, di;
-        split(j, e, dj, di);
-        return rebase(v, mods[dj].q, m);
-    }
-    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &) const
-    {
-        u32 e, dj, di;
-        split(j, e, dj, di);
-        P.ext[(((size_t)e * P.L + dj) * (P.L + 1) + di) * P.n + i] = x;
-    }
+    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return r.src[i]; }
+    __device__ __forceinline__ u64 load_fix(const R &r, u64 v, const ModConst &m) const { return rebase(v, r.from_q, m); }
     struct Ops {};
-    __device__ __forceinline__ Ops fetch(u32, u32, const ModConst &) const { return Ops{}; }
-    __device__ __forceinline__ void store(u32 j, u32 i, u64 v, const ModConst &m, const Ops &) const { store(j, i, v, m); }
+    __device__ __forceinline__ Ops fetch(const R &, u32, const ModConst &) const { return Ops{}; }
+    __device__ __forceinline__ void store(const R &r, u32 i, u64 v, const ModConst &, const Ops &) const { r.dst[i] = v; }
 };
 
 // INTT of a dropped limb with the rounding offset added: t = (INTT_d(src) + floor(d/2)) mod d.
 // Used by K7 step 4 (d = special prime) and by rescale (d = q_{L-1}).
 struct HalfInttJob {
     static constexpr bool PIPE = false;
+    static constexpr bool R_SMEM = false;
     const u64 *src;  // job j at src + (j / inner) * s_outer + (j % inner) * s_inner
     u64 *dst;        // [jobs][N]
     size_t s_outer, s_inner;
     u32 inner, drop_mod, n;
     u32 lazy_in;  // the words are sums of up to 16 canonical residues (multi-GPU partial sums): reduce while loading
+    struct R {
+        const u64 *src;
+        u64 *dst;
+    };
     __device__ __forceinline__ u32 mod(u32) const { return drop_mod; }
-    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const { return src[(j / inner) * s_outer + (j % inner) * s_inner + i]; }
-    __device__ __forceinline__ u64 load_fix(u32, u64 v, const ModConst &m) const { return lazy_in ? barrett64(v, m) : v; }
-    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m) const
-    {
-        dst[(size_t)j * n + i] = addmod(x, m.q >> 1, m.q);
-    }
+    __device__ __forceinline__ R resolve(u32 j) const { return R{ src + (j / inner) * s_outer + (j % inner) * s_inner, dst + (size_t)j * n }; }
+    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return r.src[i]; }
+    __device__ __forceinline__ u64 load_fix(const R &, u64 v, const ModConst &m) const { return lazy_in ? barrett64(v, m) : v; }
+    __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &m) const { r.dst[i] = addmod(x, m.q >> 1, m.q); }
 };
 
 // K7 step 5: out[c][i] = base_c[i] + (acc[c][i] - NTT_{q_i}((t_c mod q_i) - half)) * P^-1
 struct KsModDownJob {
     static constexpr bool PIPE = false;
+    static constexpr bool R_SMEM = true;
     KsParams P;
     const MdConst *md;  // [K] constants of the dropped modulus (special prime) per target limb
     const ModConst *mods;
-    __device__ __forceinline__ void split(u32 j, u32 &e, u32 &c, u32 &l) const
+    u32 per;  // != 0: jobs in limb-major order, per = jobs per limb (the CTAs that share an SM then run one arithmetic
+              // policy, i.e. one third of the kernel's code); 0: limbs interleaved over neighbouring CTAs
+    struct R {
+        const u64 *t, *acc, *base;  // base: null when nothing is added after the mod-down
+        const u32 *pm;              // Galois gather of the base (component 0) or null
+        u64 *out;
+        u64 from_q, halfmod, inv, inv_sh;
+    };
+    // job -> (r = polynomial index: e*2 + c, or e when only_c1; l = target limb)
+    __device__ __forceinline__ void rl(u32 j, u32 &r, u32 &l) const
     {
-        l = j % P.L;
-        c = P.only_c1 ? 1u : (j / P.L) & 1u;
-        e = P.only_c1 ? j / P.L : j / (2 * P.L);
+        if (per) {
+            l = j / per;
+            r = j % per;
+        } else {
+            l = j % P.L;
+            r = j / P.L;
+        }
     }
-    __device__ __forceinline__ u32 mod(u32 j) const { return j % P.L; }
-    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const { return P.t[(size_t)(j / P.L) * P.n + i]; }
-    __device__ __forceinline__ u64 load_fix(u32 j, u64 v, const ModConst &m) const
+    __device__ __forceinline__ u32 mod(u32 j) const
     {
-        return submod(rebase(v, mods[P.K - 1].q, m), md[j % P.L].halfmod, m.q);
+        u32 r, l;
+        rl(j, r, l);
+        return l;
     }
+    __device__ __forceinline__ R resolve(u32 j) const
+    {
+        u32 rr, l;
+        rl(j, rr, l);
+        const u32 c = P.only_c1 ? 1u : rr & 1u, e = P.only_c1 ? rr : rr >> 1;
+        const u32 g = e / P.B, b = e % P.B;
+        const CtView &vi = P.in[g], &vo = P.out[g];
+        R r;
+        r.t = P.t + (size_t)rr * P.n;
+        r.acc = P.acc + (((size_t)e * 2 + c) * (P.L + 1) + l) * P.n;
+        r.base = nullptr;
+        r.pm = nullptr;
+        if (c == 0) {
+            if (!P.no_base0) {
+                r.base = vi.p + b * vi.sb + l * vi.sl;
+                r.pm = P.perm[g];
+            }
+        } else if (P.has_base1) {
+            r.base = vi.p + b * vi.sb + vi.sp + l * vi.sl;
+        }
+        r.out = vo.p + b * vo.sb + c * vo.sp + l * vo.sl;
+        r.from_q = mods[P.K - 1].q;
+        r.halfmod = md[l].halfmod;
+        r.inv = md[l].inv;
+        r.inv_sh = md[l].inv_sh;
+        return r;
+    }
+    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return r.t[i]; }
+    __device__ __forceinline__ u64 load_fix(const R &r, u64 v, const ModConst &m) const { return submod(rebase(v, r.from_q, m), r.halfmod, m.q); }
     struct Ops {
         u64 acc, base;
     };
-    __device__ __forceinline__ Ops fetch(u32 j, u32 i, const ModConst &) const
+    __device__ __forceinline__ Ops fetch(const R &r, u32 i, const ModConst &) const
     {
-        u32 e, c, l;
-        split(j, e, c, l);
-        const u32 g = e / P.B, b = e % P.B;
         Ops o;
-        o.acc = P.acc[(((size_t)e * 2 + c) * (P.L + 1) + l) * P.n + i];
-        const CtView &vi = P.in[g];
-        o.base = 0;
-        if (c == 0) {
-            if (!P.no_base0) {
-                const u32 *pm = P.perm[g];
-                o.base = vi.p[b * vi.sb + l * vi.sl + (pm ? __ldg(pm + i) : i)];
-            }
-        } else if (P.has_base1) {
-            o.base = vi.p[b * vi.sb + vi.sp + l * vi.sl + i];
-        }
+        o.acc = r.acc[i];
+        o.base = r.base ? r.base[r.pm ? __ldg(r.pm + i) : i] : 0;
         return o;
     }
-    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m, const Ops &o) const
+    __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &m, const Ops &o) const
     {
-        u32 e, c, l;
-        split(j, e, c, l);
-        const u32 g = e / P.B, b = e % P.B;
-        const u64 r = mul_shoup(submod(o.acc, x, m.q), md[l].inv, md[l].inv_sh, m.q);
-        const CtView &vo = P.out[g];
-        vo.p[b * vo.sb + c * vo.sp + l * vo.sl + i] = addmod(o.base, r, m.q);
+        r.out[i] = addmod(o.base, mul_shoup(submod(o.acc, x, m.q), r.inv, r.inv_sh, m.q), m.q);
     }
 };
 
 // rescale step 2: out[b][p][i] = (a[b][p][i] - NTT_{q_i}((t mod q_i) - half)) * q_last^-1
 struct RescaleJob {
     static constexpr bool PIPE = false;
+    static constexpr bool R_SMEM = true;
     CtView a, out;
     const u64 *t;       // [B*size][N]
     const MdConst *md;  // constants of dropped modulus q_{L-1} per target limb
     const ModConst *mods;
     u32 size, Lm1, drop_mod, n;  // Lm1 = L-1 target limbs
     u32 lazy_in;                 // `a` holds sums of up to 16 canonical residues: reduced in the epilogue's operand fetch
+    struct R {
+        const u64 *t, *a;
+        u64 *out;
+        u64 from_q, halfmod, inv, inv_sh;
+    };
     __device__ __forceinline__ u32 mod(u32 j) const { return j % Lm1; }
-    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const { return t[(size_t)(j / Lm1) * n + i]; }
-    __device__ __forceinline__ u64 load_fix(u32 j, u64 v, const ModConst &m) const
+    __device__ __forceinline__ R resolve(u32 j) const
     {
-        return submod(rebase(v, mods[drop_mod].q, m), md[j % Lm1].halfmod, m.q);
+        const u32 l = j % Lm1, bp = j / Lm1, p = bp % size, b = bp / size;
+        return R{ t + (size_t)bp * n, a.p + b * a.sb + p * a.sp + l * a.sl, out.p + b * out.sb + p * out.sp + l * out.sl,
+                  mods[drop_mod].q, md[l].halfmod, md[l].inv, md[l].inv_sh };
     }
+    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return r.t[i]; }
+    __device__ __forceinline__ u64 load_fix(const R &r, u64 v, const ModConst &m) const { return submod(rebase(v, r.from_q, m), r.halfmod, m.q); }
     struct Ops {
         u64 av;
     };
-    __device__ __forceinline__ Ops fetch(u32 j, u32 i, const ModConst &) const
+    __device__ __forceinline__ Ops fetch(const R &r, u32 i, const ModConst &m) const
     {
-        const u32 l = j % Lm1, bp = j / Lm1, p = bp % size, b = bp / size;
-        const u64 v = a.p[b * a.sb + p * a.sp + l * a.sl + i];
-        return Ops{ lazy_in ? barrett64(v, mods[l]) : v };
+        const u64 v = r.a[i];
+        return Ops{ lazy_in ? barrett64(v, m) : v };
     }
-    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m, const Ops &o) const
+    __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &m, const Ops &o) const
     {
-        const u32 l = j % Lm1, bp = j / Lm1, p = bp % size, b = bp / size;
-        out.p[b * out.sb + p * out.sp + l * out.sl + i] = mul_shoup(submod(o.av, x, m.q), md[l].inv, md[l].inv_sh, m.q);
+        r.out[i] = mul_shoup(submod(o.av, x, m.q), r.inv, r.inv_sh, m.q);
     }
 };
 
@@ -263,73 +320,117 @@ struct FinalParams {
     const ModConst *mods;
     u32 B, L, K, n;
     u32 has_base0, has_base1;
+    u32 per;  // FinalNttJob: != 0: jobs in limb-major order, per = jobs per limb (see KsModDownJob)
 };
 struct FinalInttJob {
     static constexpr bool PIPE = false;
+    static constexpr bool R_SMEM = true;
     FinalParams P;
+    struct R {
+        const u64 *f, *base, *t;  // base: null when nothing is added
+        u64 *t2;
+        u64 from_q, invP, invP_sh, halfP;
+    };
     __device__ __forceinline__ u32 mod(u32) const { return P.L - 1; }
-    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const  // (base + F P^-1)[limb L-1], NTT form
+    __device__ __forceinline__ R resolve(u32 j) const
     {
         const u32 b = j >> 1, c = j & 1u, l = P.L - 1;
-        const u64 q = P.mods[l].q;
-        const u64 f = P.acc[((size_t)j * (P.L + 1) + l) * P.n + i];
-        u64 g = mul_shoup(f, P.mdP[l].inv, P.mdP[l].inv_sh, q);
-        if (c ? P.has_base1 : P.has_base0) g = addmod(g, P.base.p[b * P.base.sb + c * P.base.sp + l * P.base.sl + i], q);
+        return R{ P.acc + ((size_t)j * (P.L + 1) + l) * P.n,
+                  (c ? P.has_base1 : P.has_base0) ? P.base.p + b * P.base.sb + c * P.base.sp + l * P.base.sl : nullptr,
+                  P.t + (size_t)j * P.n, P.t2 + (size_t)j * P.n, P.mods[P.K - 1].q, P.mdP[l].inv, P.mdP[l].inv_sh, P.mdP[l].halfmod };
+    }
+    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &m) const  // (base + F P^-1)[limb L-1], NTT form
+    {
+        u64 g = mul_shoup(r.f[i], r.invP, r.invP_sh, m.q);
+        if (r.base) g = addmod(g, r.base[i], m.q);
         return g;
     }
-    __device__ __forceinline__ u64 load_fix(u32, u64 v, const ModConst &) const { return v; }
-    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m) const
+    __device__ __forceinline__ u64 load_fix(const R &, u64 v, const ModConst &) const { return v; }
+    __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &m) const
     {
-        const u32 l = P.L - 1;
-        const u64 d = submod(rebase(P.t[(size_t)j * P.n + i], P.mods[P.K - 1].q, m), P.mdP[l].halfmod, m.q);
-        const u64 r = submod(x, mul_shoup(d, P.mdP[l].inv, P.mdP[l].inv_sh, m.q), m.q);
-        P.t2[(size_t)j * P.n + i] = addmod(r, m.q >> 1, m.q);
+        const u64 d = submod(rebase(r.t[i], r.from_q, m), r.halfP, m.q);
+        const u64 v = submod(x, mul_shoup(d, r.invP, r.invP_sh, m.q), m.q);
+        r.t2[i] = addmod(v, m.q >> 1, m.q);
     }
 };
 struct FinalNttJob {
     static constexpr bool PIPE = false;
+    static constexpr bool R_SMEM = true;
     FinalParams P;
-    __device__ __forceinline__ u32 mod(u32 j) const { return j % (P.L - 1); }
-    __device__ __forceinline__ u64 load_raw(u32 j, u32 i) const  // d P^-1 + d2, coefficient form
+    struct R {
+        const u64 *t, *t2, *f, *base;  // base: null when nothing is added
+        u64 *out;
+        u64 qP, qL, invP, invP_sh, halfP, invQ, invQ_sh, halfQ;
+    };
+    __device__ __forceinline__ void rl(u32 j, u32 &bc, u32 &l) const
     {
-        const u32 l = j % (P.L - 1), bc = j / (P.L - 1);
-        const ModConst &m = P.mods[l];
-        const u64 d = submod(rebase(P.t[(size_t)bc * P.n + i], P.mods[P.K - 1].q, m), P.mdP[l].halfmod, m.q);
-        const u64 d2 = submod(rebase(P.t2[(size_t)bc * P.n + i], P.mods[P.L - 1].q, m), P.mdQ[l].halfmod, m.q);
-        return addmod(mul_shoup(d, P.mdP[l].inv, P.mdP[l].inv_sh, m.q), d2, m.q);
+        if (P.per) {
+            l = j / P.per;
+            bc = j % P.per;
+        } else {
+            l = j % (P.L - 1);
+            bc = j / (P.L - 1);
+        }
     }
-    __device__ __forceinline__ u64 load_fix(u32, u64 v, const ModConst &) const { return v; }
+    __device__ __forceinline__ u32 mod(u32 j) const
+    {
+        u32 bc, l;
+        rl(j, bc, l);
+        return l;
+    }
+    __device__ __forceinline__ R resolve(u32 j) const
+    {
+        u32 bc, l;
+        rl(j, bc, l);
+        const u32 b = bc >> 1, c = bc & 1u;
+        return R{ P.t + (size_t)bc * P.n, P.t2 + (size_t)bc * P.n, P.acc + ((size_t)bc * (P.L + 1) + l) * P.n,
+                  (c ? P.has_base1 : P.has_base0) ? P.base.p + b * P.base.sb + c * P.base.sp + l * P.base.sl : nullptr,
+                  P.out.p + b * P.out.sb + c * P.out.sp + l * P.out.sl, P.mods[P.K - 1].q, P.mods[P.L - 1].q,
+                  P.mdP[l].inv, P.mdP[l].inv_sh, P.mdP[l].halfmod, P.mdQ[l].inv, P.mdQ[l].inv_sh, P.mdQ[l].halfmod };
+    }
+    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &m) const  // d P^-1 + d2, coefficient form
+    {
+        const u64 d = submod(rebase(r.t[i], r.qP, m), r.halfP, m.q);
+        const u64 d2 = submod(rebase(r.t2[i], r.qL, m), r.halfQ, m.q);
+        return addmod(mul_shoup(d, r.invP, r.invP_sh, m.q), d2, m.q);
+    }
+    __device__ __forceinline__ u64 load_fix(const R &, u64 v, const ModConst &) const { return v; }
     struct Ops {
         u64 f, base;
     };
-    __device__ __forceinline__ Ops fetch(u32 j, u32 i, const ModConst &) const
+    __device__ __forceinline__ Ops fetch(const R &r, u32 i, const ModConst &) const { return Ops{ r.f[i], r.base ? r.base[i] : 0 }; }
+    __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &m, const Ops &o) const
     {
-        const u32 l = j % (P.L - 1), bc = j / (P.L - 1), b = bc >> 1, c = bc & 1u;
-        Ops o;
-        o.f = P.acc[((size_t)bc * (P.L + 1) + l) * P.n + i];
-        o.base = (c ? P.has_base1 : P.has_base0) ? P.base.p[b * P.base.sb + c * P.base.sp + l * P.base.sl + i] : 0;
-        return o;
-    }
-    __device__ __forceinline__ void store(u32 j, u32 i, u64 x, const ModConst &m, const Ops &o) const
-    {
-        const u32 l = j % (P.L - 1), bc = j / (P.L - 1), b = bc >> 1, c = bc & 1u;
-        const u64 r = addmod(o.base, mul_shoup(o.f, P.mdP[l].inv, P.mdP[l].inv_sh, m.q), m.q);
-        P.out.p[b * P.out.sb + c * P.out.sp + l * P.out.sl + i] = mul_shoup(submod(r, x, m.q), P.mdQ[l].inv, P.mdQ[l].inv_sh, m.q);
+        const u64 v = addmod(o.base, mul_shoup(o.f, r.invP, r.invP_sh, m.q), m.q);
+        r.out[i] = mul_shoup(submod(v, x, m.q), r.invQ, r.invQ_sh, m.q);
     }
 };
 
 // ---------------------------------------------------------------------------------------
 // Loaders (protocol in ntt.cuh): raw() = memory only, fix() = arithmetic only.
 // ---------------------------------------------------------------------------------------
+// rows and constants of this CTA's job (Job::R): in registers when small, else computed by thread 0 into shared memory
+#define HEGPU_RESOLVE_JOB(job, jid)                          \
+    __shared__ typename Job::R r_sh;                         \
+    typename Job::R r_loc;                                   \
+    if constexpr (Job::R_SMEM) {                             \
+        if (threadIdx.x == 0) r_sh = (job).resolve(jid);     \
+        __syncthreads();                                     \
+    } else {                                                 \
+        r_loc = (job).resolve(jid);                          \
+    }                                                        \
+    const typename Job::R &r = *(Job::R_SMEM ? &r_sh : &r_loc)
+
 template <class Job>
-struct PlainLoader {  // coefficient boff + i of job jid
+struct PlainLoader {  // coefficient boff + i of the resolved job
     typedef u64 Raw;
     static constexpr bool PIPE = Job::PIPE;
     const Job &job;
     const ModConst &m;
-    u32 jid, boff;
-    __device__ __forceinline__ Raw raw(u32 i) const { return job.load_raw(jid, boff + i); }
-    __device__ __forceinline__ u64 fix(Raw r, u32) const { return job.load_fix(jid, r, m); }
+    const typename Job::R &jr;
+    u32 boff;
+    __device__ __forceinline__ Raw raw(u32 i) const { return job.load_raw(jr, boff + i, m); }
+    __device__ __forceinline__ u64 fix(Raw r, u32) const { return job.load_fix(jr, r, m); }
 };
 // product of the stride-N/2 stage that the fold loaders compute while loading (canonical inputs): with the approximate
 // quotient the outputs are below 4q instead of 3q, which the range analysis of ArI64 covers (pass 0 has no correction and
@@ -350,13 +451,14 @@ struct FoldLoader {
     static constexpr bool PIPE = Job::PIPE;
     const Job &job;
     const ModConst &m;
-    u32 jid, h;
+    const typename Job::R &jr;
+    u32 h;
     ulonglong2 W;  // twiddle of the first stage
     u64 *park;
-    __device__ __forceinline__ Raw raw(u32 i) const { return Pair64{ job.load_raw(jid, i), job.load_raw(jid, i + (1u << LOGL)) }; }
+    __device__ __forceinline__ Raw raw(u32 i) const { return Pair64{ job.load_raw(jr, i, m), job.load_raw(jr, i + (1u << LOGL), m) }; }
     __device__ __forceinline__ u64 fix(Raw r, u32 i) const
     {
-        const u64 X = job.load_fix(jid, r.x, m), Y = job.load_fix(jid, r.y, m);
+        const u64 X = job.load_fix(jr, r.x, m), Y = job.load_fix(jr, r.y, m);
         const u64 Tm = fold_mul(Y, W, m);
         const u64 top = X + Tm, bot = X + fold_off(m) - Tm;
         if (park) park[i] = h ? top : bot;
@@ -373,18 +475,19 @@ struct ParkFoldLoader {
     static constexpr bool PIPE = Job::PIPE;
     const Job &job;
     const ModConst &m;
-    u32 jid, half;
+    const typename Job::R &jr;
+    u32 half;
     ulonglong2 W;  // twiddle of the first stage
     u64 *park;
     __device__ __forceinline__ Raw raw(u32 i) const
     {
         if (half) return Pair64{ park[i], 0 };
-        return Pair64{ job.load_raw(jid, i), job.load_raw(jid, i + (1u << LOGL)) };
+        return Pair64{ job.load_raw(jr, i, m), job.load_raw(jr, i + (1u << LOGL), m) };
     }
     __device__ __forceinline__ u64 fix(Raw r, u32 i) const
     {
         if (half) return r.x;
-        const u64 X = job.load_fix(jid, r.x, m), Y = job.load_fix(jid, r.y, m);
+        const u64 X = job.load_fix(jr, r.x, m), Y = job.load_fix(jr, r.y, m);
         const u64 Tm = fold_mul(Y, W, m);
         park[i] = X + fold_off(m) - Tm;
         return X + Tm;
@@ -401,14 +504,15 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
     const u32 jid = blockIdx.x >> SPLIT;
     const u32 h = blockIdx.x & ((1u << SPLIT) - 1u);
     const u32 mi = job.mod(jid);
+    HEGPU_RESOLVE_JOB(job, jid);
     const ModConst m = T.mods[mi];
     const ulonglong2 *tw = T.fwd + (size_t)mi * T.n;
     const u32 boff = h << LOGL;
-    auto fetch = [&](u32 i) { return job.fetch(jid, boff + i, m); };
-    auto store = [&](u32 i, u64 v, const typename Job::Ops &o) { job.store(jid, boff + i, v, m, o); };
+    auto fetch = [&](u32 i) { return job.fetch(r, boff + i, m); };
+    auto store = [&](u32 i, u64 v, const typename Job::Ops &o) { job.store(r, boff + i, v, m, o); };
     const ulonglong2 nowl = make_ulonglong2(0, 0);
     if constexpr (SPLIT == 0) {
-        PlainLoader<Job> load{ job, m, jid, 0 };
+        PlainLoader<Job> load{ job, m, r, 0 };
         if (m.big & 4u)
             ntt_fwd_cta<LOGL, LOGE>(load, fetch, store, T.fwd_d + (size_t)mi * T.n, T.n, ArF64(T.modsd[mi]), sm);
         else if (m.big & 1u)
@@ -417,7 +521,7 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
             ntt_fwd_cta<LOGL, LOGE>(load, fetch, store, tw, T.n, ArI64<false>(m, nowl), sm);
     } else {
         // stage 1 (stride N/2) redone from global memory by both halves
-        FoldLoader<Job, LOGL> load{ job, m, jid, h, __ldg(tw + 1), nullptr };
+        FoldLoader<Job, LOGL> load{ job, m, r, h, __ldg(tw + 1), nullptr };
         if (m.big & 1u)
             ntt_fwd_cta<LOGL, LOGE>(load, fetch, store, tw, T.n + boff, ArI64<true>(m, nowl), sm);
         else
@@ -435,13 +539,14 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
     const u32 jid = blockIdx.x >> SPLIT;
     const u32 h = blockIdx.x & ((1u << SPLIT) - 1u);
     const u32 mi = job.mod(jid);
+    HEGPU_RESOLVE_JOB(job, jid);
     const ModConst m = T.mods[mi];
     const ulonglong2 *tw = T.inv + (size_t)mi * T.n;
     const ulonglong2 wl = T.inv_last[mi];
     const u32 boff = h << LOGL;
-    PlainLoader<Job> load{ job, m, jid, boff };
+    PlainLoader<Job> load{ job, m, r, boff };
     if constexpr (SPLIT == 0) {
-        auto store = [&](u32 i, u64 v) { job.store(jid, i, v, m); };
+        auto store = [&](u32 i, u64 v) { job.store(r, i, v, m); };
         if (m.big & 4u)
             ntt_inv_cta<LOGL, LOGE, LOGL - 1>(load, store, T.inv_d + (size_t)mi * T.n, T.n, ArF64(T.modsd[mi]), sm);
         else if (m.big & 2u)
@@ -473,14 +578,15 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
     extern __shared__ __align__(16) u64 sm[];
     const u32 jid = blockIdx.x;
     const u32 mi = job.mod(jid);
+    HEGPU_RESOLVE_JOB(job, jid);
     const ModConst m = T.mods[mi];
     const ulonglong2 *tw = T.fwd + (size_t)mi * T.n;
     constexpr u32 half = 1u << LOGL;
     u64 *pk = park + (size_t)jid * half;
-    ParkFoldLoader<Job, LOGL> load{ job, m, jid, 0, __ldg(tw + 1), pk };
+    ParkFoldLoader<Job, LOGL> load{ job, m, r, 0, __ldg(tw + 1), pk };
     u32 boff = 0;  // block offset of the half being transformed
-    auto fetch = [&](u32 i) { return job.fetch(jid, boff + i, m); };
-    auto store = [&](u32 i, u64 v, const typename Job::Ops &o) { job.store(jid, boff + i, v, m, o); };
+    auto fetch = [&](u32 i) { return job.fetch(r, boff + i, m); };
+    auto store = [&](u32 i, u64 v, const typename Job::Ops &o) { job.store(r, boff + i, v, m, o); };
     const ulonglong2 nowl = make_ulonglong2(0, 0);
     if (m.big & 4u) {
         const ArF64 ar(T.modsd[mi]);
@@ -514,11 +620,11 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
 }
 
 template <int LOGL, int LOGE, class A, class TWP, class Job>
-__device__ __forceinline__ void inv_park_body(const Job &job, u32 jid, const ModConst &m, const A &ar, const TWP tw, u32 n,
+__device__ __forceinline__ void inv_park_body(const Job &job, const typename Job::R &r, const ModConst &m, const A &ar, const TWP tw, u32 n,
                                               typename A::V *pk, u64 *sm)
 {
     constexpr u32 half = 1u << LOGL;
-    PlainLoader<Job> load{ job, m, jid, 0 };
+    PlainLoader<Job> load{ job, m, r, 0 };
     u32 h = 0;
     // half 0 is transformed and parked; half 1 is transformed and its last-pass registers are combined
     // with the parked half in the final stride-N/2 stage.  One store for both halves: shared code.
@@ -529,8 +635,8 @@ __device__ __forceinline__ void inv_park_body(const Job &job, u32 jid, const Mod
         }
         typename A::V x = pk[i];
         ar.template inv_bfly_last<LOGL>(x, y);
-        job.store(jid, i, ar.inv_final(x), m);
-        job.store(jid, half + i, ar.inv_final(y), m);
+        job.store(r, i, ar.inv_final(x), m);
+        job.store(r, half + i, ar.inv_final(y), m);
     };
 #pragma unroll 1
     for (h = 0; h < 2; ++h) {
@@ -547,15 +653,16 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
     extern __shared__ __align__(16) u64 sm[];
     const u32 jid = blockIdx.x;
     const u32 mi = job.mod(jid);
+    HEGPU_RESOLVE_JOB(job, jid);
     const ModConst m = T.mods[mi];
     const ulonglong2 *tw = T.inv + (size_t)mi * T.n;
     u64 *pk = park + ((size_t)jid << LOGL);
     if (m.big & 4u)
-        inv_park_body<LOGL, LOGE>(job, jid, m, ArF64(T.modsd[mi]), T.inv_d + (size_t)mi * T.n, T.n, reinterpret_cast<double *>(pk), sm);
+        inv_park_body<LOGL, LOGE>(job, r, m, ArF64(T.modsd[mi]), T.inv_d + (size_t)mi * T.n, T.n, reinterpret_cast<double *>(pk), sm);
     else if (m.big & 2u)
-        inv_park_body<LOGL, LOGE>(job, jid, m, ArI64<true>(m, T.inv_last[mi]), tw, T.n, pk, sm);
+        inv_park_body<LOGL, LOGE>(job, r, m, ArI64<true>(m, T.inv_last[mi]), tw, T.n, pk, sm);
     else
-        inv_park_body<LOGL, LOGE>(job, jid, m, ArI64<false>(m, T.inv_last[mi]), tw, T.n, pk, sm);
+        inv_park_body<LOGL, LOGE>(job, r, m, ArI64<false>(m, T.inv_last[mi]), tw, T.n, pk, sm);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -576,14 +683,15 @@ struct Park4FoldLoader {
     static constexpr bool PIPE = false;
     const Job &job;
     const ModConst &m;
-    u32 jid, quarter;
+    const typename Job::R &jr;
+    u32 quarter;
     ulonglong2 W1, W2, W3;  // twiddles of the first stage (index 1) and of the second (indices 2, 3)
     u64 *park;              // [3][2^LOGL]
     __device__ __forceinline__ Raw raw(u32 i) const
     {
         constexpr u32 Q = 1u << LOGL;
         if (quarter) return Quad64{ park[(quarter - 1) * Q + i], 0, 0, 0 };
-        return Quad64{ job.load_raw(jid, i), job.load_raw(jid, i + Q), job.load_raw(jid, i + 2 * Q), job.load_raw(jid, i + 3 * Q) };
+        return Quad64{ job.load_raw(jr, i, m), job.load_raw(jr, i + Q, m), job.load_raw(jr, i + 2 * Q, m), job.load_raw(jr, i + 3 * Q, m) };
     }
     // canonical inputs; outputs below 7q with the approximate quotient (q -> 4q -> 7q), 5q with the exact one: pass 0 of
     // the sub-transform has no correction and ends below 7q + 8q < 16q
@@ -591,7 +699,7 @@ struct Park4FoldLoader {
     {
         constexpr u32 Q = 1u << LOGL;
         if (quarter) return r.a;
-        const u64 a = job.load_fix(jid, r.a, m), b = job.load_fix(jid, r.b, m), c = job.load_fix(jid, r.c, m), d = job.load_fix(jid, r.d, m);
+        const u64 a = job.load_fix(jr, r.a, m), b = job.load_fix(jr, r.b, m), c = job.load_fix(jr, r.c, m), d = job.load_fix(jr, r.d, m);
         const u64 off = fold_off(m);
         u64 T = fold_mul(c, W1, m);
         const u64 a1 = a + T, c1 = a + off - T;
@@ -614,13 +722,14 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
     extern __shared__ __align__(16) u64 sm[];
     const u32 jid = blockIdx.x;
     const u32 mi = job.mod(jid);
+    HEGPU_RESOLVE_JOB(job, jid);
     const ModConst m = T.mods[mi];
     const ulonglong2 *tw = T.fwd + (size_t)mi * T.n;
     u64 *pk = park + (size_t)jid * (3u << LOGL);
-    Park4FoldLoader<Job, LOGL> load{ job, m, jid, 0, __ldg(tw + 1), __ldg(tw + 2), __ldg(tw + 3), pk };
+    Park4FoldLoader<Job, LOGL> load{ job, m, r, 0, __ldg(tw + 1), __ldg(tw + 2), __ldg(tw + 3), pk };
     u32 boff = 0;  // block offset of the quarter being transformed
-    auto fetch = [&](u32 i) { return job.fetch(jid, boff + i, m); };
-    auto store = [&](u32 i, u64 v, const typename Job::Ops &o) { job.store(jid, boff + i, v, m, o); };
+    auto fetch = [&](u32 i) { return job.fetch(r, boff + i, m); };
+    auto store = [&](u32 i, u64 v, const typename Job::Ops &o) { job.store(r, boff + i, v, m, o); };
     const ulonglong2 nowl = make_ulonglong2(0, 0);
     if (m.big & 4u) {
         const ArF64 ar(T.modsd[mi]);
@@ -654,11 +763,11 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
 }
 
 template <int LOGL, int LOGE, class A, class TWP, class Job>
-__device__ __forceinline__ void inv_park4_body(const Job &job, u32 jid, const ModConst &m, const A &ar, const TWP tw, u32 n,
+__device__ __forceinline__ void inv_park4_body(const Job &job, const typename Job::R &r, const ModConst &m, const A &ar, const TWP tw, u32 n,
                                                typename A::V *pk, u64 *sm)
 {
     constexpr u32 Q = 1u << LOGL;
-    PlainLoader<Job> load{ job, m, jid, 0 };
+    PlainLoader<Job> load{ job, m, r, 0 };
     u32 h = 0;
     const typename A::TW W2 = __ldg(tw + 2), W3 = __ldg(tw + 3);  // stage LOGL: quarters (0,1) and (2,3)
     auto store = [&](u32 i, typename A::V y) {
@@ -671,10 +780,10 @@ __device__ __forceinline__ void inv_park4_body(const Job &job, u32 jid, const Mo
         ar.template inv_bfly<LOGL>(x2, y, W3);
         ar.template inv_bfly_last<LOGL + 1>(x0, x2);
         ar.template inv_bfly_last<LOGL + 1>(x1, y);
-        job.store(jid, i, ar.inv_final(x0), m);
-        job.store(jid, Q + i, ar.inv_final(x1), m);
-        job.store(jid, 2 * Q + i, ar.inv_final(x2), m);
-        job.store(jid, 3 * Q + i, ar.inv_final(y), m);
+        job.store(r, i, ar.inv_final(x0), m);
+        job.store(r, Q + i, ar.inv_final(x1), m);
+        job.store(r, 2 * Q + i, ar.inv_final(x2), m);
+        job.store(r, 3 * Q + i, ar.inv_final(y), m);
     };
 #pragma unroll 1
     for (h = 0; h < 4; ++h) {
@@ -691,15 +800,16 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
     extern __shared__ __align__(16) u64 sm[];
     const u32 jid = blockIdx.x;
     const u32 mi = job.mod(jid);
+    HEGPU_RESOLVE_JOB(job, jid);
     const ModConst m = T.mods[mi];
     const ulonglong2 *tw = T.inv + (size_t)mi * T.n;
     u64 *pk = park + (size_t)jid * (3u << LOGL);
     if (m.big & 4u)
-        inv_park4_body<LOGL, LOGE>(job, jid, m, ArF64(T.modsd[mi]), T.inv_d + (size_t)mi * T.n, T.n, reinterpret_cast<double *>(pk), sm);
+        inv_park4_body<LOGL, LOGE>(job, r, m, ArF64(T.modsd[mi]), T.inv_d + (size_t)mi * T.n, T.n, reinterpret_cast<double *>(pk), sm);
     else if (m.big & 2u)
-        inv_park4_body<LOGL, LOGE>(job, jid, m, ArI64<true>(m, T.inv_last[mi]), tw, T.n, pk, sm);
+        inv_park4_body<LOGL, LOGE>(job, r, m, ArI64<true>(m, T.inv_last[mi]), tw, T.n, pk, sm);
     else
-        inv_park4_body<LOGL, LOGE>(job, jid, m, ArI64<false>(m, T.inv_last[mi]), tw, T.n, pk, sm);
+        inv_park4_body<LOGL, LOGE>(job, r, m, ArI64<false>(m, T.inv_last[mi]), tw, T.n, pk, sm);
 }
 
 // last (stride N/2) INTT stage for N = 2^(LOGL+1), element-wise over scratch
@@ -712,14 +822,15 @@ __global__ void __launch_bounds__(256) ntt_inv_final_kernel(const Job job, const
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const u32 jid = (u32)(idx >> LOGL), i = (u32)(idx & (halfn - 1));
         const u32 mi = job.mod(jid);
+        const typename Job::R r = job.resolve(jid);
         const ModConst m = T.mods[mi];
         const ulonglong2 wl = T.inv_last[mi];
         const u64 X = scratch[(size_t)jid * T.n + i], Y = scratch[(size_t)jid * T.n + halfn + i];
         // lazy ranges of ArI64::inv_bfly: [0, LZ q) (corrected per stage) or [0, LZ q * 2^LOGL) (sums left to double)
         const u64 Sm = X + Y;
         const u64 D = (m.big & 2u) ? X + (ArI64<true>::LZ == 3 ? m.q3 : m.q << 1) - Y : X + (m.q << (LOGL + 2)) - Y;
-        job.store(jid, i, mul_shoup(Sm, m.ninv, m.ninv_sh, m.q), m);
-        job.store(jid, i + halfn, mul_shoup(D, wl.x, wl.y, m.q), m);
+        job.store(r, i, mul_shoup(Sm, m.ninv, m.ninv_sh, m.q), m);
+        job.store(r, i + halfn, mul_shoup(D, wl.x, wl.y, m.q), m);
     }
 }
 
