@@ -54,6 +54,41 @@ __device__ __forceinline__ u64 rebase(u64 v, u64 from, const ModConst &m)
 //   inverse jobs:  void store(r, i, x, m)
 //   forward jobs:  Ops fetch(r, i, m);  void store(r, i, x, m, ops)     (epilogue operands fetched before the last stages)
 
+// the same for E values at once: the branch on the pair of moduli is taken once, not once per coefficient (ptxas keeps
+// the per-coefficient form as a branch tree in front of every load's arithmetic)
+template <int E>
+__device__ __forceinline__ void rebase_set(u64 (&v)[E], u64 from, const ModConst &m)
+{
+    if (from <= m.q) return;
+    if ((from >> 1) < m.q) {
+#pragma unroll
+        for (int k = 0; k < E; ++k) v[k] = csub(v[k], m.q);
+    } else {
+#pragma unroll
+        for (int k = 0; k < E; ++k) v[k] = barrett64(v[k], m);
+    }
+}
+// canonical residues of the modulus `from` as doubles congruent mod q (FP64 butterfly policy, q < 2^43), magnitude below
+// q/2 + 2^30 or below 2q: a word below 2^51 converts exactly (and is reduced once if `from` is far above q); a 60-bit word is
+// split at bit 30 and hi * 2^30 is reduced with the exact FP64 product -- 2 conversions + 7 FP64 operations instead of the
+// 64-bit Barrett reduction (4 wide multiplies + ~15 integer instructions) followed by a conversion
+template <int E>
+__device__ __forceinline__ void rebase_f64_set(const u64 (&v)[E], double (&d)[E], u64 from, const ArF64 &ar)
+{
+    if ((from >> 51) == 0) {
+#pragma unroll
+        for (int k = 0; k < E; ++k) d[k] = ar.from_load(v[k]);
+        if ((double)from > 2.0 * ar.f.q) {
+#pragma unroll
+            for (int k = 0; k < E; ++k) d[k] = ar.reduce(d[k]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < E; ++k)
+            d[k] = __dadd_rn(ar.mulmod(ar.from_load(v[k] >> 30), 1073741824.0), ar.from_load(v[k] & 0x3FFFFFFFull));
+    }
+}
+
 // plain transform of `count` limb polynomials [count][N] (measurement API, host tooling)
 struct PlainJob {
     static constexpr bool PIPE = true;  // software-pipelined first-pass loads (no epilogue operands -> no spills)
@@ -69,6 +104,9 @@ struct PlainJob {
     __device__ __forceinline__ R resolve(u32 j) const { return R{ src + (size_t)j * n, dst + (size_t)j * n }; }
     __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return r.src[i]; }
     __device__ __forceinline__ u64 load_fix(const R &, u64 v, const ModConst &) const { return v; }
+    static constexpr bool F64_LOAD = false;
+    template <int E>
+    __device__ __forceinline__ void fix_set(const R &, u64 (&)[E], const ModConst &) const {}
     __device__ __forceinline__ void store(const R &r, u32 i, u64 v, const ModConst &) const { r.dst[i] = v; }
     struct Ops {};
     __device__ __forceinline__ Ops fetch(const R &, u32, const ModConst &) const { return Ops{}; }
@@ -116,9 +154,9 @@ struct KsInttJob {
         const CtView &v = P.in[g];
         return R{ v.p + b * v.sb + P.target_poly * v.sp + l * v.sl, P.hoisted ? nullptr : P.perm[g], P.coef + (size_t)j * P.n };
     }
-    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return r.row[r.pm ? __ldg(r.pm + i) : i]; }
+    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return __ldcg(r.row + (r.pm ? __ldg(r.pm + i) : i)); }
     __device__ __forceinline__ u64 load_fix(const R &, u64 v, const ModConst &) const { return v; }
-    __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &) const { r.dst[i] = x; }
+    __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &) const { __stcg(r.dst + i, x); }
 };
 
 // K7 step 2: ext[e][j][i] = NTT_{m_i}( c_j mod m_i ), i != j, i in [0, L]
@@ -153,11 +191,16 @@ struct KsLiftJob {
         split(j, e, dj, di);
         return R{ P.coef + ((size_t)e * P.L + dj) * P.n, P.ext + (((size_t)e * P.L + dj) * (P.L + 1) + di) * P.n, mods[dj].q };
     }
-    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return r.src[i]; }
+    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return __ldcg(r.src + i); }
     __device__ __forceinline__ u64 load_fix(const R &r, u64 v, const ModConst &m) const { return rebase(v, r.from_q, m); }
+    static constexpr bool F64_LOAD = true;
+    template <int E>
+    __device__ __forceinline__ void fix_set(const R &r, u64 (&v)[E], const ModConst &m) const { rebase_set<E>(v, r.from_q, m); }
+    template <int E>
+    __device__ __forceinline__ void f64_set(const R &r, const u64 (&v)[E], double (&d)[E], const ArF64 &ar) const { rebase_f64_set<E>(v, d, r.from_q, ar); }
     struct Ops {};
     __device__ __forceinline__ Ops fetch(const R &, u32, const ModConst &) const { return Ops{}; }
-    __device__ __forceinline__ void store(const R &r, u32 i, u64 v, const ModConst &, const Ops &) const { r.dst[i] = v; }
+    __device__ __forceinline__ void store(const R &r, u32 i, u64 v, const ModConst &, const Ops &) const { __stcg(r.dst + i, v); }
 };
 
 // INTT of a dropped limb with the rounding offset added: t = (INTT_d(src) + floor(d/2)) mod d.
@@ -240,21 +283,38 @@ struct KsModDownJob {
         r.inv_sh = md[l].inv_sh;
         return r;
     }
-    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return r.t[i]; }
+    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return __ldcg(r.t + i); }
     __device__ __forceinline__ u64 load_fix(const R &r, u64 v, const ModConst &m) const { return submod(rebase(v, r.from_q, m), r.halfmod, m.q); }
+    static constexpr bool F64_LOAD = true;
+    template <int E>
+    __device__ __forceinline__ void fix_set(const R &r, u64 (&v)[E], const ModConst &m) const
+    {
+        rebase_set<E>(v, r.from_q, m);
+        const u64 hm = r.halfmod;
+#pragma unroll
+        for (int k = 0; k < E; ++k) v[k] = submod(v[k], hm, m.q);
+    }
+    template <int E>
+    __device__ __forceinline__ void f64_set(const R &r, const u64 (&v)[E], double (&d)[E], const ArF64 &ar) const
+    {
+        rebase_f64_set<E>(v, d, r.from_q, ar);
+        const double hm = ar.from_load(r.halfmod);
+#pragma unroll
+        for (int k = 0; k < E; ++k) d[k] = __dadd_rn(d[k], -hm);
+    }
     struct Ops {
         u64 acc, base;
     };
     __device__ __forceinline__ Ops fetch(const R &r, u32 i, const ModConst &) const
     {
         Ops o;
-        o.acc = r.acc[i];
-        o.base = r.base ? r.base[r.pm ? __ldg(r.pm + i) : i] : 0;
+        o.acc = __ldcg(r.acc + i);
+        o.base = r.base ? __ldcg(r.base + (r.pm ? __ldg(r.pm + i) : i)) : 0;
         return o;
     }
     __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &m, const Ops &o) const
     {
-        r.out[i] = addmod(o.base, mul_shoup(submod(o.acc, x, m.q), r.inv, r.inv_sh, m.q), m.q);
+        __stcg(r.out + i, addmod(o.base, mul_shoup(submod(o.acc, x, m.q), r.inv, r.inv_sh, m.q), m.q));
     }
 };
 
@@ -280,19 +340,36 @@ struct RescaleJob {
         return R{ t + (size_t)bp * n, a.p + b * a.sb + p * a.sp + l * a.sl, out.p + b * out.sb + p * out.sp + l * out.sl,
                   mods[drop_mod].q, md[l].halfmod, md[l].inv, md[l].inv_sh };
     }
-    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return r.t[i]; }
+    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return __ldcg(r.t + i); }
     __device__ __forceinline__ u64 load_fix(const R &r, u64 v, const ModConst &m) const { return submod(rebase(v, r.from_q, m), r.halfmod, m.q); }
+    static constexpr bool F64_LOAD = true;
+    template <int E>
+    __device__ __forceinline__ void fix_set(const R &r, u64 (&v)[E], const ModConst &m) const
+    {
+        rebase_set<E>(v, r.from_q, m);
+        const u64 hm = r.halfmod;
+#pragma unroll
+        for (int k = 0; k < E; ++k) v[k] = submod(v[k], hm, m.q);
+    }
+    template <int E>
+    __device__ __forceinline__ void f64_set(const R &r, const u64 (&v)[E], double (&d)[E], const ArF64 &ar) const
+    {
+        rebase_f64_set<E>(v, d, r.from_q, ar);
+        const double hm = ar.from_load(r.halfmod);
+#pragma unroll
+        for (int k = 0; k < E; ++k) d[k] = __dadd_rn(d[k], -hm);
+    }
     struct Ops {
         u64 av;
     };
     __device__ __forceinline__ Ops fetch(const R &r, u32 i, const ModConst &m) const
     {
-        const u64 v = r.a[i];
+        const u64 v = __ldcg(r.a + i);
         return Ops{ lazy_in ? barrett64(v, m) : v };
     }
     __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &m, const Ops &o) const
     {
-        r.out[i] = mul_shoup(submod(o.av, x, m.q), r.inv, r.inv_sh, m.q);
+        __stcg(r.out + i, mul_shoup(submod(o.av, x, m.q), r.inv, r.inv_sh, m.q));
     }
 };
 
@@ -341,16 +418,16 @@ struct FinalInttJob {
     }
     __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &m) const  // (base + F P^-1)[limb L-1], NTT form
     {
-        u64 g = mul_shoup(r.f[i], r.invP, r.invP_sh, m.q);
-        if (r.base) g = addmod(g, r.base[i], m.q);
+        u64 g = mul_shoup(__ldcg(r.f + i), r.invP, r.invP_sh, m.q);
+        if (r.base) g = addmod(g, __ldcg(r.base + i), m.q);
         return g;
     }
     __device__ __forceinline__ u64 load_fix(const R &, u64 v, const ModConst &) const { return v; }
     __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &m) const
     {
-        const u64 d = submod(rebase(r.t[i], r.from_q, m), r.halfP, m.q);
+        const u64 d = submod(rebase(__ldcg(r.t + i), r.from_q, m), r.halfP, m.q);
         const u64 v = submod(x, mul_shoup(d, r.invP, r.invP_sh, m.q), m.q);
-        r.t2[i] = addmod(v, m.q >> 1, m.q);
+        __stcg(r.t2 + i, addmod(v, m.q >> 1, m.q));
     }
 };
 struct FinalNttJob {
@@ -390,19 +467,22 @@ struct FinalNttJob {
     }
     __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &m) const  // d P^-1 + d2, coefficient form
     {
-        const u64 d = submod(rebase(r.t[i], r.qP, m), r.halfP, m.q);
-        const u64 d2 = submod(rebase(r.t2[i], r.qL, m), r.halfQ, m.q);
+        const u64 d = submod(rebase(__ldcg(r.t + i), r.qP, m), r.halfP, m.q);
+        const u64 d2 = submod(rebase(__ldcg(r.t2 + i), r.qL, m), r.halfQ, m.q);
         return addmod(mul_shoup(d, r.invP, r.invP_sh, m.q), d2, m.q);
     }
     __device__ __forceinline__ u64 load_fix(const R &, u64 v, const ModConst &) const { return v; }
+    static constexpr bool F64_LOAD = false;
+    template <int E>
+    __device__ __forceinline__ void fix_set(const R &, u64 (&)[E], const ModConst &) const {}
     struct Ops {
         u64 f, base;
     };
-    __device__ __forceinline__ Ops fetch(const R &r, u32 i, const ModConst &) const { return Ops{ r.f[i], r.base ? r.base[i] : 0 }; }
+    __device__ __forceinline__ Ops fetch(const R &r, u32 i, const ModConst &) const { return Ops{ __ldcg(r.f + i), r.base ? __ldcg(r.base + i) : 0 }; }
     __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &m, const Ops &o) const
     {
         const u64 v = addmod(o.base, mul_shoup(o.f, r.invP, r.invP_sh, m.q), m.q);
-        r.out[i] = mul_shoup(submod(v, x, m.q), r.invQ, r.invQ_sh, m.q);
+        __stcg(r.out + i, mul_shoup(submod(v, x, m.q), r.invQ, r.invQ_sh, m.q));
     }
 };
 
@@ -431,6 +511,17 @@ struct PlainLoader {  // coefficient boff + i of the resolved job
     u32 boff;
     __device__ __forceinline__ Raw raw(u32 i) const { return job.load_raw(jr, boff + i, m); }
     __device__ __forceinline__ u64 fix(Raw r, u32) const { return job.load_fix(jr, r, m); }
+    // a whole register set at once (forward pass 0): idx(k) = coefficient index of element k
+    template <int E, class A, class IdxF>
+    __device__ __forceinline__ void fix_set(const Raw (&raw)[E], typename A::V (&x)[E], IdxF, const A &ar) const
+    {
+        u64 v[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) v[k] = raw[k];
+        job.template fix_set<E>(jr, v, m);
+#pragma unroll
+        for (int k = 0; k < E; ++k) x[k] = ar.from_load(v[k]);
+    }
 };
 // product of the stride-N/2 stage that the fold loaders compute while loading (canonical inputs): with the approximate
 // quotient the outputs are below 4q instead of 3q, which the range analysis of ArI64 covers (pass 0 has no correction and
@@ -464,6 +555,12 @@ struct FoldLoader {
         if (park) park[i] = h ? top : bot;
         return h ? bot : top;
     }
+    template <int E, class A, class IdxF>
+    __device__ __forceinline__ void fix_set(const Raw (&raw)[E], typename A::V (&x)[E], IdxF idx, const A &ar) const
+    {
+#pragma unroll
+        for (int k = 0; k < E; ++k) x[k] = ar.from_load(fix(raw[k], idx(k)));
+    }
 };
 // loader of the park kernels: half 0 folds the stride-N/2 stage from the job's input and parks the
 // bottom outputs; half 1 reads what half 0 parked (same thread wrote it).  One type for both halves
@@ -478,6 +575,7 @@ struct ParkFoldLoader {
     const typename Job::R &jr;
     u32 half;
     ulonglong2 W;  // twiddle of the first stage
+    double Wd;     // the same as a double (FP64 policy)
     u64 *park;
     __device__ __forceinline__ Raw raw(u32 i) const
     {
@@ -491,6 +589,51 @@ struct ParkFoldLoader {
         const u64 Tm = fold_mul(Y, W, m);
         park[i] = X + fold_off(m) - Tm;
         return X + Tm;
+    }
+    // A whole register set at once: the branches on the half and on the pair of moduli are taken once per set.  In the FP64
+    // policy (jobs with F64_LOAD) the operands become doubles straight away and the folded stage runs on the FP64 pipe; the
+    // parked half then holds doubles.
+    template <int E, class A, class IdxF>
+    __device__ __forceinline__ void fix_set(const Raw (&raw)[E], typename A::V (&x)[E], IdxF idx, const A &ar) const
+    {
+        constexpr bool F64 = std::is_same<A, ArF64>::value && Job::F64_LOAD;
+        if (half) {
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                if constexpr (F64)
+                    x[k] = __longlong_as_double((long long)raw[k].x);
+                else
+                    x[k] = ar.from_load(raw[k].x);
+            }
+            return;
+        }
+        u64 X[E], Y[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            X[k] = raw[k].x;
+            Y[k] = raw[k].y;
+        }
+        if constexpr (F64) {
+            double dx[E], dy[E];
+            job.template f64_set<E>(jr, X, dx, ar);
+            job.template f64_set<E>(jr, Y, dy, ar);
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                const double Tm = ar.mulmod(dy[k], Wd);
+                park[idx(k)] = (u64)__double_as_longlong(__dadd_rn(dx[k], -Tm));
+                x[k] = __dadd_rn(dx[k], Tm);
+            }
+        } else {
+            job.template fix_set<E>(jr, X, m);
+            job.template fix_set<E>(jr, Y, m);
+            const u64 off = fold_off(m);
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                const u64 Tm = fold_mul(Y[k], W, m);
+                park[idx(k)] = X[k] + off - Tm;
+                x[k] = ar.from_load(X[k] + Tm);
+            }
+        }
     }
 };
 
@@ -583,7 +726,8 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
     const ulonglong2 *tw = T.fwd + (size_t)mi * T.n;
     constexpr u32 half = 1u << LOGL;
     u64 *pk = park + (size_t)jid * half;
-    ParkFoldLoader<Job, LOGL> load{ job, m, r, 0, __ldg(tw + 1), pk };
+    const double *twd0 = T.fwd_d + (size_t)mi * T.n;
+    ParkFoldLoader<Job, LOGL> load{ job, m, r, 0, __ldg(tw + 1), (m.big & 4u) ? __ldg(twd0 + 1) : 0.0, pk };
     u32 boff = 0;  // block offset of the half being transformed
     auto fetch = [&](u32 i) { return job.fetch(r, boff + i, m); };
     auto store = [&](u32 i, u64 v, const typename Job::Ops &o) { job.store(r, boff + i, v, m, o); };
@@ -686,6 +830,7 @@ struct Park4FoldLoader {
     const typename Job::R &jr;
     u32 quarter;
     ulonglong2 W1, W2, W3;  // twiddles of the first stage (index 1) and of the second (indices 2, 3)
+    double W1d, W2d, W3d;   // the same as doubles (FP64 policy)
     u64 *park;              // [3][2^LOGL]
     __device__ __forceinline__ Raw raw(u32 i) const
     {
@@ -713,6 +858,71 @@ struct Park4FoldLoader {
         park[2 * Q + i] = c1 + off - T;
         return a2;
     }
+    template <int E, class A, class IdxF>
+    __device__ __forceinline__ void fix_set(const Raw (&raw)[E], typename A::V (&x)[E], IdxF idx, const A &ar) const
+    {
+        constexpr u32 Q = 1u << LOGL;
+        constexpr bool F64 = std::is_same<A, ArF64>::value && Job::F64_LOAD;
+        if (quarter) {
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                if constexpr (F64)
+                    x[k] = __longlong_as_double((long long)raw[k].a);
+                else
+                    x[k] = ar.from_load(raw[k].a);
+            }
+            return;
+        }
+        u64 va[E], vb[E], vc[E], vd[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            va[k] = raw[k].a;
+            vb[k] = raw[k].b;
+            vc[k] = raw[k].c;
+            vd[k] = raw[k].d;
+        }
+        if constexpr (F64) {
+            double a[E], b[E], c[E], d[E];
+            job.template f64_set<E>(jr, va, a, ar);
+            job.template f64_set<E>(jr, vb, b, ar);
+            job.template f64_set<E>(jr, vc, c, ar);
+            job.template f64_set<E>(jr, vd, d, ar);
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                const u32 i = idx(k);
+                double T = ar.mulmod(c[k], W1d);
+                const double a1 = __dadd_rn(a[k], T), c1 = __dadd_rn(a[k], -T);
+                T = ar.mulmod(d[k], W1d);
+                const double b1 = __dadd_rn(b[k], T), d1 = __dadd_rn(b[k], -T);
+                T = ar.mulmod(b1, W2d);
+                park[i] = (u64)__double_as_longlong(__dadd_rn(a1, -T));
+                x[k] = __dadd_rn(a1, T);
+                T = ar.mulmod(d1, W3d);
+                park[Q + i] = (u64)__double_as_longlong(__dadd_rn(c1, T));
+                park[2 * Q + i] = (u64)__double_as_longlong(__dadd_rn(c1, -T));
+            }
+        } else {
+            job.template fix_set<E>(jr, va, m);
+            job.template fix_set<E>(jr, vb, m);
+            job.template fix_set<E>(jr, vc, m);
+            job.template fix_set<E>(jr, vd, m);
+            const u64 off = fold_off(m);
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                const u32 i = idx(k);
+                u64 T = fold_mul(vc[k], W1, m);
+                const u64 a1 = va[k] + T, c1 = va[k] + off - T;
+                T = fold_mul(vd[k], W1, m);
+                const u64 b1 = vb[k] + T, d1 = vb[k] + off - T;
+                T = fold_mul(b1, W2, m);
+                park[i] = a1 + off - T;
+                x[k] = ar.from_load(a1 + T);
+                T = fold_mul(d1, W3, m);
+                park[Q + i] = c1 + T;
+                park[2 * Q + i] = c1 + off - T;
+            }
+        }
+    }
 };
 
 template <int LOGL, int LOGE, class Job>
@@ -726,7 +936,10 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
     const ModConst m = T.mods[mi];
     const ulonglong2 *tw = T.fwd + (size_t)mi * T.n;
     u64 *pk = park + (size_t)jid * (3u << LOGL);
-    Park4FoldLoader<Job, LOGL> load{ job, m, r, 0, __ldg(tw + 1), __ldg(tw + 2), __ldg(tw + 3), pk };
+    const double *twd0 = T.fwd_d + (size_t)mi * T.n;
+    const bool f64 = (m.big & 4u) != 0;
+    Park4FoldLoader<Job, LOGL> load{ job, m, r, 0, __ldg(tw + 1), __ldg(tw + 2), __ldg(tw + 3),
+                                     f64 ? __ldg(twd0 + 1) : 0.0, f64 ? __ldg(twd0 + 2) : 0.0, f64 ? __ldg(twd0 + 3) : 0.0, pk };
     u32 boff = 0;  // block offset of the quarter being transformed
     auto fetch = [&](u32 i) { return job.fetch(r, boff + i, m); };
     auto store = [&](u32 i, u64 v, const typename Job::Ops &o) { job.store(r, boff + i, v, m, o); };

@@ -352,8 +352,7 @@ __device__ __forceinline__ void fwd_full_passes(Load &ld, const typename A::TW *
 #pragma unroll
                 for (int k = 0; k < E; ++k) raw[k] = ld.raw(b + M::off(k));
                 typename A::V x[E];
-#pragma unroll
-                for (int k = 0; k < E; ++k) x[k] = ar.from_load(ld.fix(raw[k], b + M::off(k)));
+                ld.template fix_set<E, A>(raw, x, [&](int k) { return b + M::off(k); }, ar);
                 fwd_stages<LOGE, LOGE, P, LOGL>(x, goff + b, tw, ar);
 #pragma unroll
                 for (int k = 0; k < E; ++k) sm[swz(b + M::off(k))] = x[k];
