@@ -94,21 +94,29 @@ __global__ void __launch_bounds__(256) ks_inner_sum_kernel(const KsParams P, con
     for (u32 b = b0; b < b1; ++b) {
         const size_t o0 = (((size_t)b * 2 + 0) * (L + 1) + i) * n + x, o1 = o0 + (size_t)(L + 1) * n;
         u64 s0 = init ? init[o0] : 0, s1 = init ? init[o1] : 0;
-        for (u32 g = 0; g < P.ngroups; ++g) {
-            const CtView &v = P.in[g];
-            const u32 *pm = P.perm[g];
-            const u32 xp = pm ? __ldg(pm + x) : x;
-            const u32 xs = i < L ? xp : x;
-            if (P.u0) s0 = addmod(s0, P.u0[((((size_t)g * P.B + b) * 2) * (L + 1) + i) * n + xp], m.q);
-            const u64 *key = P.key[g] + (size_t)ki * n + x;
-            const size_t e = (size_t)g * P.B + b;
+        // The products of up to GR groups share one 128-bit sum and ONE Montgomery reduction per component: GR * L products
+        // of canonical residues stay below q * 2^64 while GR * L < 16 (q < 2^60), so the reduced value is canonical after one
+        // conditional subtraction -- the same residue as the sum of the separately reduced group sums (bit-identical), for a
+        // third of the reductions at three groups (they were ~28 % of this kernel's multiplier-pipe work).
+        constexpr u32 GR = 15 / LT;
+        for (u32 g0 = 0; g0 < P.ngroups; g0 += GR) {
             u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+            const u32 g1 = min(P.ngroups, g0 + GR);
+            for (u32 g = g0; g < g1; ++g) {
+                const CtView &v = P.in[g];
+                const u32 *pm = P.perm[g];
+                const u32 xp = pm ? __ldg(pm + x) : x;
+                const u32 xs = i < L ? xp : x;
+                if (P.u0) s0 = addmod(s0, P.u0[((((size_t)g * P.B + b) * 2) * (L + 1) + i) * n + xp], m.q);
+                const u64 *key = P.key[g] + (size_t)ki * n + x;
+                const size_t e = (size_t)g * P.B + b;
 #pragma unroll
-            for (int j = 0; j < LT; ++j) {
-                const u64 d = ((u32)j == i) ? v.p[b * v.sb + P.target_poly * v.sp + j * v.sl + xs]
-                                            : P.ext[((e * L + j) * (L + 1) + i) * n + x];
-                mac128(h0, l0, d, __ldg(key + (size_t)(2 * j) * kstride));      // L1-resident across the batch chunk
-                mac128(h1, l1, d, __ldg(key + (size_t)(2 * j + 1) * kstride));
+                for (int j = 0; j < LT; ++j) {
+                    const u64 d = ((u32)j == i) ? v.p[b * v.sb + P.target_poly * v.sp + j * v.sl + xs]
+                                                : P.ext[((e * L + j) * (L + 1) + i) * n + x];
+                    mac128(h0, l0, d, __ldg(key + (size_t)(2 * j) * kstride));      // L1-resident across the batch chunk
+                    mac128(h1, l1, d, __ldg(key + (size_t)(2 * j + 1) * kstride));
+                }
             }
             s0 = addmod(s0, mont_reduce(h0, l0, m), m.q);
             s1 = addmod(s1, mont_reduce(h1, l1, m), m.q);
