@@ -206,7 +206,7 @@ struct KsLiftJob {
 // INTT of a dropped limb with the rounding offset added: t = (INTT_d(src) + floor(d/2)) mod d.
 // Used by K7 step 4 (d = special prime) and by rescale (d = q_{L-1}).
 struct HalfInttJob {
-    static constexpr bool PIPE = true;
+    static constexpr bool PIPE = false;
     static constexpr bool R_SMEM = false;
     const u64 *src;  // job j at src + (j / inner) * s_outer + (j % inner) * s_inner
     u64 *dst;        // [jobs][N]
