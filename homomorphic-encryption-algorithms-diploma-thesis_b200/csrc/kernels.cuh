@@ -103,10 +103,10 @@ struct PlainJob {
     __device__ __forceinline__ u32 mod(u32 j) const { return first_mod + j % n_mods; }
     __device__ __forceinline__ R resolve(u32 j) const { return R{ src + (size_t)j * n, dst + (size_t)j * n }; }
     __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return r.src[i]; }
-    __device__ __forceinline__ u64 load_fix(const R &, u64 v, const ModConst &) const { return v; }
+    __device__ __forceinline__ u64 load_fix(const R &, u64 v, u32, const ModConst &) const { return v; }
     static constexpr bool F64_LOAD = false;
-    template <int E>
-    __device__ __forceinline__ void fix_set(const R &, u64 (&)[E], const ModConst &) const {}
+    template <int E, class IdxF>
+    __device__ __forceinline__ void fix_set(const R &, u64 (&)[E], IdxF, const ModConst &) const {}
     __device__ __forceinline__ void store(const R &r, u32 i, u64 v, const ModConst &) const { r.dst[i] = v; }
     struct Ops {};
     __device__ __forceinline__ Ops fetch(const R &, u32, const ModConst &) const { return Ops{}; }
@@ -155,7 +155,7 @@ struct KsInttJob {
         return R{ v.p + b * v.sb + P.target_poly * v.sp + l * v.sl, P.hoisted ? nullptr : P.perm[g], P.coef + (size_t)j * P.n };
     }
     __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return __ldcg(r.row + (r.pm ? __ldg(r.pm + i) : i)); }
-    __device__ __forceinline__ u64 load_fix(const R &, u64 v, const ModConst &) const { return v; }
+    __device__ __forceinline__ u64 load_fix(const R &, u64 v, u32, const ModConst &) const { return v; }
     __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &) const { __stcg(r.dst + i, x); }
 };
 
@@ -192,12 +192,12 @@ struct KsLiftJob {
         return R{ P.coef + ((size_t)e * P.L + dj) * P.n, P.ext + (((size_t)e * P.L + dj) * (P.L + 1) + di) * P.n, mods[dj].q };
     }
     __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return __ldcg(r.src + i); }
-    __device__ __forceinline__ u64 load_fix(const R &r, u64 v, const ModConst &m) const { return rebase(v, r.from_q, m); }
+    __device__ __forceinline__ u64 load_fix(const R &r, u64 v, u32, const ModConst &m) const { return rebase(v, r.from_q, m); }
     static constexpr bool F64_LOAD = true;
-    template <int E>
-    __device__ __forceinline__ void fix_set(const R &r, u64 (&v)[E], const ModConst &m) const { rebase_set<E>(v, r.from_q, m); }
-    template <int E>
-    __device__ __forceinline__ void f64_set(const R &r, const u64 (&v)[E], double (&d)[E], const ArF64 &ar) const { rebase_f64_set<E>(v, d, r.from_q, ar); }
+    template <int E, class IdxF>
+    __device__ __forceinline__ void fix_set(const R &r, u64 (&v)[E], IdxF, const ModConst &m) const { rebase_set<E>(v, r.from_q, m); }
+    template <int E, class IdxF>
+    __device__ __forceinline__ void f64_set(const R &r, const u64 (&v)[E], double (&d)[E], IdxF, const ArF64 &ar) const { rebase_f64_set<E>(v, d, r.from_q, ar); }
     struct Ops {};
     __device__ __forceinline__ Ops fetch(const R &, u32, const ModConst &) const { return Ops{}; }
     __device__ __forceinline__ void store(const R &r, u32 i, u64 v, const ModConst &, const Ops &) const { __stcg(r.dst + i, v); }
@@ -220,7 +220,7 @@ struct HalfInttJob {
     __device__ __forceinline__ u32 mod(u32) const { return drop_mod; }
     __device__ __forceinline__ R resolve(u32 j) const { return R{ src + (j / inner) * s_outer + (j % inner) * s_inner, dst + (size_t)j * n }; }
     __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return r.src[i]; }
-    __device__ __forceinline__ u64 load_fix(const R &, u64 v, const ModConst &m) const { return lazy_in ? barrett64(v, m) : v; }
+    __device__ __forceinline__ u64 load_fix(const R &, u64 v, u32, const ModConst &m) const { return lazy_in ? barrett64(v, m) : v; }
     __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &m) const { r.dst[i] = addmod(x, m.q >> 1, m.q); }
 };
 
@@ -284,18 +284,18 @@ struct KsModDownJob {
         return r;
     }
     __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return __ldcg(r.t + i); }
-    __device__ __forceinline__ u64 load_fix(const R &r, u64 v, const ModConst &m) const { return submod(rebase(v, r.from_q, m), r.halfmod, m.q); }
+    __device__ __forceinline__ u64 load_fix(const R &r, u64 v, u32, const ModConst &m) const { return submod(rebase(v, r.from_q, m), r.halfmod, m.q); }
     static constexpr bool F64_LOAD = true;
-    template <int E>
-    __device__ __forceinline__ void fix_set(const R &r, u64 (&v)[E], const ModConst &m) const
+    template <int E, class IdxF>
+    __device__ __forceinline__ void fix_set(const R &r, u64 (&v)[E], IdxF, const ModConst &m) const
     {
         rebase_set<E>(v, r.from_q, m);
         const u64 hm = r.halfmod;
 #pragma unroll
         for (int k = 0; k < E; ++k) v[k] = submod(v[k], hm, m.q);
     }
-    template <int E>
-    __device__ __forceinline__ void f64_set(const R &r, const u64 (&v)[E], double (&d)[E], const ArF64 &ar) const
+    template <int E, class IdxF>
+    __device__ __forceinline__ void f64_set(const R &r, const u64 (&v)[E], double (&d)[E], IdxF, const ArF64 &ar) const
     {
         rebase_f64_set<E>(v, d, r.from_q, ar);
         const double hm = ar.from_load(r.halfmod);
@@ -341,18 +341,18 @@ struct RescaleJob {
                   mods[drop_mod].q, md[l].halfmod, md[l].inv, md[l].inv_sh };
     }
     __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return __ldcg(r.t + i); }
-    __device__ __forceinline__ u64 load_fix(const R &r, u64 v, const ModConst &m) const { return submod(rebase(v, r.from_q, m), r.halfmod, m.q); }
+    __device__ __forceinline__ u64 load_fix(const R &r, u64 v, u32, const ModConst &m) const { return submod(rebase(v, r.from_q, m), r.halfmod, m.q); }
     static constexpr bool F64_LOAD = true;
-    template <int E>
-    __device__ __forceinline__ void fix_set(const R &r, u64 (&v)[E], const ModConst &m) const
+    template <int E, class IdxF>
+    __device__ __forceinline__ void fix_set(const R &r, u64 (&v)[E], IdxF, const ModConst &m) const
     {
         rebase_set<E>(v, r.from_q, m);
         const u64 hm = r.halfmod;
 #pragma unroll
         for (int k = 0; k < E; ++k) v[k] = submod(v[k], hm, m.q);
     }
-    template <int E>
-    __device__ __forceinline__ void f64_set(const R &r, const u64 (&v)[E], double (&d)[E], const ArF64 &ar) const
+    template <int E, class IdxF>
+    __device__ __forceinline__ void f64_set(const R &r, const u64 (&v)[E], double (&d)[E], IdxF, const ArF64 &ar) const
     {
         rebase_f64_set<E>(v, d, r.from_q, ar);
         const double hm = ar.from_load(r.halfmod);
@@ -422,7 +422,7 @@ struct FinalInttJob {
         if (r.base) g = addmod(g, __ldcg(r.base + i), m.q);
         return g;
     }
-    __device__ __forceinline__ u64 load_fix(const R &, u64 v, const ModConst &) const { return v; }
+    __device__ __forceinline__ u64 load_fix(const R &, u64 v, u32, const ModConst &) const { return v; }
     __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &m) const
     {
         const u64 d = submod(rebase(__ldcg(r.t + i), r.from_q, m), r.halfP, m.q);
@@ -465,16 +465,42 @@ struct FinalNttJob {
                   P.out.p + b * P.out.sb + c * P.out.sp + l * P.out.sl, P.mods[P.K - 1].q, P.mods[P.L - 1].q,
                   P.mdP[l].inv, P.mdP[l].inv_sh, P.mdP[l].halfmod, P.mdQ[l].inv, P.mdQ[l].inv_sh, P.mdQ[l].halfmod };
     }
-    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &m) const  // d P^-1 + d2, coefficient form
+    // loader value = d P^-1 + d2 (coefficient form), d = (t mod q) - (floor(P/2) mod q), d2 = (t2 mod q) - (floor(q_last/2) mod q):
+    // load_raw reads t, the fix functions read t2 (all loads of a register set are issued before its arithmetic)
+    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return __ldcg(r.t + i); }
+    __device__ __forceinline__ u64 load_fix(const R &r, u64 v, u32 i, const ModConst &m) const
     {
-        const u64 d = submod(rebase(__ldcg(r.t + i), r.qP, m), r.halfP, m.q);
+        const u64 d = submod(rebase(v, r.qP, m), r.halfP, m.q);
         const u64 d2 = submod(rebase(__ldcg(r.t2 + i), r.qL, m), r.halfQ, m.q);
         return addmod(mul_shoup(d, r.invP, r.invP_sh, m.q), d2, m.q);
     }
-    __device__ __forceinline__ u64 load_fix(const R &, u64 v, const ModConst &) const { return v; }
-    static constexpr bool F64_LOAD = false;
-    template <int E>
-    __device__ __forceinline__ void fix_set(const R &, u64 (&)[E], const ModConst &) const {}
+    static constexpr bool F64_LOAD = true;
+    template <int E, class IdxF>
+    __device__ __forceinline__ void fix_set(const R &r, u64 (&v)[E], IdxF idx, const ModConst &m) const
+    {
+        u64 w[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) w[k] = __ldcg(r.t2 + idx(k));
+        rebase_set<E>(v, r.qP, m);
+        rebase_set<E>(w, r.qL, m);
+        const u64 hp = r.halfP, hq = r.halfQ, ip = r.invP, ips = r.invP_sh;
+#pragma unroll
+        for (int k = 0; k < E; ++k)
+            v[k] = addmod(mul_shoup(submod(v[k], hp, m.q), ip, ips, m.q), submod(w[k], hq, m.q), m.q);
+    }
+    template <int E, class IdxF>
+    __device__ __forceinline__ void f64_set(const R &r, const u64 (&v)[E], double (&d)[E], IdxF idx, const ArF64 &ar) const
+    {
+        u64 w[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) w[k] = __ldcg(r.t2 + idx(k));
+        double d2[E];
+        rebase_f64_set<E>(v, d, r.qP, ar);
+        rebase_f64_set<E>(w, d2, r.qL, ar);
+        const double hp = ar.from_load(r.halfP), hq = ar.from_load(r.halfQ), ip = ar.from_load(r.invP);
+#pragma unroll
+        for (int k = 0; k < E; ++k) d[k] = __dadd_rn(ar.mulmod(__dadd_rn(d[k], -hp), ip), __dadd_rn(d2[k], -hq));
+    }
     struct Ops {
         u64 f, base;
     };
@@ -510,15 +536,15 @@ struct PlainLoader {  // coefficient boff + i of the resolved job
     const typename Job::R &jr;
     u32 boff;
     __device__ __forceinline__ Raw raw(u32 i) const { return job.load_raw(jr, boff + i, m); }
-    __device__ __forceinline__ u64 fix(Raw r, u32) const { return job.load_fix(jr, r, m); }
+    __device__ __forceinline__ u64 fix(Raw r, u32 i) const { return job.load_fix(jr, r, boff + i, m); }
     // a whole register set at once (forward pass 0): idx(k) = coefficient index of element k
     template <int E, class A, class IdxF>
-    __device__ __forceinline__ void fix_set(const Raw (&raw)[E], typename A::V (&x)[E], IdxF, const A &ar) const
+    __device__ __forceinline__ void fix_set(const Raw (&raw)[E], typename A::V (&x)[E], IdxF idx, const A &ar) const
     {
         u64 v[E];
 #pragma unroll
         for (int k = 0; k < E; ++k) v[k] = raw[k];
-        job.template fix_set<E>(jr, v, m);
+        job.template fix_set<E>(jr, v, [&](int k) { return boff + idx(k); }, m);
 #pragma unroll
         for (int k = 0; k < E; ++k) x[k] = ar.from_load(v[k]);
     }
@@ -549,7 +575,7 @@ struct FoldLoader {
     __device__ __forceinline__ Raw raw(u32 i) const { return Pair64{ job.load_raw(jr, i, m), job.load_raw(jr, i + (1u << LOGL), m) }; }
     __device__ __forceinline__ u64 fix(Raw r, u32 i) const
     {
-        const u64 X = job.load_fix(jr, r.x, m), Y = job.load_fix(jr, r.y, m);
+        const u64 X = job.load_fix(jr, r.x, i, m), Y = job.load_fix(jr, r.y, i + (1u << LOGL), m);
         const u64 Tm = fold_mul(Y, W, m);
         const u64 top = X + Tm, bot = X + fold_off(m) - Tm;
         if (park) park[i] = h ? top : bot;
@@ -585,7 +611,7 @@ struct ParkFoldLoader {
     __device__ __forceinline__ u64 fix(Raw r, u32 i) const
     {
         if (half) return r.x;
-        const u64 X = job.load_fix(jr, r.x, m), Y = job.load_fix(jr, r.y, m);
+        const u64 X = job.load_fix(jr, r.x, i, m), Y = job.load_fix(jr, r.y, i + (1u << LOGL), m);
         const u64 Tm = fold_mul(Y, W, m);
         park[i] = X + fold_off(m) - Tm;
         return X + Tm;
@@ -615,8 +641,8 @@ struct ParkFoldLoader {
         }
         if constexpr (F64) {
             double dx[E], dy[E];
-            job.template f64_set<E>(jr, X, dx, ar);
-            job.template f64_set<E>(jr, Y, dy, ar);
+            job.template f64_set<E>(jr, X, dx, idx, ar);
+            job.template f64_set<E>(jr, Y, dy, [&](int k) { return idx(k) + (1u << LOGL); }, ar);
 #pragma unroll
             for (int k = 0; k < E; ++k) {
                 const double Tm = ar.mulmod(dy[k], Wd);
@@ -624,8 +650,8 @@ struct ParkFoldLoader {
                 x[k] = __dadd_rn(dx[k], Tm);
             }
         } else {
-            job.template fix_set<E>(jr, X, m);
-            job.template fix_set<E>(jr, Y, m);
+            job.template fix_set<E>(jr, X, idx, m);
+            job.template fix_set<E>(jr, Y, [&](int k) { return idx(k) + (1u << LOGL); }, m);
             const u64 off = fold_off(m);
 #pragma unroll
             for (int k = 0; k < E; ++k) {
@@ -844,7 +870,7 @@ struct Park4FoldLoader {
     {
         constexpr u32 Q = 1u << LOGL;
         if (quarter) return r.a;
-        const u64 a = job.load_fix(jr, r.a, m), b = job.load_fix(jr, r.b, m), c = job.load_fix(jr, r.c, m), d = job.load_fix(jr, r.d, m);
+        const u64 a = job.load_fix(jr, r.a, i, m), b = job.load_fix(jr, r.b, i + Q, m), c = job.load_fix(jr, r.c, i + 2 * Q, m), d = job.load_fix(jr, r.d, i + 3 * Q, m);
         const u64 off = fold_off(m);
         u64 T = fold_mul(c, W1, m);
         const u64 a1 = a + T, c1 = a + off - T;
@@ -883,10 +909,10 @@ struct Park4FoldLoader {
         }
         if constexpr (F64) {
             double a[E], b[E], c[E], d[E];
-            job.template f64_set<E>(jr, va, a, ar);
-            job.template f64_set<E>(jr, vb, b, ar);
-            job.template f64_set<E>(jr, vc, c, ar);
-            job.template f64_set<E>(jr, vd, d, ar);
+            job.template f64_set<E>(jr, va, a, idx, ar);
+            job.template f64_set<E>(jr, vb, b, [&](int k) { return idx(k) + Q; }, ar);
+            job.template f64_set<E>(jr, vc, c, [&](int k) { return idx(k) + 2 * Q; }, ar);
+            job.template f64_set<E>(jr, vd, d, [&](int k) { return idx(k) + 3 * Q; }, ar);
 #pragma unroll
             for (int k = 0; k < E; ++k) {
                 const u32 i = idx(k);
@@ -902,10 +928,10 @@ struct Park4FoldLoader {
                 park[2 * Q + i] = (u64)__double_as_longlong(__dadd_rn(c1, -T));
             }
         } else {
-            job.template fix_set<E>(jr, va, m);
-            job.template fix_set<E>(jr, vb, m);
-            job.template fix_set<E>(jr, vc, m);
-            job.template fix_set<E>(jr, vd, m);
+            job.template fix_set<E>(jr, va, idx, m);
+            job.template fix_set<E>(jr, vb, [&](int k) { return idx(k) + Q; }, m);
+            job.template fix_set<E>(jr, vc, [&](int k) { return idx(k) + 2 * Q; }, m);
+            job.template fix_set<E>(jr, vd, [&](int k) { return idx(k) + 3 * Q; }, m);
             const u64 off = fold_off(m);
 #pragma unroll
             for (int k = 0; k < E; ++k) {
