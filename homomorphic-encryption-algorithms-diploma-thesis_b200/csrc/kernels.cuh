@@ -715,7 +715,10 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
     const u32 boff = h << LOGL;
     PlainLoader<Job> load{ job, m, r, boff };
     if constexpr (SPLIT == 0) {
-        auto store = [&](u32 i, u64 v) { job.store(r, i, v, m); };
+        auto store = [&](const u32 (&idx)[1 << LOGE], const u64 (&v)[1 << LOGE]) {
+#pragma unroll
+            for (int k = 0; k < (1 << LOGE); ++k) job.store(r, idx[k], v[k], m);
+        };
         if (m.big & 4u)
             ntt_inv_cta<LOGL, LOGE, LOGL - 1>(load, store, T.inv_d + (size_t)mi * T.n, T.n, ArF64(T.modsd[mi]), sm);
         else if (m.big & 2u)
@@ -724,7 +727,10 @@ __global__ void __launch_bounds__(NttShape<LOGL, LOGE>::THREADS, NttShape<LOGL, 
             ntt_inv_cta<LOGL, LOGE, LOGL - 1>(load, store, tw, T.n, ArI64<false>(m, wl), sm);
     } else {
         u64 *dst = scratch + (size_t)jid * T.n + boff;
-        auto store = [&](u32 i, u64 v) { dst[i] = v; };
+        auto store = [&](const u32 (&idx)[1 << LOGE], const u64 (&v)[1 << LOGE]) {
+#pragma unroll
+            for (int k = 0; k < (1 << LOGE); ++k) dst[idx[k]] = v[k];
+        };
         if (m.big & 2u)
             ntt_inv_cta<LOGL, LOGE, -1>(load, store, tw, T.n + boff, ArI64<true>(m, wl), sm);
         else
@@ -798,15 +804,22 @@ __device__ __forceinline__ void inv_park_body(const Job &job, const typename Job
     u32 h = 0;
     // half 0 is transformed and parked; half 1 is transformed and its last-pass registers are combined
     // with the parked half in the final stride-N/2 stage.  One store for both halves: shared code.
-    auto store = [&](u32 i, typename A::V y) {
+    constexpr int E = 1 << LOGE;
+    auto store = [&](const u32 (&idx)[E], typename A::V (&y)[E]) {
         if (h == 0) {
-            pk[i] = y;
+#pragma unroll
+            for (int k = 0; k < E; ++k) pk[idx[k]] = y[k];
             return;
         }
-        typename A::V x = pk[i];
-        ar.template inv_bfly_last<LOGL>(x, y);
-        job.store(r, i, ar.inv_final(x), m);
-        job.store(r, half + i, ar.inv_final(y), m);
+        typename A::V x[E];  // all parked loads first: one L2 latency per register set, not one per element
+#pragma unroll
+        for (int k = 0; k < E; ++k) x[k] = __ldcg(pk + idx[k]);
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            ar.template inv_bfly_last<LOGL>(x[k], y[k]);
+            job.store(r, idx[k], ar.inv_final(x[k]), m);
+            job.store(r, half + idx[k], ar.inv_final(y[k]), m);
+        }
     };
 #pragma unroll 1
     for (h = 0; h < 2; ++h) {
@@ -1009,20 +1022,37 @@ __device__ __forceinline__ void inv_park4_body(const Job &job, const typename Jo
     PlainLoader<Job> load{ job, m, r, 0 };
     u32 h = 0;
     const typename A::TW W2 = __ldg(tw + 2), W3 = __ldg(tw + 3);  // stage LOGL: quarters (0,1) and (2,3)
-    auto store = [&](u32 i, typename A::V y) {
+    constexpr int E = 1 << LOGE;
+    auto store = [&](const u32 (&idx)[E], typename A::V (&y)[E]) {
         if (h < 3) {
-            pk[h * Q + i] = y;
+#pragma unroll
+            for (int k = 0; k < E; ++k) pk[h * Q + idx[k]] = y[k];
             return;
         }
-        typename A::V x0 = pk[i], x1 = pk[Q + i], x2 = pk[2 * Q + i];
-        ar.template inv_bfly<LOGL>(x0, x1, W2);
-        ar.template inv_bfly<LOGL>(x2, y, W3);
-        ar.template inv_bfly_last<LOGL + 1>(x0, x2);
-        ar.template inv_bfly_last<LOGL + 1>(x1, y);
-        job.store(r, i, ar.inv_final(x0), m);
-        job.store(r, Q + i, ar.inv_final(x1), m);
-        job.store(r, 2 * Q + i, ar.inv_final(x2), m);
-        job.store(r, 3 * Q + i, ar.inv_final(y), m);
+        // parked loads of half a register set at a time (three per element: a whole set would not fit the register budget)
+        constexpr int H = E / 2;
+#pragma unroll
+        for (int k0 = 0; k0 < E; k0 += H) {
+            typename A::V x0[H], x1[H], x2[H];
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                x0[k] = __ldcg(pk + idx[k0 + k]);
+                x1[k] = __ldcg(pk + Q + idx[k0 + k]);
+                x2[k] = __ldcg(pk + 2 * Q + idx[k0 + k]);
+            }
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                const u32 i = idx[k0 + k];
+                ar.template inv_bfly<LOGL>(x0[k], x1[k], W2);
+                ar.template inv_bfly<LOGL>(x2[k], y[k0 + k], W3);
+                ar.template inv_bfly_last<LOGL + 1>(x0[k], x2[k]);
+                ar.template inv_bfly_last<LOGL + 1>(x1[k], y[k0 + k]);
+                job.store(r, i, ar.inv_final(x0[k]), m);
+                job.store(r, Q + i, ar.inv_final(x1[k]), m);
+                job.store(r, 2 * Q + i, ar.inv_final(x2[k]), m);
+                job.store(r, 3 * Q + i, ar.inv_final(y[k0 + k]), m);
+            }
+        }
     };
 #pragma unroll 1
     for (h = 0; h < 4; ++h) {

@@ -467,12 +467,18 @@ __device__ __forceinline__ void inv_full_passes(Store &store, const typename A::
             for (int k = 0; k < E; ++k) x[k] = ar.inv_fix(sm[swz(b + M::off(k))]);
             inv_stages<LOGE, LOGE, P, LOGL, LAST_BIT>(x, goff + b, tw, ar);
             if constexpr (PASS == Sh::NFULL - 1) {
+                // the store receives the whole register set: it can issue the loads of everything it combines the set with
+                // (parked halves, epilogue operands) before the arithmetic of the first element
+                u32 idx[E];
 #pragma unroll
-                for (int k = 0; k < E; ++k) {
-                    if constexpr (LAST_BIT >= 0)
-                        store(b + M::off(k), ar.inv_final(x[k]));
-                    else
-                        store(b + M::off(k), x[k]);
+                for (int k = 0; k < E; ++k) idx[k] = b + M::off(k);
+                if constexpr (LAST_BIT >= 0) {
+                    u64 y[E];
+#pragma unroll
+                    for (int k = 0; k < E; ++k) y[k] = ar.inv_final(x[k]);
+                    store(idx, y);
+                } else {
+                    store(idx, x);
                 }
             } else {
 #pragma unroll
@@ -487,7 +493,7 @@ __device__ __forceinline__ void inv_full_passes(Store &store, const typename A::
 }
 
 // One limb polynomial (block), inverse.  LAST_BIT = index of the final stage of the whole
-// transform (logN-1) if this CTA performs it (store receives canonical values), else -1
+// transform (logN-1) if this CTA performs it (store(idx[E], v[E]) receives the canonical values of a register set and their positions), else -1
 // (SPLIT, integer policies only: values leave in [0,2q) (BIG) or [0, 2q*2^LOGL) (!BIG);
 // ntt_inv_final_kernel finishes).  load(i) must return canonical residues.
 template <int LOGL, int LOGE, int LAST_BIT, class A, class Load, class Store>
