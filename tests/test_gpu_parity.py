@@ -158,7 +158,11 @@ def test_transparent_ciphertext_query(hg):
 
 # ------------------------------------------------------------------ rescale / key switching
 @pytest.mark.parametrize("n,bits", [(8192, (60, 40, 40, 60)), (16384, (60, 31, 30, 30, 30, 60)), (4096, (36, 36, 37)),
-                                    (32768, (60, 40, 40, 60))])
+                                    (32768, (60, 40, 40, 60)),
+                                    # loader paths of the fused transforms: 50-bit digits on 30-bit limbs (direct conversion + one FP64
+                                    # reduction), 30-bit digits on 50-bit limbs (integer policy without corrections), SEAL's 4_levels chain;
+                                    # a 59 / 47 / 35-bit mix (every arithmetic policy in one chain); N = 32768 with small primes
+                                    (8192, (50, 30, 30, 50, 50)), (16384, (59, 47, 35, 60)), (32768, (60, 30, 50, 60))])
 def test_rescale_relin_galois_bit_exact(hg, n, bits):
     S = setup(n, bits)
     ctx = make_ctx(hg, S)
@@ -356,7 +360,8 @@ def test_matvec_bsgs_double_hoisted(hg, n, dim, n1, n2):
         ctx.matvec_bsgs(out, X, D, min(n1, 16), n2, hoist=True)
 
 
-@pytest.mark.parametrize("bits,L", [((60, 40, 40, 60), 2), ((60, 40, 40, 40, 60), 4), ((60, 40, 40, 40, 60), 3), ((50, 50, 60), 2), ((40, 60), 1)])
+@pytest.mark.parametrize("bits,L", [((60, 40, 40, 60), 2), ((60, 40, 40, 40, 60), 4), ((60, 40, 40, 40, 60), 3), ((50, 50, 60), 2), ((40, 60), 1),
+                                    ((50, 40, 40, 50, 50), 4), ((59, 47, 41, 60), 3)])
 def test_matvec_double_hoisted_levels(hg, bits, L):
     """Double-hoisted matvec below the top level (the special prime is then NOT the limb after the
     ciphertext's last one), with four digits, with 50-bit primes only (integer policy everywhere) and with
