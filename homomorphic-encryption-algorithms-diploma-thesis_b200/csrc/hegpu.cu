@@ -197,6 +197,7 @@ extern "C" int hegpu_ctx_create(hegpu_ctx **out, uint32_t n, const uint64_t *mod
     if (const char *e = getenv("HEGPU_DH_F64")) c->dh_f64 = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_SWZ")) c->dh_swz = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_STCS")) c->dh_stcs = atoi(e) != 0;
+    if (const char *e = getenv("HEGPU_DH_BK")) c->dh_bk = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_LIMB_MAJOR")) c->limb_major = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_DH_IMMA")) c->dh_imma = atoi(e) != 0;
     if (const char *e = getenv("HEGPU_IMMA_TX")) c->imma_tx = atoi(e) == 16 ? 16 : 8;
@@ -1618,11 +1619,30 @@ static int launch_dh_inner(hegpu_ctx *c, const DhInnerParams &P)
     Q.stream_out = (u32)c->dh_stcs;
     TRY(configure_smem(c, (const void *)kern, smem));
     dim3 grid(P.n / DH_TX * (LT + 1), 1, (P.B + DH_BCH - 1) / DH_BCH);
+    const bool use_bk = P.bk != nullptr && N2 == 4 && P.n2 > (u32)N2;
+    if (!use_bk) Q.bk = nullptr;
+    if constexpr (N2 == 4) {
+        if (use_bk) {
+            TRY(configure_smem(c, (const void *)dh_inner_bk_kernel<LT, N2, 1>, smem));
+            TRY(configure_smem(c, (const void *)dh_inner_bk_kernel<LT, N2, 2>, smem));
+        }
+    }
     for (u32 g0 = 0; g0 < P.n2; g0 += N2) {
         Q.g0 = g0;
         Q.ng = std::min<u32>(N2, P.n2 - g0);
+        Q.bk_mode = !use_bk ? 0u : (g0 == 0 ? 1u : 2u);
         const int swz = (c->dh_swz && LT == 3 && c->sms % 4 == 0) ? (c->sms << 8) : 0;
-        kern<<<grid, DH_TX * DH_KG, smem, c->stream>>>(Q, c->d_mods, c->dh_f64 | swz);
+        bool launched = false;
+        if constexpr (N2 == 4) {
+            if (Q.bk_mode == 1) {
+                dh_inner_bk_kernel<LT, N2, 1><<<grid, DH_TX * DH_KG, smem, c->stream>>>(Q, c->d_mods, c->dh_f64 | swz);
+                launched = true;
+            } else if (Q.bk_mode == 2) {
+                dh_inner_bk_kernel<LT, N2, 2><<<grid, DH_TX * DH_KG, smem, c->stream>>>(Q, c->d_mods, c->dh_f64 | swz);
+                launched = true;
+            }
+        }
+        if (!launched) kern<<<grid, DH_TX * DH_KG, smem, c->stream>>>(Q, c->d_mods, c->dh_f64 | swz);
         c->launches++;
         CU(cudaGetLastError());
     }
@@ -1681,8 +1701,12 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
     const u32 nr1 = std::max<u32>(nrot, 1);
     const bool fused = c->dh_fused && L <= 4 && dh_inner_smem(n1, dh_n2_pad(n2), L) <= (size_t)110 * 1024;
     const size_t nbaby = fused ? 0 : n1;  // the rotated ciphertexts only exist in HBM on the unfused path
+    // fused path with more than 4 giant steps (several launches of dh_inner): the first launch keeps the rotated ciphertexts
+    // b_k (lazy residues, extended basis) so that the later launches read them back instead of redoing the key products
+    const bool keep_bk = fused && c->dh_bk && n2 > 4 && !((imma || c->dh_imma) && L == 3);
+    const size_t bkw = keep_bk ? (size_t)(L + 1) * n1 * 2 * n : 0;  // words per ciphertext
     auto need = [&](u32 Bc) {
-        return align256((size_t)Bc * L * n) + align256((size_t)Bc * L * (L + 1) * n) + align256(inv_scratch_words(c, (size_t)Bc * std::max<u32>(L, 2))) +
+        return align256((size_t)Bc * bkw) + align256((size_t)Bc * L * n) + align256((size_t)Bc * L * (L + 1) * n) + align256(inv_scratch_words(c, (size_t)Bc * std::max<u32>(L, 2))) +
                align256((size_t)nbaby * Bc * accw) + align256((size_t)n2 * Bc * accw) + align256((size_t)nr1 * Bc * ctw) +
                align256((size_t)nr1 * Bc * 2 * n) + align256(inv_scratch_words(c, (size_t)nr1 * Bc * 2)) + align256((size_t)Bc * accw) +
                align256((size_t)Bc * 2 * n) + 2 * align256((size_t)Bc * ctw) + align256((size_t)Bc * L * n) +
@@ -1724,6 +1748,7 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
         select_slot(c, slot);
         ArenaPlan ap{ c };
         ap.off = (size_t)slot * need(Bc);
+        u64 *bk = ap.take((size_t)Bc * bkw);
         u64 *coef = ap.take((size_t)Bc * L * n);
         u64 *ext = ap.take((size_t)Bc * L * (L + 1) * n);
         u64 *scr0 = ap.take(inv_scratch_words(c, (size_t)Bc * std::max<u32>(L, 2)));
@@ -1775,6 +1800,7 @@ static int matvec_bsgs_dh(hegpu_ctx *c, hegpu_ct *out, const hegpu_ct *in, const
             P.diag = dmont;
             P.diag_si = diags->stride();
             P.u = u;
+            P.bk = keep_bk ? bk : nullptr;
             P.n1 = n1;
             P.n2 = n2;
             P.B = Bn;

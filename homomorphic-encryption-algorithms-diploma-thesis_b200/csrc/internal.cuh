@@ -103,6 +103,7 @@ struct hegpu_ctx {
     int imma_tx = 8;   // coefficients per CTA of the integer-MMA kernel: 8 = two CTAs of 8 warps per SM (measured faster), HEGPU_IMMA_TX=16 = one CTA of 16 warps
     u64 key_epoch = 0; // bumped whenever a Galois key is (re)loaded: invalidates pre-multiplied diagonals
     int limb_major = 0;  // HEGPU_LIMB_MAJOR=1: mod-down / final NTT jobs in limb-major order (co-resident CTAs share one arithmetic policy)
+    int dh_bk = 1;     // fused kernel, more than 4 giant steps: keep the rotated ciphertexts b_k of the first launch in HBM for the later ones (HEGPU_DH_BK=0: recompute)
     int dh_stcs = 1;   // fused kernel: evict-first stores of the inner sums (HEGPU_DH_STCS=0: plain stores)
     int dh_swz = 0;    // fused kernel: limb order rotated per wave of CTAs so that co-resident CTAs mix the two policies (HEGPU_DH_SWZ=1)
     int fuse_final = 1;  // double-hoisted matvec: final mod-down and rescale as one pass (HEGPU_FUSE_FINAL=0: two steps)

@@ -380,6 +380,10 @@ struct DhInnerParams {
     u64 *u;                // [n2][B][2][L+1][N]
     u32 n1, n2, B, L, K, n;
     u32 g0, ng;            // this launch accumulates giant steps g0 .. g0+ng-1 (ng <= N2)
+    u64 *bk;               // [B][L+1][n1][2][N] rotated ciphertexts b_k (lazy residues) of this chunk, or null: with more than N2
+                           // giant steps the first launch writes them and the later launches read them back instead of gathering the
+                           // digits and redoing the (n1-1) * 2L key products per launch
+    u32 bk_mode;           // 0: not used, 1: compute and write, 2: read
     u32 stream_out;        // inner sums leave with evict-first stores (st.global.cs): they are > 1 GB per launch, are not read again
                            // by this kernel and would otherwise push the lifted digits that every CTA re-gathers out of L2
 };
@@ -456,7 +460,7 @@ struct DhArF64 {
     static __device__ __forceinline__ u64 reduce_wide(const Acc &a, const ModConst &m) { return csub(reduce(a, 0, m), m.q); }
 };
 
-template <int LT, int N2, class Ar>
+template <int LT, int N2, class Ar, int BK = 0>
 __device__ __forceinline__ void dh_inner_body(const DhInnerParams &P, const ModConst &m, u32 i, u32 x0, u32 b0, u32 b1, u64 *skey, u64 *sdiag,
                                               u32 *sperm)
 {
@@ -464,17 +468,21 @@ __device__ __forceinline__ void dh_inner_body(const DhInnerParams &P, const ModC
     const u32 n = P.n, n1 = P.n1;
     const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const u32 ki = (i == L) ? P.K - 1 : i;
-    for (u32 idx = threadIdx.x; idx < n1 * 2 * L * TX; idx += NT) {
-        const u32 x = idx % TX, r = idx / TX, jc = r % (2 * L), k = r / (2 * L);
-        skey[idx] = k ? Ar::stage(__ldg(P.key[k] + ((size_t)jc * P.K + ki) * n + x0 + x)) : 0;
+    if constexpr (BK != 2) {
+        for (u32 idx = threadIdx.x; idx < n1 * 2 * L * TX; idx += NT) {
+            const u32 x = idx % TX, r = idx / TX, jc = r % (2 * L), k = r / (2 * L);
+            skey[idx] = k ? Ar::stage(__ldg(P.key[k] + ((size_t)jc * P.K + ki) * n + x0 + x)) : 0;
+        }
     }
     for (u32 idx = threadIdx.x; idx < n1 * N2 * TX; idx += NT) {
         const u32 x = idx % TX, r = idx / TX, g = r % N2, k = r / N2;
         sdiag[idx] = g < P.ng ? Ar::stage(__ldg(P.diag + (size_t)((P.g0 + g) * n1 + k) * P.diag_si + (size_t)i * n + x0 + x)) : 0;
     }
-    for (u32 idx = threadIdx.x; idx < n1 * TX; idx += NT) {
-        const u32 x = idx % TX, k = idx / TX;
-        sperm[idx] = k ? __ldg(P.perm[k] + x0 + x) : x0 + x;
+    if constexpr (BK != 2) {
+        for (u32 idx = threadIdx.x; idx < n1 * TX; idx += NT) {
+            const u32 x = idx % TX, k = idx / TX;
+            sperm[idx] = k ? __ldg(P.perm[k] + x0 + x) : x0 + x;
+        }
     }
     __syncthreads();
     const bool data_limb = i < L;
@@ -491,11 +499,18 @@ __device__ __forceinline__ void dh_inner_body(const DhInnerParams &P, const ModC
             for (int j = 0; j < LT; ++j) src[j] = ((u32)j == i) ? cb + P.in.sp + j * P.in.sl : eb + (size_t)j * (L + 1) * n;
             src[LT] = P.c0p + ((size_t)b * L + (data_limb ? i : 0)) * n;  // P * c0, limb i
         }
+        // b_k of this ciphertext and limb: [n1][2][N]
+        u64 *bkp = BK ? P.bk + (((size_t)b * (L + 1) + i) * n1 * 2) * n + x0 + lane : nullptr;
         auto fetch = [&](u32 k, u64 (&d)[LT + 1]) {
-            const u32 xs = sperm[k * TX + lane];
+            if constexpr (BK == 2) {
+                d[0] = __ldcs(bkp + (size_t)(2 * k) * n);
+                d[1] = __ldcs(bkp + (size_t)(2 * k + 1) * n);
+            } else {
+                const u32 xs = sperm[k * TX + lane];
 #pragma unroll
-            for (int j = 0; j < LT; ++j) d[j] = src[j][xs];
-            d[LT] = data_limb ? src[LT][xs] : 0;
+                for (int j = 0; j < LT; ++j) d[j] = src[j][xs];
+                d[LT] = data_limb ? src[LT][xs] : 0;
+            }
         };
         typename Ar::Acc acc[N2][2];
 #pragma unroll
@@ -516,26 +531,44 @@ __device__ __forceinline__ void dh_inner_body(const DhInnerParams &P, const ModC
         // baby step 0: b_0 = P * (c0, c1); component 0 is the gathered (pre-scaled) word itself
         {
             if (2 < n1) fetch(2, d2);
-            u64 w1 = d0[0];
+            if constexpr (BK == 2) {
+                feed(0, Ar::from_word(d0[0]), Ar::from_word(d0[1]));
+            } else {
+                u64 w1 = d0[0];
 #pragma unroll
-            for (int j = 1; j < LT; ++j) w1 = ((u32)j == i) ? d0[j] : w1;
-            typename Ar::Acc s1 = Ar::zero();
-            Ar::mac(s1, Ar::from_word(w1), pm);
-            feed(0, Ar::from_word(d0[LT]), Ar::from_word(Ar::reduce(s1, 0, m)));
+                for (int j = 1; j < LT; ++j) w1 = ((u32)j == i) ? d0[j] : w1;
+                typename Ar::Acc s1 = Ar::zero();
+                Ar::mac(s1, Ar::from_word(w1), pm);
+                const u64 r1 = Ar::reduce(s1, 0, m);
+                if constexpr (BK == 1) {
+                    __stcs(bkp, d0[LT]);
+                    __stcs(bkp + n, r1);
+                }
+                feed(0, Ar::from_word(d0[LT]), Ar::from_word(r1));
+            }
         }
         // baby step k >= 1: start the gathers of step k+2 into `nxt` (GUARD: only if it exists), then consume `cur`
         auto step = [&](auto guard, u32 k, const u64 (&cur)[LT + 1], u64 (&nxt)[LT + 1]) {
             if (!decltype(guard)::value || k + 2 < n1) fetch(k + 2, nxt);
-            typename Ar::Acc s0 = Ar::zero(), s1 = Ar::zero();
-            const u64 *kp = skey + (size_t)k * 2 * L * TX + lane;
+            if constexpr (BK == 2) {
+                feed(k, Ar::from_word(cur[0]), Ar::from_word(cur[1]));
+            } else {
+                typename Ar::Acc s0 = Ar::zero(), s1 = Ar::zero();
+                const u64 *kp = skey + (size_t)k * 2 * L * TX + lane;
 #pragma unroll
-            for (int j = 0; j < LT; ++j) {
-                const typename Ar::Opnd dj = Ar::from_word(cur[j]);
-                Ar::mac(s0, dj, Ar::from_staged(kp[(2 * j) * TX]));
-                Ar::mac(s1, dj, Ar::from_staged(kp[(2 * j + 1) * TX]));
+                for (int j = 0; j < LT; ++j) {
+                    const typename Ar::Opnd dj = Ar::from_word(cur[j]);
+                    Ar::mac(s0, dj, Ar::from_staged(kp[(2 * j) * TX]));
+                    Ar::mac(s1, dj, Ar::from_staged(kp[(2 * j + 1) * TX]));
+                }
+                // b_k[0] = key products + P * pi_k(c0): the pre-scaled word joins the Montgomery reduction
+                const u64 r0 = Ar::reduce(s0, cur[LT], m), r1 = Ar::reduce(s1, 0, m);
+                if constexpr (BK == 1) {
+                    __stcs(bkp + (size_t)(2 * k) * n, r0);
+                    __stcs(bkp + (size_t)(2 * k + 1) * n, r1);
+                }
+                feed(k, Ar::from_word(r0), Ar::from_word(r1));
             }
-            // b_k[0] = key products + P * pi_k(c0): the pre-scaled word joins the Montgomery reduction
-            feed(k, Ar::from_word(Ar::reduce(s0, cur[LT], m)), Ar::from_word(Ar::reduce(s1, 0, m)));
         };
         // the three operand sets rotate by name, not by copying; whole triples run without range checks so that
         // the loop body is one straight block (no register moves where guarded paths would merge)
@@ -567,10 +600,9 @@ __device__ __forceinline__ void dh_inner_body(const DhInnerParams &P, const ModC
     }
 }
 
-template <int LT, int N2>
-__global__ void __launch_bounds__(DH_TX * DH_KG, 2) dh_inner_kernel(const DhInnerParams P, const ModConst *__restrict__ mods, int use_f64)
+template <int LT, int N2, int BK>
+__device__ __forceinline__ void dh_inner_cta(const DhInnerParams &P, const ModConst *__restrict__ mods, int use_f64, u64 *dh_smem)
 {
-    extern __shared__ __align__(16) u64 dh_smem[];
     constexpr u32 TX = DH_TX, L = LT;
     // neighbouring CTAs take different limbs of the same tile: the CTAs that share an SM then mix the
     // integer-pipe policy (60-bit limbs) with the FP64-pipe policy (40-bit limbs)
@@ -589,9 +621,24 @@ __global__ void __launch_bounds__(DH_TX * DH_KG, 2) dh_inner_kernel(const DhInne
     u64 *sdiag = skey + (size_t)P.n1 * 2 * L * TX;                       // [n1][N2][TX]
     u32 *sperm = reinterpret_cast<u32 *>(sdiag + (size_t)P.n1 * N2 * TX);  // [n1][TX]
     if (use_f64 && (m.q >> 40) == 0)
-        dh_inner_body<LT, N2, DhArF64>(P, m, i, x0, b0, b1, skey, sdiag, sperm);
+        dh_inner_body<LT, N2, DhArF64, BK>(P, m, i, x0, b0, b1, skey, sdiag, sperm);
     else
-        dh_inner_body<LT, N2, DhArI64>(P, m, i, x0, b0, b1, skey, sdiag, sperm);
+        dh_inner_body<LT, N2, DhArI64, BK>(P, m, i, x0, b0, b1, skey, sdiag, sperm);
+}
+template <int LT, int N2>
+__global__ void __launch_bounds__(DH_TX * DH_KG, 2) dh_inner_kernel(const DhInnerParams P, const ModConst *__restrict__ mods, int use_f64)
+{
+    extern __shared__ __align__(16) u64 dh_smem[];
+    dh_inner_cta<LT, N2, 0>(P, mods, use_f64, dh_smem);
+}
+// the launches of a matvec with more than N2 giant steps: BK = 1 (first launch) also writes the rotated ciphertexts b_k,
+// BK = 2 (later launches) reads them back instead of gathering digits and redoing the key products.  Kernels of their own:
+// as branches of dh_inner_kernel they cost the single-launch case 3 % (register allocation of the merged kernel).
+template <int LT, int N2, int BK>
+__global__ void __launch_bounds__(DH_TX * DH_KG, 2) dh_inner_bk_kernel(const DhInnerParams P, const ModConst *__restrict__ mods, int use_f64)
+{
+    extern __shared__ __align__(16) u64 dh_smem[];
+    dh_inner_cta<LT, N2, BK>(P, mods, use_f64, dh_smem);
 }
 
 // sum of `terms` ciphertext batches laid out at batch offsets g*B: out = sum_g src_g
