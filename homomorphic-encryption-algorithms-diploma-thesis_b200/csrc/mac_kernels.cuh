@@ -469,11 +469,13 @@ __device__ __forceinline__ void dh_inner_body(const DhInnerParams &P, const ModC
     const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const u32 ki = (i == L) ? P.K - 1 : i;
     if constexpr (BK != 2) {
+#pragma unroll 8
         for (u32 idx = threadIdx.x; idx < n1 * 2 * L * TX; idx += NT) {
             const u32 x = idx % TX, r = idx / TX, jc = r % (2 * L), k = r / (2 * L);
             skey[idx] = k ? Ar::stage(__ldg(P.key[k] + ((size_t)jc * P.K + ki) * n + x0 + x)) : 0;
         }
     }
+#pragma unroll 8
     for (u32 idx = threadIdx.x; idx < n1 * N2 * TX; idx += NT) {
         const u32 x = idx % TX, r = idx / TX, g = r % N2, k = r / N2;
         sdiag[idx] = g < P.ng ? Ar::stage(__ldg(P.diag + (size_t)((P.g0 + g) * n1 + k) * P.diag_si + (size_t)i * n + x0 + x)) : 0;
