@@ -93,6 +93,7 @@ __device__ __forceinline__ void rebase_f64_set(const u64 (&v)[E], double (&d)[E]
 struct PlainJob {
     static constexpr bool PIPE = true;  // software-pipelined first-pass loads (no epilogue operands -> no spills)
     static constexpr bool R_SMEM = false;
+    static constexpr bool INV_OPS = false;  // no epilogue operands on the inverse side
     const u64 *src;
     u64 *dst;
     u32 first_mod, n_mods, n;
@@ -141,6 +142,7 @@ struct KsParams {
 struct KsInttJob {
     static constexpr bool PIPE = true;  // gathered loads of the next register set fly during this set's butterflies
     static constexpr bool R_SMEM = true;
+    static constexpr bool INV_OPS = false;  // no epilogue operands on the inverse side
     KsParams P;
     struct R {
         const u64 *row;  // limb l of the target polynomial
@@ -208,6 +210,7 @@ struct KsLiftJob {
 struct HalfInttJob {
     static constexpr bool PIPE = false;
     static constexpr bool R_SMEM = false;
+    static constexpr bool INV_OPS = false;  // no epilogue operands on the inverse side
     const u64 *src;  // job j at src + (j / inner) * s_outer + (j % inner) * s_inner
     u64 *dst;        // [jobs][N]
     size_t s_outer, s_inner;
@@ -221,6 +224,14 @@ struct HalfInttJob {
     __device__ __forceinline__ R resolve(u32 j) const { return R{ src + (j / inner) * s_outer + (j % inner) * s_inner, dst + (size_t)j * n }; }
     __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return r.src[i]; }
     __device__ __forceinline__ u64 load_fix(const R &, u64 v, u32, const ModConst &m) const { return lazy_in ? barrett64(v, m) : v; }
+    template <int E, class IdxF>
+    __device__ __forceinline__ void fix_set(const R &, u64 (&v)[E], IdxF, const ModConst &m) const
+    {
+        if (lazy_in) {
+#pragma unroll
+            for (int k = 0; k < E; ++k) v[k] = barrett64(v[k], m);
+        }
+    }
     __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &m) const { r.dst[i] = addmod(x, m.q >> 1, m.q); }
 };
 
@@ -416,19 +427,42 @@ struct FinalInttJob {
                   (c ? P.has_base1 : P.has_base0) ? P.base.p + b * P.base.sb + c * P.base.sp + l * P.base.sl : nullptr,
                   P.t + (size_t)j * P.n, P.t2 + (size_t)j * P.n, P.mods[P.K - 1].q, P.mdP[l].inv, P.mdP[l].inv_sh, P.mdP[l].halfmod };
     }
-    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &m) const  // (base + F P^-1)[limb L-1], NTT form
+    // loader value = (base + F P^-1)[limb L-1], NTT form: load_raw reads F, the fix functions read the base
+    __device__ __forceinline__ u64 load_raw(const R &r, u32 i, const ModConst &) const { return __ldcg(r.f + i); }
+    __device__ __forceinline__ u64 load_fix(const R &r, u64 v, u32 i, const ModConst &m) const
     {
-        u64 g = mul_shoup(__ldcg(r.f + i), r.invP, r.invP_sh, m.q);
+        u64 g = mul_shoup(v, r.invP, r.invP_sh, m.q);
         if (r.base) g = addmod(g, __ldcg(r.base + i), m.q);
         return g;
     }
-    __device__ __forceinline__ u64 load_fix(const R &, u64 v, u32, const ModConst &) const { return v; }
-    __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &m) const
+    template <int E, class IdxF>
+    __device__ __forceinline__ void fix_set(const R &r, u64 (&v)[E], IdxF idx, const ModConst &m) const
     {
-        const u64 d = submod(rebase(__ldcg(r.t + i), r.from_q, m), r.halfP, m.q);
+        const u64 ip = r.invP, ips = r.invP_sh;
+        if (r.base) {
+            u64 w[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) w[k] = __ldcg(r.base + idx(k));
+#pragma unroll
+            for (int k = 0; k < E; ++k) v[k] = addmod(mul_shoup(v[k], ip, ips, m.q), w[k], m.q);
+        } else {
+#pragma unroll
+            for (int k = 0; k < E; ++k) v[k] = mul_shoup(v[k], ip, ips, m.q);
+        }
+    }
+    // epilogue operand of position i (fetched for a whole register set before the first element's arithmetic)
+    static constexpr bool INV_OPS = true;
+    struct IOps {
+        u64 t;
+    };
+    __device__ __forceinline__ IOps ifetch(const R &r, u32 i, const ModConst &) const { return IOps{ __ldcg(r.t + i) }; }
+    __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &m, const IOps &o) const
+    {
+        const u64 d = submod(rebase(o.t, r.from_q, m), r.halfP, m.q);
         const u64 v = submod(x, mul_shoup(d, r.invP, r.invP_sh, m.q), m.q);
         __stcg(r.t2 + i, addmod(v, m.q >> 1, m.q));
     }
+    __device__ __forceinline__ void store(const R &r, u32 i, u64 x, const ModConst &m) const { store(r, i, x, m, ifetch(r, i, m)); }
 };
 struct FinalNttJob {
     static constexpr bool PIPE = false;
@@ -811,14 +845,36 @@ __device__ __forceinline__ void inv_park_body(const Job &job, const typename Job
             for (int k = 0; k < E; ++k) pk[idx[k]] = y[k];
             return;
         }
-        typename A::V x[E];  // all parked loads first: one L2 latency per register set, not one per element
+        if constexpr (Job::INV_OPS) {
+            // half a register set at a time: parked partner and the two epilogue operands of every element first
+            constexpr int H = E / 2;
 #pragma unroll
-        for (int k = 0; k < E; ++k) x[k] = __ldcg(pk + idx[k]);
+            for (int k0 = 0; k0 < E; k0 += H) {
+                typename A::V x[H];
+                typename Job::IOps o0[H], o1[H];
 #pragma unroll
-        for (int k = 0; k < E; ++k) {
-            ar.template inv_bfly_last<LOGL>(x[k], y[k]);
-            job.store(r, idx[k], ar.inv_final(x[k]), m);
-            job.store(r, half + idx[k], ar.inv_final(y[k]), m);
+                for (int k = 0; k < H; ++k) {
+                    x[k] = __ldcg(pk + idx[k0 + k]);
+                    o0[k] = job.ifetch(r, idx[k0 + k], m);
+                    o1[k] = job.ifetch(r, half + idx[k0 + k], m);
+                }
+#pragma unroll
+                for (int k = 0; k < H; ++k) {
+                    ar.template inv_bfly_last<LOGL>(x[k], y[k0 + k]);
+                    job.store(r, idx[k0 + k], ar.inv_final(x[k]), m, o0[k]);
+                    job.store(r, half + idx[k0 + k], ar.inv_final(y[k0 + k]), m, o1[k]);
+                }
+            }
+        } else {
+            typename A::V x[E];  // all parked loads first: one L2 latency per register set, not one per element
+#pragma unroll
+            for (int k = 0; k < E; ++k) x[k] = __ldcg(pk + idx[k]);
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                ar.template inv_bfly_last<LOGL>(x[k], y[k]);
+                job.store(r, idx[k], ar.inv_final(x[k]), m);
+                job.store(r, half + idx[k], ar.inv_final(y[k]), m);
+            }
         }
     };
 #pragma unroll 1

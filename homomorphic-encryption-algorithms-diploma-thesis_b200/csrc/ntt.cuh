@@ -548,8 +548,7 @@ __device__ __forceinline__ void ntt_inv_cta(Load load, Store store, const typena
 #pragma unroll
             for (int k = 0; k < E; ++k) raw[k] = load.raw(b + M::off(k));
             typename A::V x[E];
-#pragma unroll
-            for (int k = 0; k < E; ++k) x[k] = ar.from_load(load.fix(raw[k], b + M::off(k)));
+            load.template fix_set<E, A>(raw, x, [&](int k) { return b + M::off(k); }, ar);
             inv_stages<LOGE, S, 0, PHI, LAST_BIT>(x, goff + b, tw, ar);
 #pragma unroll
             for (int k = 0; k < E; ++k) sm[swz(b + M::off(k))] = x[k];
